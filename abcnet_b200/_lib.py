@@ -1,0 +1,112 @@
+"""ctypes binding of ``libabcnet_b200.so`` (the C-ABI declared in ``include/abcnet_b200.h``).
+
+There is no CPU / PyTorch fallback: if the shared library is missing or a call fails, an exception
+is raised. Build the library with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C abcnet_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libabcnet_b200.so")
+
+EXPORTS = (
+    "abc_last_error", "abc_version", "abc_device_ok", "abc_sm_count", "abc_launch_count",
+    "abc_conv3x3_c1", "abc_conv_igemm", "abc_conv_wpack_bytes", "abc_decode_peaks",
+    "abc_loss_partials", "abc_loss_backward",
+)
+
+
+class AbcConvDesc(C.Structure):
+    _fields_ = [
+        ("in_", C.c_void_p), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("in_planes", C.c_int), ("in_plane_off", C.c_int), ("cin", C.c_int),
+        ("wpack", C.c_void_p), ("bias", C.c_void_p),
+        ("cout", C.c_int), ("n_tile", C.c_int), ("ntaps", C.c_int),
+        ("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9),
+        ("act", C.c_int), ("out_mode", C.c_int),
+        ("out", C.c_void_p), ("out_planes", C.c_int), ("out_plane_off", C.c_int),
+        ("out_H", C.c_int), ("out_W", C.c_int),
+        ("out_sy", C.c_int), ("out_oy", C.c_int), ("out_sx", C.c_int), ("out_ox", C.c_int),
+        ("pool_out", C.c_void_p), ("pool_planes", C.c_int), ("pool_plane_off", C.c_int),
+    ]
+
+
+class AbcAtomRec(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("type", C.c_uint8), ("charge", C.c_uint8),
+                ("hs", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class AbcBondRec(C.Structure):
+    _fields_ = [("x", C.c_uint16), ("y", C.c_uint16), ("omega", C.c_uint8), ("type", C.c_uint8),
+                ("pad", C.c_uint16), ("rho", C.c_float)]
+
+
+class AbcDecodeDesc(C.Structure):
+    _fields_ = [
+        ("maps", C.c_void_p * 8), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("c_type", C.c_int), ("c_charge", C.c_int), ("c_hs", C.c_int), ("n_omega", C.c_int), ("n_btype", C.c_int),
+        ("thr", C.c_float), ("omega_mode", C.c_int),
+        ("atoms", C.c_void_p), ("atom_cap", C.c_int),
+        ("bonds", C.c_void_p), ("bond_cap", C.c_int),
+        ("counts", C.c_void_p),
+    ]
+
+
+class AbcLossDesc(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p * 8), ("targets", C.c_void_p * 8), ("tgt_f64", C.c_int),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("c_type", C.c_int), ("c_charge", C.c_int), ("c_hs", C.c_int), ("n_omega", C.c_int), ("n_btype", C.c_int),
+        ("type_weights", C.c_void_p), ("sums", C.c_void_p), ("scale", C.c_void_p),
+        ("dlogits", C.c_void_p * 8),
+    ]
+
+
+assert C.sizeof(AbcAtomRec) == 8 and C.sizeof(AbcBondRec) == 12
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the abcnet_b200 CUDA library has not been built "
+            "(run __graft_entry__.build() or `make -C abcnet_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.abc_last_error.restype = C.c_char_p
+    lib.abc_launch_count.restype = C.c_int64
+    lib.abc_conv_wpack_bytes.restype = C.c_int64
+    lib.abc_conv_wpack_bytes.argtypes = [C.c_int] * 4
+    lib.abc_conv3x3_c1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p]
+    lib.abc_conv_igemm.argtypes = [C.POINTER(AbcConvDesc), C.c_void_p]
+    lib.abc_decode_peaks.argtypes = [C.POINTER(AbcDecodeDesc), C.c_void_p]
+    lib.abc_loss_partials.argtypes = [C.POINTER(AbcLossDesc), C.c_void_p]
+    lib.abc_loss_backward.argtypes = [C.POINTER(AbcLossDesc), C.c_void_p]
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "abcnet_b200") -> None:
+    if rc != 0:
+        msg = lib.abc_last_error()
+        raise RuntimeError(f"{what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+
+def require_device() -> None:
+    if not lib.abc_device_ok():
+        msg = lib.abc_last_error()
+        raise RuntimeError("abcnet_b200 needs an sm_100 (B200) CUDA device and has no CPU fallback: "
+                           + (msg.decode() if msg else ""))
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib.abc_launch_count())

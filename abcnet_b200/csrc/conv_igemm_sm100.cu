@@ -1,0 +1,455 @@
+// Implicit-GEMM convolution for sm_100a: TMA halo tiles -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> fused epilogue.
+//
+// Replaces the cuDNN calls behind nn.Conv2d(3x3, pad 1) / nn.Conv2d(1x1) / nn.ConvTranspose2d(k3, s2) + crop of the
+// reference U-Net (/root/reference/src/unet.py:12-17, :44-55, :66-70), with BatchNorm (eval) folded into the weights,
+// ReLU / LeakyReLU, the 2x2 max-pool of Down (:30) and the channel concatenation of Up (:59) fused into the epilogue.
+//
+// Data layout ("P8"): activations are bf16 [N][C/8][H][W][8]. For one 8-channel plane, consecutive pixels are
+// consecutive 16-byte vectors, which is exactly the SWIZZLE_NONE K-major core-matrix layout of the tcgen05 shared
+// memory descriptor (8 rows x 16 bytes, contiguous). A (TH+2) x (TW+2) halo tile of KP planes is brought in by ONE
+// 4-D TMA box (zero fill outside the image = conv padding) and the nine 3x3 taps are nine descriptors whose start
+// address is shifted by (dy*(TW+2) + dx) * 16 bytes: the activation tile is read from L2 once per K-chunk, not 9 times.
+//
+//   GEMM M = 128 output pixels = 16 rows x 8 columns of one image (8-row core-matrix groups = tile rows, SBO = row pitch)
+//   GEMM N = n_tile output channels (runtime, multiple of 16, <= 256)
+//   GEMM K = 16 channels per MMA (two planes, LBO = plane pitch), KC = min(cin, 64) channels per pipeline stage
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over M tiles, blockIdx.y = N tile):
+//   warp 0 : TMA producer for activation halo tiles (A ring)
+//   warp 3 : bulk-copy producer for packed weight blocks (B ring, or resident when the layer's weights fit in smem)
+//   warp 1 : MMA issuer (one thread), accumulators double-buffered in TMEM
+//   warp 2 : TMEM allocation / release
+//   warps 4-7 : epilogue (tcgen05.ld -> bias + activation -> bf16 P8 / fp32 NCHW stores, optional fused max-pool)
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace abc {
+
+constexpr int kMaxNA = 4;
+constexpr int kMaxNB = 16;
+constexpr uint32_t kHeaderBytes = 2048;
+constexpr uint32_t kSmemBudget = 232448;   // 227 KB opt-in limit per CTA
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+
+struct ConvKParams {
+  int N, H, W, tiles_x, tiles_y, num_m_tiles;
+  int in_plane_off, kp, nkc, ntaps, halo, n_tile, resident_b, na, nb;
+  uint32_t a_stage_bytes, a_plane_bytes, a_row_bytes, b_block_bytes;
+  uint32_t tap_off[9];
+  uint32_t smem_a_off, smem_b_off;
+  const uint8_t* wpack;
+  const float* bias;
+  int cout, act, out_mode;
+  void* out;
+  int out_planes, out_plane_off, out_H, out_W, out_sy, out_oy, out_sx, out_ox;
+  void* pool_out;
+  int pool_planes, pool_plane_off;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  r.z = *reinterpret_cast<uint32_t*>(&c);
+  r.w = *reinterpret_cast<uint32_t*>(&d);
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // barrier slots (8 bytes each)
+  const uint32_t bar_a_full = sbase;                        // [kMaxNA]
+  const uint32_t bar_a_empty = sbase + 8 * kMaxNA;          // [kMaxNA]
+  const uint32_t bar_b_full = sbase + 8 * (2 * kMaxNA);     // [kMaxNB]
+  const uint32_t bar_b_empty = bar_b_full + 8 * kMaxNB;     // [kMaxNB]
+  const uint32_t bar_acc_full = bar_b_empty + 8 * kMaxNB;   // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 16;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
+  float* bias_s = reinterpret_cast<float*>(smem + 1024);    // [256]
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxNA; ++i) {
+      mbar_init(bar_a_full + 8 * i, 1);
+      mbar_init(bar_a_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < kMaxNB; ++i) {
+      mbar_init(bar_b_full + 8 * i, 1);
+      mbar_init(bar_b_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
+  for (int i = threadIdx.x; i < p.n_tile; i += kThreads) bias_s[i] = p.bias[blockIdx.y * p.n_tile + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const uint32_t a_region = sbase + p.smem_a_off;
+  const uint32_t b_region = sbase + p.smem_b_off;
+  const int blocks_per_ntile = p.nkc * p.ntaps;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ A producer (TMA halo tiles)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int ty = rem / p.tiles_x;
+      const int tx = rem - ty * p.tiles_x;
+      const int c0 = (tx * 8 - p.halo) * 8;
+      const int c1 = ty * 16 - p.halo;
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        mbar_wait(bar_a_empty + 8 * stage, phase ^ 1);
+        mbar_arrive_expect_tx(bar_a_full + 8 * stage, p.a_stage_bytes);
+        tma_load_4d(a_region + stage * p.a_stage_bytes, &tmap, bar_a_full + 8 * stage, c0, c1,
+                    p.in_plane_off + kc * p.kp, n);
+        if (++stage == p.na) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ------------------------------------------------------------------ B producer (packed weight blocks)
+    const uint8_t* wsrc = p.wpack + static_cast<size_t>(blockIdx.y) * blocks_per_ntile * p.b_block_bytes;
+    if (p.resident_b) {
+      if (blockIdx.x < p.num_m_tiles) {
+        mbar_arrive_expect_tx(bar_b_full, static_cast<uint32_t>(blocks_per_ntile) * p.b_block_bytes);
+        for (int blk = 0; blk < blocks_per_ntile; ++blk)
+          bulk_load_1d(b_region + blk * p.b_block_bytes, wsrc + static_cast<size_t>(blk) * p.b_block_bytes,
+                       p.b_block_bytes, bar_b_full);
+      }
+    } else {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+        for (int blk = 0; blk < blocks_per_ntile; ++blk) {
+          mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(bar_b_full + 8 * stage, p.b_block_bytes);
+          bulk_load_1d(b_region + stage * p.b_block_bytes, wsrc + static_cast<size_t>(blk) * p.b_block_bytes,
+                       p.b_block_bytes, bar_b_full + 8 * stage);
+          if (++stage == p.nb) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
+    const uint64_t a_hi = umma_desc_hi(p.a_plane_bytes, p.a_row_bytes);   // LBO = plane pitch, SBO = tile-row pitch
+    const uint64_t b_hi = umma_desc_hi(p.n_tile * 16, 128);              // LBO = plane pitch, SBO = 8 rows * 16 B
+    const int ksteps = p.kp >> 1;
+    int a_stage = 0, b_stage = 0, acc = 0;
+    uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+    if (p.resident_b && blockIdx.x < p.num_m_tiles) {
+      mbar_wait(bar_b_full, 0);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+      mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * 256;
+      uint32_t first = 0;
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        mbar_wait(bar_a_full + 8 * a_stage, a_phase);
+        tc_fence_after();
+        const uint32_t a_base = a_region + a_stage * p.a_stage_bytes;
+        for (int t = 0; t < p.ntaps; ++t) {
+          uint32_t b_base;
+          if (p.resident_b) {
+            b_base = b_region + (kc * p.ntaps + t) * p.b_block_bytes;
+          } else {
+            mbar_wait(bar_b_full + 8 * b_stage, b_phase);
+            tc_fence_after();
+            b_base = b_region + b_stage * p.b_block_bytes;
+          }
+          const uint32_t a_tap = a_base + p.tap_off[t];
+          for (int j = 0; j < ksteps; ++j) {
+            umma_bf16(tmem_d, umma_desc(a_hi, a_tap + 2 * j * p.a_plane_bytes),
+                      umma_desc(b_hi, b_base + 2 * j * p.n_tile * 16), idesc, first);
+            first = 1;
+          }
+          if (!p.resident_b) {
+            umma_commit(bar_b_empty + 8 * b_stage);
+            if (++b_stage == p.nb) {
+              b_stage = 0;
+              b_phase ^= 1;
+            }
+          }
+        }
+        umma_commit(bar_a_empty + 8 * a_stage);
+        if (++a_stage == p.na) {
+          a_stage = 0;
+          a_phase ^= 1;
+        }
+      }
+      umma_commit(bar_acc_full + 8 * acc);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp - 4;                 // TMEM lane quarter == warp_id % 4
+    const int m = q * 32 + lane;            // GEMM row = pixel within the 16 x 8 tile
+    const int r = m >> 3, c = m & 7;
+    const int n0 = blockIdx.y * p.n_tile;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img;
+      const int rem = tile - n * tiles_per_img;
+      const int ty = rem / p.tiles_x;
+      const int tx = rem - ty * p.tiles_x;
+      const int y = ty * 16 + r, x = tx * 8 + c;
+      const bool valid = (y < p.H) && (x < p.W);
+      const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
+      for (int col0 = 0; col0 < p.n_tile; col0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr + col0, raw);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[i]) + bias_s[col0 + i], p.act);
+        if (p.out_mode == 0) {
+          const int plane = (n0 + col0) >> 3;
+          if (p.out != nullptr && valid && (n0 + col0) < p.cout) {
+            uint4* o = reinterpret_cast<uint4*>(p.out);
+            const size_t px = (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * p.out_H + oy;
+            o[px * p.out_W + ox] = pack8_bf16(v);
+            if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(p.out_H)) * p.out_W + ox] = pack8_bf16(v + 8);
+          }
+          if (p.pool_out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float t = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+              v[i] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
+            }
+            if (valid && !(c & 1) && !(r & 1) && (n0 + col0) < p.cout) {
+              const int ph = p.H >> 1, pw = p.W >> 1;
+              uint4* o = reinterpret_cast<uint4*>(p.pool_out);
+              const size_t px = (static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * ph + (y >> 1);
+              o[px * pw + (x >> 1)] = pack8_bf16(v);
+              if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = pack8_bf16(v + 8);
+            }
+          }
+        } else {
+          if (valid) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int co = n0 + col0 + i;
+              if (co < p.cout)
+                o[((static_cast<size_t>(n) * p.cout + co) * p.out_H + oy) * p.out_W + ox] = v[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * acc);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+static int conv_kc(int cin) { return cin < 64 ? cin : 64; }
+
+}  // namespace abc
+
+extern "C" int64_t abc_conv_wpack_bytes(int cin, int cout, int ntaps, int n_tile) {
+  if (cin <= 0 || cin % 16 || n_tile < 16 || n_tile > 256 || n_tile % 16 || ntaps < 1 || ntaps > 9 || cout < 1) return -1;
+  const int n_tiles = (cout + n_tile - 1) / n_tile;
+  return static_cast<int64_t>(n_tiles) * n_tile * cin * ntaps * 2;
+}
+
+extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
+  using namespace abc;
+  if (int rc = device_check()) return rc;
+  ABC_REQUIRE(d != nullptr, "abc_conv_igemm: null descriptor");
+  ABC_REQUIRE(d->in && d->wpack && d->bias, "abc_conv_igemm: null input / weights / bias");
+  ABC_REQUIRE(d->out || d->pool_out, "abc_conv_igemm: no output buffer");
+  ABC_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "abc_conv_igemm: bad geometry N=%d H=%d W=%d", d->N, d->H, d->W);
+  ABC_REQUIRE(d->cin >= 16 && d->cin % 16 == 0 && (d->cin <= 64 || d->cin % 64 == 0),
+              "abc_conv_igemm: cin=%d must be 16, 32, 48, 64 or a multiple of 64", d->cin);
+  ABC_REQUIRE(d->in_plane_off >= 0 && d->in_plane_off + d->cin / 8 <= d->in_planes, "abc_conv_igemm: input plane range");
+  ABC_REQUIRE(d->n_tile >= 16 && d->n_tile <= 256 && d->n_tile % 16 == 0, "abc_conv_igemm: n_tile=%d", d->n_tile);
+  ABC_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "abc_conv_igemm: ntaps=%d", d->ntaps);
+  ABC_REQUIRE(d->cout >= 1, "abc_conv_igemm: cout=%d", d->cout);
+  ABC_REQUIRE(d->out_mode == 0 || d->out_mode == 1, "abc_conv_igemm: out_mode=%d", d->out_mode);
+  ABC_REQUIRE((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->wpack) & 15) == 0,
+              "abc_conv_igemm: input / weights must be 16-byte aligned");
+  int halo = 0;
+  for (int t = 0; t < d->ntaps; ++t) {
+    ABC_REQUIRE(d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1,
+                "abc_conv_igemm: tap %d offset out of [-1,1]", t);
+    if (d->tap_dy[t] || d->tap_dx[t]) halo = 1;
+  }
+  if (d->out_mode == 0) {
+    ABC_REQUIRE(d->cout % 8 == 0, "abc_conv_igemm: P8 output needs cout %% 8 == 0 (got %d)", d->cout);
+    if (d->out) ABC_REQUIRE(d->out_plane_off >= 0 && d->out_plane_off + d->cout / 8 <= d->out_planes, "abc_conv_igemm: output plane range");
+  } else {
+    ABC_REQUIRE(d->out != nullptr && d->pool_out == nullptr, "abc_conv_igemm: NCHW mode needs out and no pool_out");
+  }
+  if (d->out) {
+    ABC_REQUIRE(d->out_sy >= 1 && d->out_sx >= 1 && d->out_oy >= 0 && d->out_ox >= 0 &&
+                    (d->H - 1) * d->out_sy + d->out_oy < d->out_H && (d->W - 1) * d->out_sx + d->out_ox < d->out_W,
+                "abc_conv_igemm: output mapping exceeds out_H x out_W");
+  }
+  if (d->pool_out) {
+    ABC_REQUIRE(d->H % 2 == 0 && d->W % 2 == 0, "abc_conv_igemm: fused max-pool needs even H, W");
+    ABC_REQUIRE(d->pool_plane_off >= 0 && d->pool_plane_off + d->cout / 8 <= d->pool_planes, "abc_conv_igemm: pool plane range");
+  }
+
+  ConvKParams p{};
+  p.N = d->N; p.H = d->H; p.W = d->W;
+  p.tiles_x = (d->W + 7) / 8;
+  p.tiles_y = (d->H + 15) / 16;
+  const int64_t m_tiles = static_cast<int64_t>(d->N) * p.tiles_x * p.tiles_y;
+  ABC_REQUIRE(m_tiles < (1ll << 31), "abc_conv_igemm: too many tiles");
+  p.num_m_tiles = static_cast<int>(m_tiles);
+  p.in_plane_off = d->in_plane_off;
+  const int kc = conv_kc(d->cin);
+  p.kp = kc / 8;
+  p.nkc = d->cin / kc;
+  p.ntaps = d->ntaps;
+  p.halo = halo;
+  p.n_tile = d->n_tile;
+  const int rows = 16 + 2 * halo, cols = 8 + 2 * halo;
+  p.a_row_bytes = cols * 16;
+  p.a_plane_bytes = rows * p.a_row_bytes;
+  p.a_stage_bytes = p.kp * p.a_plane_bytes;
+  p.b_block_bytes = static_cast<uint32_t>(d->n_tile) * kc * 2;
+  for (int t = 0; t < d->ntaps; ++t)
+    p.tap_off[t] = static_cast<uint32_t>(((d->tap_dy[t] + halo) * cols + (d->tap_dx[t] + halo)) * 16);
+  const uint32_t a_stage_al = (p.a_stage_bytes + 127u) & ~127u;
+  ABC_REQUIRE(a_stage_al == p.a_stage_bytes, "abc_conv_igemm: internal: A stage not 128-byte multiple");
+  const uint32_t total_b = static_cast<uint32_t>(p.nkc * p.ntaps) * p.b_block_bytes;
+  p.smem_a_off = kHeaderBytes;
+  uint32_t smem_bytes;
+  if (kHeaderBytes + 2 * p.a_stage_bytes + total_b <= kSmemBudget && total_b < (1u << 20)) {
+    p.resident_b = 1;
+    p.nb = 1;
+    int na = static_cast<int>((kSmemBudget - kHeaderBytes - total_b) / p.a_stage_bytes);
+    p.na = na > kMaxNA ? kMaxNA : na;
+    p.smem_b_off = kHeaderBytes + p.na * p.a_stage_bytes;
+    smem_bytes = p.smem_b_off + total_b;
+  } else {
+    p.resident_b = 0;
+    p.na = 3;
+    p.smem_b_off = kHeaderBytes + p.na * p.a_stage_bytes;
+    int nb = static_cast<int>((kSmemBudget - p.smem_b_off) / p.b_block_bytes);
+    p.nb = nb > kMaxNB ? kMaxNB : nb;
+    ABC_REQUIRE(p.nb >= 2, "abc_conv_igemm: n_tile=%d too large for the weight ring", d->n_tile);
+    smem_bytes = p.smem_b_off + p.nb * p.b_block_bytes;
+  }
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // keep 1 CTA / SM: the kernel owns all 512 TMEM columns
+  p.wpack = static_cast<const uint8_t*>(d->wpack);
+  p.bias = d->bias;
+  p.cout = d->cout; p.act = d->act; p.out_mode = d->out_mode;
+  p.out = d->out;
+  p.out_planes = d->out_planes; p.out_plane_off = d->out_plane_off;
+  p.out_H = d->out_H; p.out_W = d->out_W;
+  p.out_sy = d->out_sy; p.out_oy = d->out_oy; p.out_sx = d->out_sx; p.out_ox = d->out_ox;
+  p.pool_out = d->pool_out; p.pool_planes = d->pool_planes; p.pool_plane_off = d->pool_plane_off;
+
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return ABC_ERR_NO_DEVICE;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->W) * 8, static_cast<cuuint64_t>(d->H),
+                              static_cast<cuuint64_t>(d->in_planes), static_cast<cuuint64_t>(d->N)};
+  const cuuint64_t gstride[3] = {static_cast<cuuint64_t>(d->W) * 16, static_cast<cuuint64_t>(d->W) * d->H * 16,
+                                 static_cast<cuuint64_t>(d->W) * d->H * 16 * d->in_planes};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(cols * 8), static_cast<cuuint32_t>(rows),
+                             static_cast<cuuint32_t>(p.kp), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->in), gdim, gstride, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d planes=%d N=%d box=%ux%ux%u)", static_cast<int>(cr),
+              d->W, d->H, d->in_planes, d->N, box[0], box[1], box[2]);
+    return ABC_ERR_CUDA;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    ABC_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    attr_set = true;
+  }
+  const int n_tiles = (d->cout + d->n_tile - 1) / d->n_tile;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int gx = sms / n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > p.num_m_tiles) gx = p.num_m_tiles;
+  dim3 grid(gx, n_tiles, 1);
+  conv_igemm_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
+  return launch_check("conv_igemm_kernel");
+}

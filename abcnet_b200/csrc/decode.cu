@@ -1,0 +1,270 @@
+// Fused heat-map decoder: threshold + 3x3 NMS on the atom / bond centre maps, ordered (row-major) peak compaction,
+// per-peak class arg-max, circular omega NMS + half-circle test, rho / bond-type gather -- one CTA per image.
+//
+// Replaces, bit-exactly, the dense tensor statements and the per-scalar .cpu().item() loop of
+// /root/reference/src/img2smiles.py:62-80, :115-124 and the gather part of :134-182 (see include/abcnet_b200.h).
+// Only the two centre maps are read densely (2 x H x W x 4 B); every other map is touched at peaks only.
+#include "common.cuh"
+
+namespace abc {
+
+constexpr int kDecThreads = 1024;
+constexpr int kDecWarps = kDecThreads / 32;
+
+struct DecParams {
+  const float* maps[8];
+  int N, H, W;
+  int c_type, c_charge, c_hs, n_omega, n_btype;
+  float thr;
+  int omega_mode;
+  AbcAtomRec* atoms;
+  int atom_cap;
+  AbcBondRec* bonds;
+  int bond_cap;
+  int32_t* counts;
+};
+
+// Exclusive block scan of one int per thread (1024 threads). Returns the exclusive prefix; *total = block sum.
+__device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_sums[lane] = winc - w;          // exclusive warp offsets
+    if (lane == 31) warp_sums[32] = winc;
+  }
+  __syncthreads();
+  const int res = warp_sums[warp] + inc - v;
+  *total = warp_sums[32];
+  __syncthreads();
+  return res;
+}
+
+__device__ __forceinline__ bool is_peak(const float* m, int y, int x, int H, int W, float thr) {
+  const float v = m[y * W + x];
+  if (!(v > thr)) return false;
+  const int y0 = y > 0 ? y - 1 : 0, y1 = y < H - 1 ? y + 1 : H - 1;
+  const int x0 = x > 0 ? x - 1 : 0, x1 = x < W - 1 ? x + 1 : W - 1;
+  for (int yy = y0; yy <= y1; ++yy)
+    for (int xx = x0; xx <= x1; ++xx)
+      if (m[yy * W + xx] > v) return false;     // max_pool2d(z) == z  <=>  no neighbour is larger
+  return true;
+}
+
+__device__ __forceinline__ int argmax_gather(const float* base, int C, size_t cstride) {
+  float best = base[0];
+  int bi = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = base[c * cstride];
+    if (v > best) {                               // first maximum wins (torch.argmax)
+      best = v;
+      bi = c;
+    }
+  }
+  return bi;
+}
+
+// Survivor mask of the omega bins of one bond peak, evaluated by a full warp on the n_omega (<= 64) logits in `z`.
+// Bit layout: lo = bins 0..31, hi = bins 32..63.
+__device__ __forceinline__ void omega_survivors(const float* z, int n, float thr, int mode, uint32_t* lo, uint32_t* hi) {
+  const int lane = threadIdx.x & 31;
+  const int h = n >> 1;
+  bool keep[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int w = lane + 32 * k;
+    bool s = false;
+    if (w < n) {
+      const float v = z[w];
+      bool cand;
+      if (mode == 1) {
+        cand = (v != 0.f);
+      } else {
+        const float l = z[w == 0 ? n - 1 : w - 1], r = z[w == n - 1 ? 0 : w + 1];
+        cand = (v > thr) && !(l > v) && !(r > v);
+      }
+      if (cand) {
+        if (w <= h - 2) s = !(v < fmaxf(z[w + h - 1], z[w + h]));
+        else if (w == h - 1) s = !(v < z[w + h - 1] || v < z[0]);
+        else if (w == h) s = !(v <= z[0] || v <= z[n - 1]);
+        else s = !(v <= fmaxf(z[w - h - 1], z[w - h]));
+      }
+    }
+    keep[k] = s;
+  }
+  *lo = __ballot_sync(0xffffffffu, keep[0]);
+  *hi = __ballot_sync(0xffffffffu, keep[1]);
+}
+
+__global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams p) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int HW = p.H * p.W;
+  float* map = reinterpret_cast<float*>(dsm);                                  // [HW]  (later: per-peak offsets)
+  uint16_t* bpix = reinterpret_cast<uint16_t*>(dsm + static_cast<size_t>(HW) * 4);   // [HW] bond peak pixel indices
+  uint8_t* bcnt = reinterpret_cast<uint8_t*>(bpix + HW);                       // [HW] survivors per bond peak
+  __shared__ int warp_sums[33];
+  __shared__ float wz[kDecWarps][64];
+
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (HW + kDecThreads - 1) / kDecThreads;
+  const int p0 = tid * per, p1 = min(p0 + per, HW);
+  const size_t hw = static_cast<size_t>(HW);
+
+  // ------------------------------------------------------------------ atoms
+  const float* za = p.maps[0] + static_cast<size_t>(n) * HW;
+  for (int i = tid; i < HW; i += kDecThreads) map[i] = za[i];
+  __syncthreads();
+  int cnt = 0;
+  for (int i = p0; i < p1; ++i) cnt += is_peak(map, i / p.W, i % p.W, p.H, p.W, p.thr) ? 1 : 0;
+  int total_atoms;
+  int idx = block_exscan(cnt, warp_sums, &total_atoms);
+  if (cnt) {
+    const float* zt = p.maps[1] + static_cast<size_t>(n) * p.c_type * hw;
+    const float* zc = p.maps[2] + static_cast<size_t>(n) * p.c_charge * hw;
+    const float* zh = p.maps[3] + static_cast<size_t>(n) * p.c_hs * hw;
+    for (int i = p0; i < p1; ++i) {
+      const int y = i / p.W, x = i % p.W;
+      if (!is_peak(map, y, x, p.H, p.W, p.thr)) continue;
+      if (idx < p.atom_cap) {
+        AbcAtomRec r;
+        r.x = static_cast<uint16_t>(y);          // reference naming: x = row, y = column (img2smiles.py:178)
+        r.y = static_cast<uint16_t>(x);
+        r.type = static_cast<uint8_t>(argmax_gather(zt + i, p.c_type, hw));
+        r.charge = static_cast<uint8_t>(argmax_gather(zc + i, p.c_charge, hw));
+        r.hs = static_cast<uint8_t>(argmax_gather(zh + i, p.c_hs, hw));
+        r.pad = 0;
+        p.atoms[static_cast<size_t>(n) * p.atom_cap + idx] = r;
+      }
+      ++idx;
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ bond peaks (ordered list in smem)
+  const float* zb = p.maps[4] + static_cast<size_t>(n) * HW;
+  for (int i = tid; i < HW; i += kDecThreads) map[i] = zb[i];
+  __syncthreads();
+  cnt = 0;
+  for (int i = p0; i < p1; ++i) cnt += is_peak(map, i / p.W, i % p.W, p.H, p.W, p.thr) ? 1 : 0;
+  int total_bpeaks;
+  idx = block_exscan(cnt, warp_sums, &total_bpeaks);
+  for (int i = p0; i < p1 && cnt; ++i)
+    if (is_peak(map, i / p.W, i % p.W, p.H, p.W, p.thr)) bpix[idx++] = static_cast<uint16_t>(i);
+  __syncthreads();
+
+  // ------------------------------------------------------------------ pass A: survivors per bond peak
+  const float* zw = p.maps[7] + static_cast<size_t>(n) * p.n_omega * hw;
+  for (int b = warp; b < total_bpeaks; b += kDecWarps) {
+    const int pix = bpix[b];
+    if (lane < p.n_omega) wz[warp][lane] = zw[lane * hw + pix];
+    if (lane + 32 < p.n_omega) wz[warp][lane + 32] = zw[(lane + 32) * hw + pix];
+    __syncwarp();
+    uint32_t lo, hi;
+    omega_survivors(wz[warp], p.n_omega, p.thr, p.omega_mode, &lo, &hi);
+    if (lane == 0) bcnt[b] = static_cast<uint8_t>(__popc(lo) + __popc(hi));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ exclusive offsets over bond peaks
+  int* boff = reinterpret_cast<int*>(map);      // the bond map is no longer needed
+  const int perb = (total_bpeaks + kDecThreads - 1) / kDecThreads;
+  const int b0 = min(tid * perb, total_bpeaks), b1 = min(b0 + perb, total_bpeaks);
+  cnt = 0;
+  for (int b = b0; b < b1; ++b) cnt += bcnt[b];
+  int total_bonds;
+  idx = block_exscan(cnt, warp_sums, &total_bonds);
+  for (int b = b0; b < b1; ++b) {
+    boff[b] = idx;
+    idx += bcnt[b];
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ pass B: emit bond records
+  const float* zr = p.maps[6] + static_cast<size_t>(n) * p.n_omega * hw;
+  const float* zbt = p.maps[5] + static_cast<size_t>(n) * p.n_btype * p.n_omega * hw;
+  for (int b = warp; b < total_bpeaks; b += kDecWarps) {
+    if (bcnt[b] == 0) continue;
+    const int pix = bpix[b];
+    if (lane < p.n_omega) wz[warp][lane] = zw[lane * hw + pix];
+    if (lane + 32 < p.n_omega) wz[warp][lane + 32] = zw[(lane + 32) * hw + pix];
+    __syncwarp();
+    uint32_t lo, hi;
+    omega_survivors(wz[warp], p.n_omega, p.thr, p.omega_mode, &lo, &hi);
+    const int base = boff[b];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t mine = k == 0 ? lo : hi;
+      if ((mine >> lane) & 1u) {
+        const int w = lane + 32 * k;
+        const int rank = __popc(mine & ((1u << lane) - 1u)) + (k == 1 ? __popc(lo) : 0);
+        const int o = base + rank;
+        if (o < p.bond_cap) {
+          AbcBondRec r;
+          r.x = static_cast<uint16_t>(pix / p.W);
+          r.y = static_cast<uint16_t>(pix % p.W);
+          r.omega = static_cast<uint8_t>(w);
+          r.type = static_cast<uint8_t>(argmax_gather(zbt + w * hw + pix, p.n_btype, hw * p.n_omega));
+          r.pad = 0;
+          r.rho = fabsf(zr[w * hw + pix]);
+          p.bonds[static_cast<size_t>(n) * p.bond_cap + o] = r;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (tid == 0) {
+    p.counts[n * 4 + 0] = total_atoms;
+    p.counts[n * 4 + 1] = total_bonds;
+    p.counts[n * 4 + 2] = total_bpeaks;
+    p.counts[n * 4 + 3] = 0;
+  }
+}
+
+}  // namespace abc
+
+extern "C" int abc_decode_peaks(const AbcDecodeDesc* d, void* stream) {
+  using namespace abc;
+  if (int rc = device_check()) return rc;
+  ABC_REQUIRE(d != nullptr, "abc_decode_peaks: null descriptor");
+  for (int i = 0; i < 8; ++i) ABC_REQUIRE(d->maps[i] != nullptr, "abc_decode_peaks: map %d is null", i);
+  ABC_REQUIRE(d->atoms && d->bonds && d->counts, "abc_decode_peaks: null output");
+  ABC_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "abc_decode_peaks: bad geometry");
+  ABC_REQUIRE(static_cast<int64_t>(d->H) * d->W <= 32768 && d->H <= 65535 && d->W <= 65535,
+              "abc_decode_peaks: H*W=%lld exceeds the 32768-pixel per-image limit of the shared-memory decoder",
+              static_cast<long long>(d->H) * d->W);
+  ABC_REQUIRE(d->n_omega >= 4 && d->n_omega <= 64 && d->n_omega % 2 == 0, "abc_decode_peaks: n_omega=%d (even, 4..64)", d->n_omega);
+  ABC_REQUIRE(d->c_type >= 1 && d->c_type <= 255 && d->c_charge >= 1 && d->c_charge <= 255 && d->c_hs >= 1 &&
+                  d->c_hs <= 255 && d->n_btype >= 1 && d->n_btype <= 255,
+              "abc_decode_peaks: class counts out of range");
+  ABC_REQUIRE(d->atom_cap > 0 && d->bond_cap > 0, "abc_decode_peaks: capacities must be positive");
+  ABC_REQUIRE(d->omega_mode == 0 || d->omega_mode == 1, "abc_decode_peaks: omega_mode=%d", d->omega_mode);
+  DecParams p;
+  for (int i = 0; i < 8; ++i) p.maps[i] = d->maps[i];
+  p.N = d->N; p.H = d->H; p.W = d->W;
+  p.c_type = d->c_type; p.c_charge = d->c_charge; p.c_hs = d->c_hs; p.n_omega = d->n_omega; p.n_btype = d->n_btype;
+  p.thr = d->thr; p.omega_mode = d->omega_mode;
+  p.atoms = d->atoms; p.atom_cap = d->atom_cap; p.bonds = d->bonds; p.bond_cap = d->bond_cap; p.counts = d->counts;
+  const size_t smem = static_cast<size_t>(d->H) * d->W * 7;       // 4 B map + 2 B pixel list + 1 B survivor counts
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    ABC_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    smem_set = smem;
+  }
+  decode_kernel<<<d->N, kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return launch_check("decode_kernel");
+}

@@ -1,0 +1,227 @@
+// Fused heat-map / class losses of ABC-Net: one pass for the 8 numerators + 8 denominators, one pass for dL/dlogits.
+//
+// Replaces the ~60 ATen element-wise / reduction kernels (and their autograd twins) of
+// /root/reference/src/train.py:95-137 (= src/multi_gpu_train2.py:140-192 when type_weights == NULL):
+//   clamp(sigmoid|softmax, 1e-5, 1-1e-5), the two centre focal losses, the three atom class losses, the bond-type
+//   loss over view(-1, 6, n_omega, H, W), the rho L1 loss weighted by sum_type(target) and the omega focal loss
+//   weighted per pixel by the sum of its omega targets. Numerators / denominators are accumulated in fp64
+//   (the reference's rho / omega terms are fp64 because of the float64 targets, utils.py:91-92).
+// Bandwidth class: every logit and target is read once per pass, every dlogit written once; one thread per pixel,
+// consecutive threads = consecutive pixels of one NCHW channel plane (coalesced).
+#include "common.cuh"
+
+namespace abc {
+
+constexpr float kLo = 1e-5f, kHi = 1.f - 1e-5f;
+constexpr int kLossThreads = 256;
+constexpr int kMaxC = 16;       // max classes per soft-max group (14 atom types, 6 bond types)
+
+struct LossParams {
+  const float* z[8];
+  const void* t[8];
+  int tgt_f64;
+  int N, HW;
+  int c_type, c_charge, c_hs, n_omega, n_btype;
+  const float* type_w;
+  double* sums;
+  const float* scale;
+  float* dz[8];
+};
+
+__device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + expf(-z)); }
+__device__ __forceinline__ float clampp(float p) { return fminf(fmaxf(p, kLo), kHi); }
+
+// focal centre-style term (train.py:107-108): value and d/dz (without the global scale)
+template <bool BWD>
+__device__ __forceinline__ float focal_sigmoid(float z, float t, float* dzv) {
+  const float ps = sigmoidf(z);
+  const float p = clampp(ps);
+  const float pos = (t == 1.f) ? 1.f : 0.f;
+  const float omt = 1.f - t;
+  const float w4 = omt * omt * omt * omt;
+  const float lp = logf(p), l1p = logf(1.f - p);
+  const float val = -pos * (1.f - p) * (1.f - p) * lp - w4 * p * p * l1p;
+  if (BWD) {
+    const float dldp = pos * (2.f * (1.f - p) * lp - (1.f - p) * (1.f - p) / p) + w4 * (-2.f * p * l1p + p * p / (1.f - p));
+    const float pass = (ps >= kLo && ps <= kHi) ? 1.f : 0.f;
+    *dzv = dldp * pass * ps * (1.f - ps);
+  }
+  return val;
+}
+
+// soft-max focal class loss (train.py:109-114,119) over C channels spaced by `cs` floats; returns numerator,
+// accumulates sum of targets in *tsum; BWD: writes dz (scaled) in place.
+template <bool BWD>
+__device__ __forceinline__ float focal_softmax(const float* z, const float* t, int C, size_t cs, const float* cw,
+                                               float* tsum, float scale, float* dz) {
+  float zv[kMaxC], tv[kMaxC];
+  float mx = -INFINITY;
+  for (int c = 0; c < C; ++c) {
+    zv[c] = z[c * cs];
+    tv[c] = t[c * cs];
+    mx = fmaxf(mx, zv[c]);
+  }
+  float den = 0.f;
+  for (int c = 0; c < C; ++c) {
+    zv[c] = expf(zv[c] - mx);
+    den += zv[c];
+  }
+  const float inv = 1.f / den;
+  float num = 0.f, ts = 0.f, gdot = 0.f;
+  float g[kMaxC];
+  for (int c = 0; c < C; ++c) {
+    const float ps = zv[c] * inv;
+    const float p = clampp(ps);
+    const float w = cw ? cw[c] : 1.f;
+    const float lp = logf(p);
+    num += -w * tv[c] * (1.f - p) * (1.f - p) * lp;
+    ts += tv[c];
+    if (BWD) {
+      const float pass = (ps >= kLo && ps <= kHi) ? 1.f : 0.f;
+      g[c] = -w * tv[c] * (-2.f * (1.f - p) * lp + (1.f - p) * (1.f - p) / p) * pass;
+      gdot += g[c] * ps;
+      zv[c] = ps;
+    }
+  }
+  if (BWD)
+    for (int c = 0; c < C; ++c) dz[c * cs] = scale * zv[c] * (g[c] - gdot);
+  *tsum = ts;
+  return num;
+}
+
+__device__ __forceinline__ float ld_tgt(const void* base, size_t i, int f64) {
+  return f64 ? static_cast<float>(static_cast<const double*>(base)[i]) : static_cast<const float*>(base)[i];
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kLossThreads) loss_kernel(const LossParams p) {
+  const long long gid = static_cast<long long>(blockIdx.x) * kLossThreads + threadIdx.x;
+  const long long total = static_cast<long long>(p.N) * p.HW;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  if (gid < total) {
+    const int n = static_cast<int>(gid / p.HW);
+    const int pix = static_cast<int>(gid - static_cast<long long>(n) * p.HW);
+    const size_t hw = static_cast<size_t>(p.HW);
+    float sc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sc[k] = BWD ? p.scale[k] : 0.f;
+    float d;
+    {   // atom / bond centre maps
+      const size_t o = static_cast<size_t>(n) * hw + pix;
+      const float ta = static_cast<const float*>(p.t[0])[o];
+      acc[ABC_L_ATOM] = focal_sigmoid<BWD>(p.z[0][o], ta, &d);
+      acc[8 + ABC_L_ATOM] = (ta == 1.f) ? 1.f : 0.f;
+      if (BWD) p.dz[0][o] = sc[ABC_L_ATOM] * d;
+      const float tb = static_cast<const float*>(p.t[4])[o];
+      acc[ABC_L_BOND] = focal_sigmoid<BWD>(p.z[4][o], tb, &d);
+      acc[8 + ABC_L_BOND] = (tb == 1.f) ? 1.f : 0.f;
+      if (BWD) p.dz[4][o] = sc[ABC_L_BOND] * d;
+    }
+    {   // atom type / charge / H-count
+      size_t o = (static_cast<size_t>(n) * p.c_type) * hw + pix;
+      acc[ABC_L_TYPE] = focal_softmax<BWD>(p.z[1] + o, static_cast<const float*>(p.t[1]) + o, p.c_type, hw, p.type_w,
+                                           &acc[8 + ABC_L_TYPE], sc[ABC_L_TYPE], BWD ? p.dz[1] + o : nullptr);
+      o = (static_cast<size_t>(n) * p.c_charge) * hw + pix;
+      acc[ABC_L_CHARGE] = focal_softmax<BWD>(p.z[2] + o, static_cast<const float*>(p.t[2]) + o, p.c_charge, hw, nullptr,
+                                             &acc[8 + ABC_L_CHARGE], sc[ABC_L_CHARGE], BWD ? p.dz[2] + o : nullptr);
+      o = (static_cast<size_t>(n) * p.c_hs) * hw + pix;
+      acc[ABC_L_HS] = focal_softmax<BWD>(p.z[3] + o, static_cast<const float*>(p.t[3]) + o, p.c_hs, hw, nullptr,
+                                         &acc[8 + ABC_L_HS], sc[ABC_L_HS], BWD ? p.dz[3] + o : nullptr);
+    }
+    // bond types / rho: per omega bin
+    const size_t obt = (static_cast<size_t>(n) * p.n_btype * p.n_omega) * hw + pix;
+    const size_t ow = (static_cast<size_t>(n) * p.n_omega) * hw + pix;
+    float omega_tsum = 0.f;
+    for (int w = 0; w < p.n_omega; ++w) omega_tsum += ld_tgt(p.t[7], ow + w * hw, p.tgt_f64);
+    for (int w = 0; w < p.n_omega; ++w) {
+      float tsum;
+      acc[ABC_L_BTYPE] += focal_softmax<BWD>(p.z[5] + obt + w * hw, static_cast<const float*>(p.t[5]) + obt + w * hw,
+                                             p.n_btype, hw * p.n_omega, nullptr, &tsum, sc[ABC_L_BTYPE],
+                                             BWD ? p.dz[5] + obt + w * hw : nullptr);
+      acc[8 + ABC_L_BTYPE] += tsum;
+      const float zr = p.z[6][ow + w * hw];
+      const float tr = ld_tgt(p.t[6], ow + w * hw, p.tgt_f64);
+      const float diff = fabsf(zr) - tr;
+      acc[ABC_L_RHO] += fabsf(diff) * tsum;
+      if (BWD) {
+        const float sd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+        const float sz = zr > 0.f ? 1.f : (zr < 0.f ? -1.f : 0.f);
+        p.dz[6][ow + w * hw] = sc[ABC_L_RHO] * sd * sz * tsum;
+      }
+      const float tw = ld_tgt(p.t[7], ow + w * hw, p.tgt_f64);
+      acc[ABC_L_OMEGA] += omega_tsum * focal_sigmoid<BWD>(p.z[7][ow + w * hw], tw, &d);
+      if (BWD) p.dz[7][ow + w * hw] = sc[ABC_L_OMEGA] * omega_tsum * d;
+    }
+    acc[8 + ABC_L_RHO] = acc[8 + ABC_L_BTYPE];
+    acc[8 + ABC_L_OMEGA] = omega_tsum;
+  }
+  if (!BWD) {
+    __shared__ double red[16][kLossThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      double v = static_cast<double>(acc[i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[i][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      double v = 0.0;
+      for (int w = 0; w < kLossThreads / 32; ++w) v += red[threadIdx.x][w];
+      if (v != 0.0) atomicAdd(p.sums + threadIdx.x, v);
+    }
+  }
+}
+
+static int fill(const AbcLossDesc* d, LossParams* p, bool bwd) {
+  ABC_REQUIRE(d != nullptr, "abc_loss: null descriptor");
+  for (int i = 0; i < 8; ++i) {
+    ABC_REQUIRE(d->logits[i] && d->targets[i], "abc_loss: logits / targets %d null", i);
+    if (bwd) ABC_REQUIRE(d->dlogits[i] != nullptr, "abc_loss_backward: dlogits %d null", i);
+    p->z[i] = d->logits[i];
+    p->t[i] = d->targets[i];
+    p->dz[i] = d->dlogits[i];
+  }
+  ABC_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "abc_loss: bad geometry");
+  ABC_REQUIRE(d->c_type <= kMaxC && d->c_charge <= kMaxC && d->c_hs <= kMaxC && d->n_btype <= kMaxC && d->c_type >= 1 &&
+                  d->c_charge >= 1 && d->c_hs >= 1 && d->n_btype >= 1 && d->n_omega >= 1,
+              "abc_loss: class counts must be in [1, %d]", kMaxC);
+  if (bwd) ABC_REQUIRE(d->scale != nullptr, "abc_loss_backward: scale is null");
+  else ABC_REQUIRE(d->sums != nullptr, "abc_loss_partials: sums is null");
+  p->tgt_f64 = d->tgt_f64;
+  p->N = d->N;
+  p->HW = d->H * d->W;
+  p->c_type = d->c_type; p->c_charge = d->c_charge; p->c_hs = d->c_hs; p->n_omega = d->n_omega; p->n_btype = d->n_btype;
+  p->type_w = d->type_weights;
+  p->sums = d->sums;
+  p->scale = d->scale;
+  return ABC_OK;
+}
+
+}  // namespace abc
+
+extern "C" int abc_loss_partials(const AbcLossDesc* d, void* stream) {
+  using namespace abc;
+  if (int rc = device_check()) return rc;
+  LossParams p{};
+  if (int rc = fill(d, &p, false)) return rc;
+  ABC_CUDA(cudaMemsetAsync(p.sums, 0, 16 * sizeof(double), static_cast<cudaStream_t>(stream)));
+  const long long total = static_cast<long long>(p.N) * p.HW;
+  const unsigned blocks = static_cast<unsigned>((total + kLossThreads - 1) / kLossThreads);
+  loss_kernel<false><<<blocks, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return launch_check("loss_kernel<fwd>");
+}
+
+extern "C" int abc_loss_backward(const AbcLossDesc* d, void* stream) {
+  using namespace abc;
+  if (int rc = device_check()) return rc;
+  LossParams p{};
+  if (int rc = fill(d, &p, true)) return rc;
+  const long long total = static_cast<long long>(p.N) * p.HW;
+  const unsigned blocks = static_cast<unsigned>((total + kLossThreads - 1) / kLossThreads);
+  loss_kernel<true><<<blocks, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return launch_check("loss_kernel<bwd>");
+}

@@ -1,0 +1,346 @@
+"""Host-side mirror of the reference model interface, driving the sm_100a kernels through the C-ABI.
+
+Drop-in for ``from unet import UNet`` of the reference (``/root/reference/src/unet.py:77-119``):
+
+    model = UNet(in_channels=1, heads=[1, 14, 3, 2, 1, 360, 60, 60])
+    outs = model(imgs)            # list of len(heads) contiguous fp32 NCHW tensors [B, heads[i], H/4, W/4]
+
+* same constructor signature, same ``state_dict()`` keys / shapes (261 entries for the v2 heads, loadable with or
+  without the ``module.`` prefix written by ``train.py:435``), same ``model.s`` parameter (``unet.py:82``);
+* ``eval()`` forward = BatchNorm folded into the convolutions at (re)load time, bf16 activations in the planar-8
+  layout, fp32 accumulation in TMEM, fp32 logits out;
+* no CPU fallback and no PyTorch/cuDNN compute on this path: every layer is one of the kernels behind
+  ``include/abcnet_b200.h``. A CPU tensor, a missing library or a non-sm_100 device raises.
+
+The parameters live in plain torch containers only so that checkpoints, optimizers and DDP wrappers keep working.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import AbcConvDesc, check, lib
+
+BN_EPS = 1e-5
+_TAPS3 = [(ky - 1, kx - 1, ky, kx) for ky in range(3) for kx in range(3)]          # (dy, dx, ky, kx)
+
+
+def _bn(c):
+    return nn.BatchNorm2d(c)
+
+
+def _conv_bn_pair(cin, cout):
+    """Parameter container with the reference's key names '<prefix>.double_conv.{0,1,3,4}.*' (unet.py:11-18)."""
+    holder = nn.Module()
+    holder.double_conv = nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), _bn(cout), nn.ReLU(inplace=True),
+                                       nn.Conv2d(cout, cout, 3, padding=1), _bn(cout), nn.ReLU(inplace=True))
+    return holder
+
+
+def _down(cin, cout):
+    holder = nn.Module()                                   # keys '<prefix>.maxpool_conv.1.double_conv.*' (unet.py:29-32)
+    holder.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), _conv_bn_pair(cin, cout))
+    return holder
+
+
+def _up(cin, cout):
+    holder = nn.Module()                                   # keys '<prefix>.up.*', '<prefix>.conv.double_conv.*' (unet.py:44-46)
+    holder.up = nn.ConvTranspose2d(cin, cin // 2, kernel_size=3, stride=2)
+    holder.conv = _conv_bn_pair(cin, cout)
+    return holder
+
+
+def _head(cin, cout):
+    holder = nn.Module()                                   # keys 'out_modules.i.{conv1,bn,conv2}.*' (unet.py:66-70)
+    holder.conv1 = nn.Conv2d(cin, cin, 3, padding=1)
+    holder.bn = _bn(cin)
+    holder.conv2 = nn.Conv2d(cin, cout, 1)
+    return holder
+
+
+class _Packed:
+    """Device-resident, kernel-ready form of one convolution: packed bf16 weights + fp32 bias + tap list."""
+
+    def __init__(self, w_taps, bias, taps, n_tile, cout):
+        # w_taps: fp32 [ntaps, cout, cin] (already BN-folded); taps: list of (dy, dx)
+        ntaps, co, cin = w_taps.shape
+        kc = min(cin, 64)
+        n_tiles = (cout + n_tile - 1) // n_tile
+        pad = n_tiles * n_tile - co
+        if pad:
+            w_taps = torch.cat([w_taps, w_taps.new_zeros(ntaps, pad, cin)], 1)
+            bias = torch.cat([bias, bias.new_zeros(pad)])
+        w = w_taps.view(ntaps, n_tiles, n_tile, cin // kc, kc // 8, 8).permute(1, 3, 0, 4, 2, 5)
+        self.w = w.contiguous().to(torch.bfloat16)
+        assert self.w.numel() * 2 == lib.abc_conv_wpack_bytes(cin, cout, ntaps, n_tile)
+        self.bias = bias.contiguous().float()
+        self.taps, self.n_tile, self.cout, self.cin = taps, n_tile, cout, cin
+
+
+def _fold(conv_w, conv_b, bn):
+    """Inference BatchNorm fold: W' = W * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(var + eps) + beta."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    w = conv_w.detach().float() * scale.view(-1, 1, 1, 1)
+    b = (conv_b.detach().float() - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w, b
+
+
+def _default_n_tile(cin, cout):
+    env = os.environ.get(f"ABCNET_NTILE_{cin}x{cout}")
+    if env:
+        return int(env)
+    c16 = (cout + 15) // 16 * 16
+    if c16 <= 128:
+        return c16
+    return 256 if (cout % 256 == 0 and cin >= 128) else 128
+
+
+class UNet(nn.Module):
+    def __init__(self, in_channels, heads=[1, 21, 5, 1, 4, 2], crop_first=True):
+        super().__init__()
+        if in_channels != 1:
+            raise NotImplementedError("abcnet_b200.UNet: only in_channels=1 (binarised images, utils.py:80-81) is built")
+        self.n_channels = in_channels
+        self.heads = list(heads)
+        # torch >= 1.13 floor-divides the negative crop in unet.py:54-55 -> the FIRST row / column is dropped
+        self.crop_first = bool(crop_first)
+        self.s = nn.Parameter(torch.randn(10) / 100)
+        self.inc1 = _conv_bn_pair(in_channels, 16)
+        self.inc2 = _conv_bn_pair(16, 16)
+        self.down1 = _down(16, 32)
+        self.down2 = _down(32, 64)
+        self.inc3 = _conv_bn_pair(64, 64)
+        self.down3 = _down(64, 128)
+        self.down4 = _down(128, 256)
+        self.down5 = _down(256, 512)
+        self.up1 = _up(512, 256)
+        self.up2 = _up(256, 128)
+        self.up3 = _up(128, 128)
+        self.dconv1 = _conv_bn_pair(128, 128)
+        self.dconv2 = _conv_bn_pair(128, 128)
+        self.out_modules = nn.ModuleList([_head(128, h) for h in self.heads])
+        self._packed = None
+        self._packed_key = None
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ checkpoints
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        if any(k.startswith("module.") for k in state_dict):
+            state_dict = OrderedDict((k[7:] if k.startswith("module.") else k, v) for k, v in state_dict.items())
+        self._packed = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    # ------------------------------------------------------------------ weight preparation (cold path)
+    def _dc_layers(self, holder):
+        seq = holder.double_conv
+        return [(seq[0], seq[1]), (seq[3], seq[4])]
+
+    @torch.no_grad()
+    def prepare(self):
+        """Fold BatchNorm (running statistics) and pack every convolution for the kernels. Called lazily by forward."""
+        dev = self.s.device
+        if dev.type != "cuda":
+            raise RuntimeError("abcnet_b200.UNet runs on a CUDA (sm_100) device only; call .cuda() first -- there is no CPU path")
+        P = {}
+
+        def pack3(name, conv, bn):
+            w, b = _fold(conv.weight, conv.bias, bn)
+            cout, cin = w.shape[:2]
+            wt = torch.stack([w[:, :, ky, kx] for (_, _, ky, kx) in _TAPS3])
+            P[name] = _Packed(wt, b, [(dy, dx) for (dy, dx, _, _) in _TAPS3], _default_n_tile(cin, cout), cout)
+
+        # first conv (1 -> 16): direct kernel, fp32 folded weights [16][9]
+        c0, b0 = self.inc1.double_conv[0], self.inc1.double_conv[1]
+        w, b = _fold(c0.weight, c0.bias, b0)
+        P["inc1.0"] = (w.reshape(16, 9).contiguous(), b.contiguous())
+        pack3("inc1.3", self.inc1.double_conv[3], self.inc1.double_conv[4])
+        for name, holder in (("inc2", self.inc2), ("down1", self.down1.maxpool_conv[1]), ("down2", self.down2.maxpool_conv[1]),
+                             ("inc3", self.inc3), ("down3", self.down3.maxpool_conv[1]), ("down4", self.down4.maxpool_conv[1]),
+                             ("down5", self.down5.maxpool_conv[1]), ("up1.conv", self.up1.conv), ("up2.conv", self.up2.conv),
+                             ("up3.conv", self.up3.conv), ("dconv1", self.dconv1), ("dconv2", self.dconv2)):
+            (ca, ba), (cb, bb) = self._dc_layers(holder)
+            pack3(name + ".0", ca, ba)
+            pack3(name + ".3", cb, bb)
+        # up-sampling convolutions: 4 sub-pixel phases each
+        for name, holder in (("up1", self.up1), ("up2", self.up2), ("up3", self.up3)):
+            w = holder.up.weight.detach().float()          # [Cin, Cout, 3, 3]
+            b = holder.up.bias.detach().float()
+            cin, cout = w.shape[:2]
+            for py in (0, 1):
+                for px in (0, 1):
+                    ys = self._phase_taps(py)
+                    xs = self._phase_taps(px)
+                    taps = [(dy, dx) for (ky, dy) in ys for (kx, dx) in xs]
+                    wt = torch.stack([w[:, :, ky, kx].t() for (ky, dy) in ys for (kx, dx) in xs])
+                    P[f"{name}.up.{py}{px}"] = _Packed(wt.contiguous(), b, taps, _default_n_tile(cin, cout), cout)
+        # heads: the eight conv1 share their input -> one GEMM with N = 128 * len(heads); conv2 is a per-head 1x1
+        ws, bs = [], []
+        for om in self.out_modules:
+            w, b = _fold(om.conv1.weight, om.conv1.bias, om.bn)
+            ws.append(w)
+            bs.append(b)
+        w = torch.cat(ws, 0)
+        wt = torch.stack([w[:, :, ky, kx] for (_, _, ky, kx) in _TAPS3])
+        nt = int(os.environ.get("ABCNET_NTILE_HEADS", "128"))
+        P["heads.conv1"] = _Packed(wt, torch.cat(bs), [(dy, dx) for (dy, dx, _, _) in _TAPS3], nt, w.shape[0])
+        for i, om in enumerate(self.out_modules):
+            w2 = om.conv2.weight.detach().float().reshape(om.conv2.weight.shape[0], -1)
+            h = w2.shape[0]
+            n_tile = 16 if h <= 16 else (64 if h <= 64 else 128)
+            P[f"heads.{i}.conv2"] = _Packed(w2.unsqueeze(0).contiguous(), om.conv2.bias.detach().float(), [(0, 0)], n_tile, h)
+        self._packed = P
+        self._packed_key = self._param_key()
+        return self
+
+    def _phase_taps(self, parity):
+        """(kernel index, input offset) pairs of one output parity of ConvTranspose2d(k=3, s=2) + crop."""
+        if self.crop_first:      # kept[y] = U[y + 1]
+            return [(1, 0)] if parity == 0 else [(0, 1), (2, 0)]
+        return [(0, 0), (2, -1)] if parity == 0 else [(1, 0)]   # kept[y] = U[y]
+
+    # ------------------------------------------------------------------ launch helpers
+    def _buf(self, key, shape):
+        t = self._bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != self.s.device:
+            t = torch.empty(shape, dtype=torch.bfloat16, device=self.s.device)
+            self._bufs[key] = t
+        return t
+
+    @staticmethod
+    def _conv(pk, src, in_plane_off, dst, out_plane_off=0, act=1, pool=None, pool_plane_off=0, out_mode=0,
+              out_scale=(1, 0, 1, 0), stream=0):
+        d = AbcConvDesc()
+        N, in_planes, H, W, _ = src.shape
+        d.in_, d.N, d.H, d.W = src.data_ptr(), N, H, W
+        d.in_planes, d.in_plane_off, d.cin = in_planes, in_plane_off, pk.cin
+        d.wpack, d.bias = pk.w.data_ptr(), pk.bias.data_ptr()
+        d.cout, d.n_tile, d.ntaps = pk.cout, pk.n_tile, len(pk.taps)
+        for i, (dy, dx) in enumerate(pk.taps):
+            d.tap_dy[i], d.tap_dx[i] = dy, dx
+        d.act, d.out_mode = act, out_mode
+        sy, oy, sx, ox = out_scale
+        d.out_sy, d.out_oy, d.out_sx, d.out_ox = sy, oy, sx, ox
+        if dst is not None:
+            d.out = dst.data_ptr()
+            if out_mode == 0:
+                d.out_planes, d.out_H, d.out_W = dst.shape[1], dst.shape[2], dst.shape[3]
+            else:
+                d.out_planes, d.out_H, d.out_W = 0, dst.shape[2], dst.shape[3]
+            d.out_plane_off = out_plane_off
+        else:
+            d.out, d.out_H, d.out_W = None, H, W
+        if pool is not None:
+            d.pool_out, d.pool_planes, d.pool_plane_off = pool.data_ptr(), pool.shape[1], pool_plane_off
+        check(lib.abc_conv_igemm(C.byref(d), stream), "abc_conv_igemm")
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError(
+                "abcnet_b200.UNet: the training-mode forward (batch-statistics BatchNorm, dropout, backward) is not built "
+                "in this round; call .eval() -- there is deliberately no PyTorch fallback")
+        return self.infer(x)
+
+    @torch.no_grad()
+    def trunk_and_hidden(self, x):
+        """Runs everything up to the fused head conv1; returns (trunk P8, hidden P8) for tests / fused decode."""
+        if not x.is_cuda:
+            raise RuntimeError("abcnet_b200.UNet.forward needs a CUDA tensor (no CPU fallback)")
+        _lib.require_device()
+        if x.dim() != 4 or x.shape[1] != 1 or x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError(f"expected [B,1,H,W] with H, W multiples of 32, got {tuple(x.shape)}")
+        if self._packed is None or self._packed_key != self._param_key():
+            self.prepare()
+        P = self._packed
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        st = _lib.current_stream_ptr()
+        cv = lambda *a, **k: self._conv(*a, stream=st, **k)   # noqa: E731
+
+        a = self._buf("a", (B, 2, H, W, 8))
+        b = self._buf("b", (B, 2, H, W, 8))
+        w0, b0 = P["inc1.0"]
+        check(lib.abc_conv3x3_c1(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), a.data_ptr(), B, H, W, 2, 0, st), "abc_conv3x3_c1")
+        cv(P["inc1.3"], a, 0, b)
+        cv(P["inc2.0"], b, 0, a)
+        p1 = self._buf("p1", (B, 2, H // 2, W // 2, 8))
+        cv(P["inc2.3"], a, 0, None, pool=p1)                                   # x1 is never used as a skip
+        d1 = self._buf("d1", (B, 4, H // 2, W // 2, 8))
+        cv(P["down1.0"], p1, 0, d1)
+        p2 = self._buf("p2", (B, 4, H // 4, W // 4, 8))
+        cv(P["down1.3"], d1, 0, None, pool=p2)                                 # x2 neither
+        e1 = self._buf("e1", (B, 8, H // 4, W // 4, 8))
+        e2 = self._buf("e2", (B, 8, H // 4, W // 4, 8))
+        cat3 = self._buf("cat3", (B, 16, H // 4, W // 4, 8))
+        cv(P["down2.0"], p2, 0, e1)
+        cv(P["down2.3"], e1, 0, e2)
+        cv(P["inc3.0"], e2, 0, e1)
+        p3 = self._buf("p3", (B, 8, H // 8, W // 8, 8))
+        cv(P["inc3.3"], e1, 0, cat3, out_plane_off=0, pool=p3)                 # x3 -> concat slot [0, 64)
+        f1 = self._buf("f1", (B, 16, H // 8, W // 8, 8))
+        cat2 = self._buf("cat2", (B, 32, H // 8, W // 8, 8))
+        p4 = self._buf("p4", (B, 16, H // 16, W // 16, 8))
+        cv(P["down3.0"], p3, 0, f1)
+        cv(P["down3.3"], f1, 0, cat2, out_plane_off=0, pool=p4)                # x4
+        g1 = self._buf("g1", (B, 32, H // 16, W // 16, 8))
+        cat1 = self._buf("cat1", (B, 64, H // 16, W // 16, 8))
+        p5 = self._buf("p5", (B, 32, H // 32, W // 32, 8))
+        cv(P["down4.0"], p4, 0, g1)
+        cv(P["down4.3"], g1, 0, cat1, out_plane_off=0, pool=p5)                # x5
+        h1 = self._buf("h1", (B, 64, H // 32, W // 32, 8))
+        h2 = self._buf("h2", (B, 64, H // 32, W // 32, 8))
+        cv(P["down5.0"], p5, 0, h1)
+        cv(P["down5.3"], h1, 0, h2)                                            # x6
+
+        def up(name, src, cat, half_planes):
+            for py in (0, 1):
+                for px in (0, 1):
+                    cv(P[f"{name}.up.{py}{px}"], src, 0, cat, out_plane_off=half_planes, act=0, out_scale=(2, py, 2, px))
+
+        up("up1", h2, cat1, 32)
+        i1 = self._buf("i1", (B, 32, H // 16, W // 16, 8))
+        i2 = self._buf("i2", (B, 32, H // 16, W // 16, 8))
+        cv(P["up1.conv.0"], cat1, 0, i1)
+        cv(P["up1.conv.3"], i1, 0, i2)
+        up("up2", i2, cat2, 16)
+        j1 = self._buf("j1", (B, 16, H // 8, W // 8, 8))
+        j2 = self._buf("j2", (B, 16, H // 8, W // 8, 8))
+        cv(P["up2.conv.0"], cat2, 0, j1)
+        cv(P["up2.conv.3"], j1, 0, j2)
+        up("up3", j2, cat3, 8)
+        k1 = self._buf("k1", (B, 16, H // 4, W // 4, 8))
+        k2 = self._buf("k2", (B, 16, H // 4, W // 4, 8))
+        cv(P["up3.conv.0"], cat3, 0, k1)
+        cv(P["up3.conv.3"], k1, 0, k2)
+        cv(P["dconv1.0"], k2, 0, k1)
+        cv(P["dconv1.3"], k1, 0, k2)
+        cv(P["dconv2.0"], k2, 0, k1)
+        cv(P["dconv2.3"], k1, 0, k2)                                           # trunk
+        hid = self._buf("hid", (B, 16 * len(self.heads), H // 4, W // 4, 8))
+        cv(P["heads.conv1"], k2, 0, hid, act=2)                                # BN fold + LeakyReLU(0.01); Dropout is identity in eval
+        return k2, hid
+
+    @torch.no_grad()
+    def infer(self, x, outs=None):
+        _, hid = self.trunk_and_hidden(x)
+        B, _, H4, W4, _ = hid.shape
+        st = _lib.current_stream_ptr()
+        if outs is None:
+            outs = [torch.empty((B, h, H4, W4), dtype=torch.float32, device=hid.device) for h in self.heads]
+        for i, _h in enumerate(self.heads):
+            self._conv(self._packed[f"heads.{i}.conv2"], hid, 16 * i, outs[i], act=0, out_mode=1, stream=st)
+        return outs
+
+    def activation(self, name):
+        """Debug / test access to an internal P8 buffer as an NCHW fp32 tensor."""
+        t = self._bufs[name]
+        N, P_, H, W, _ = t.shape
+        return t.float().permute(0, 1, 4, 2, 3).reshape(N, P_ * 8, H, W)

@@ -1,0 +1,171 @@
+/*
+ * abcnet_b200 -- C-ABI of the B200-native ABC-Net hot path (U-Net pass + heat-map decoding + losses).
+ *
+ * The reference (zhang-xuan1314/ABC-Net) has no FFI / plugin API of its own: every GPU instruction it
+ * executes is issued by PyTorch library kernels. Each entry point below therefore
+ * replaces a *call site* of the reference, cited as file:line relative to /root/reference.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in the signatures: device pointers are void*, the CUDA stream is a
+ *     void* holding a cudaStream_t (NULL = legacy default stream);
+ *   - every function returns 0 on success or a negative AbcStatus; abc_last_error() gives a thread-local
+ *     message. Nothing throws across the ABI. Nothing allocates device memory: the caller owns all buffers;
+ *   - there is NO CPU fallback: without a CUDA device of compute capability 10.x the compute entry points
+ *     return ABC_ERR_NO_DEVICE.
+ *
+ * Activation layout "P8" (planar-8, a.k.a. NC/8HWC8): bf16 tensor [N][C/8][H][W][8]. Channel c lives in
+ * plane c/8, slot c%8. A concatenation along channels is a plane offset into a wider buffer, so the
+ * reference's F.pad + torch.cat (src/unet.py:51-59) cost nothing.
+ */
+#ifndef ABCNET_B200_H_
+#define ABCNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABC_API __attribute__((visibility("default")))
+
+typedef enum AbcStatus {
+  ABC_OK = 0,
+  ABC_ERR_INVALID = -1,    /* bad argument (shape / alignment / range) */
+  ABC_ERR_NO_DEVICE = -2,  /* no sm_100 device, or driver entry point missing */
+  ABC_ERR_CUDA = -3,       /* a CUDA call failed; see abc_last_error() */
+  ABC_ERR_CAPACITY = -4    /* caller-provided capacity too small (decode); counts still valid */
+} AbcStatus;
+
+ABC_API const char* abc_last_error(void);
+ABC_API int abc_version(void);
+/* 1 if the current device can run the kernels (compute capability 10.x), else 0. */
+ABC_API int abc_device_ok(void);
+/* Number of SMs of the current device (grid sizing), or a negative status. */
+ABC_API int abc_sm_count(void);
+/* Kernels launched by this library in the calling process so far (bench.py's gpu_launches). */
+ABC_API int64_t abc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * First convolution: 1 -> 16 channels, 3x3, pad 1, BatchNorm folded, ReLU.
+ * Replaces nn.Conv2d + BatchNorm2d + ReLU of inc1 (src/unet.py:12-14 via :83,:101) for in_channels = 1.
+ *   img   fp32 [N][1][H][W] (values {0,1}: src/utils.py:80-81, src/utils_for_test.py:22-27)
+ *   w     fp32 [16][9] folded weights, b fp32 [16] folded bias
+ *   out   P8 bf16 [N][out_planes][H][W][8], channels written to planes [out_plane_off, out_plane_off+2)
+ */
+ABC_API int abc_conv3x3_c1(const float* img, const float* w, const float* b, void* out, int N, int H, int W,
+                           int out_planes, int out_plane_off, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 in TMEM).
+ * One kernel covers: 3x3 pad-1 convolutions (src/unet.py:12,15,66), the 1x1 head convolutions (:70), and,
+ * phase by phase, the stride-2 transposed convolution followed by the crop of Up.forward (:44,:49-55).
+ *
+ * GEMM view: M = output pixels (tiles of 16 rows x 8 columns of one image), N = output channels
+ * (tiles of n_tile), K = cin * ntaps. For every tap t the input pixel of output grid position (y, x) is
+ * (y + tap_dy[t], x + tap_dx[t]); out-of-image pixels read as zero.
+ *
+ * Packed weights: bf16 [n_tiles][cin/kc][ntaps][kc/8][n_tile][8] with kc = min(cin, 64); element
+ * (nt, c, t, p, r, e) multiplies input channel c*kc + p*8 + e and produces output channel nt*n_tile + r
+ * (rows past cout are zero). bias: fp32 [n_tiles*n_tile].
+ */
+typedef struct AbcConvDesc {
+  const void* in;        /* P8 bf16 [N][in_planes][H][W][8] */
+  int N, H, W;           /* input grid */
+  int in_planes;         /* planes of the input buffer */
+  int in_plane_off;      /* first plane read */
+  int cin;               /* channels read: multiple of 16 */
+  const void* wpack;     /* packed weights (see above), 16-byte aligned */
+  const float* bias;
+  int cout;              /* valid output channels */
+  int n_tile;            /* multiple of 16, 16..256 */
+  int ntaps;             /* 1..9 */
+  int tap_dy[9];
+  int tap_dx[9];         /* each in [-1, 1] */
+  int act;               /* 0 none, 1 ReLU, 2 LeakyReLU(0.01) */
+  int out_mode;          /* 0: P8 bf16, 1: NCHW fp32 [N][cout][out_H][out_W] */
+  void* out;             /* may be NULL when only the pooled output is wanted */
+  int out_planes;        /* P8: planes of the output buffer */
+  int out_plane_off;     /* P8: first plane written (concat slot) */
+  int out_H, out_W;      /* output grid; output pixel = (y*out_sy + out_oy, x*out_sx + out_ox) */
+  int out_sy, out_oy, out_sx, out_ox;
+  void* pool_out;        /* optional fused MaxPool2d(2) (src/unet.py:30): P8 bf16 [N][pool_planes][H/2][W/2][8] */
+  int pool_planes, pool_plane_off;
+} AbcConvDesc;
+
+ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);
+/* Bytes of packed weights for a layer (host-side helper for allocation). */
+ABC_API int64_t abc_conv_wpack_bytes(int cin, int cout, int ntaps, int n_tile);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Heat-map decoding: threshold + 3x3 NMS on the atom / bond centre maps, ordered peak compaction, per-peak
+ * class / offset gather. Replaces src/img2smiles.py:62-80 (dense NMS / omega NMS), :115-124 (dense argmax
+ * maps) and the gather part of :134-182 (one .cpu().item() sync per scalar in the reference).
+ *
+ * Inputs are the 8 head outputs as the reference returns them: fp32 NCHW, contiguous
+ *   0 atom centre [N,1,H,W]   1 atom type [N,c_type,H,W]  2 charge [N,c_charge,H,W]  3 H-count [N,c_hs,H,W]
+ *   4 bond centre [N,1,H,W]   5 bond type [N,n_btype*n_omega,H,W] (channel = type*n_omega + omega)
+ *   6 rho [N,n_omega,H,W]     7 omega [N,n_omega,H,W]
+ * Outputs (caller allocated):
+ *   atoms  AbcAtomRec[N][atom_cap]  every atom-centre peak in row-major order (x = row, y = column);
+ *                                   the greedy < 2 px de-duplication of :183-187 is left to the caller
+ *   bonds  AbcBondRec[N][bond_cap]  every surviving (bond peak, omega) pair in the reference's
+ *                                   enumeration order (row-major peaks, ascending omega, :134-171)
+ *   counts int32[N][4] = (atom peaks, bond records, bond-centre peaks, 0); when a count exceeds its
+ *          capacity the list is truncated and ABC_ERR_CAPACITY is NOT raised here (no sync) -- the caller
+ *          compares counts with capacities after its D2H copy.
+ * omega_mode 0: candidates = circular 3-tap NMS & (z > thr) (img2smiles.py:74-80, img2smiles3.py)
+ *            1: candidates = every omega whose logit != 0 (img2smiles2.py:139)
+ * thr is the logit threshold (-1 in the reference, img2smiles.py:64).
+ */
+typedef struct AbcAtomRec {
+  uint16_t x, y;
+  uint8_t type, charge, hs, pad;
+} AbcAtomRec;
+typedef struct AbcBondRec {
+  uint16_t x, y;
+  uint8_t omega, type;
+  uint16_t pad;
+  float rho;               /* |z_rho| (img2smiles.py:70) */
+} AbcBondRec;
+typedef struct AbcDecodeDesc {
+  const float* maps[8];
+  int N, H, W;
+  int c_type, c_charge, c_hs, n_omega, n_btype;
+  float thr;
+  int omega_mode;
+  AbcAtomRec* atoms;
+  int atom_cap;
+  AbcBondRec* bonds;
+  int bond_cap;
+  int32_t* counts;
+} AbcDecodeDesc;
+ABC_API int abc_decode_peaks(const AbcDecodeDesc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused training losses, forward + backward in one pass. Replaces the ~60 ATen kernels (+ autograd) of
+ * src/train.py:95-137 (= src/multi_gpu_train2.py:140-192 with class_weights = 0).
+ * Pass 1 (abc_loss_partials) accumulates the 8 numerators and 8 denominators in fp64;
+ * pass 2 (abc_loss_backward) writes dL/dlogits for the 8 maps given the per-loss scale factors
+ * u_k / denom_k computed by the host wrapper from `s` (train.py:127-135).
+ * Logits and dlogits: fp32 NCHW as returned by UNet.forward. Targets: fp32 dense maps in the reference's
+ * layout (bond types [N,6,n_omega,H,W]); rho / omega targets may be fp32 or fp64 (tgt_f64 = 1: utils.py:91-92).
+ */
+typedef struct AbcLossDesc {
+  const float* logits[8];
+  const void* targets[8];   /* atom, type, charge, hs, bond, btype, rho, omega */
+  int tgt_f64;              /* 1: targets[6], targets[7] are float64 */
+  int N, H, W;
+  int c_type, c_charge, c_hs, n_omega, n_btype;
+  const float* type_weights; /* [c_type] device pointer or NULL (multi_gpu_train2.py:156) */
+  double* sums;             /* [16] device: numerators 0..7, denominators 8..15 (order of AbcLossIndex) */
+  const float* scale;       /* [8] device: dL/dnum_k = u_k / denom_k (backward pass only) */
+  float* dlogits[8];        /* backward pass only */
+} AbcLossDesc;
+enum AbcLossIndex { ABC_L_ATOM = 0, ABC_L_BOND, ABC_L_TYPE, ABC_L_CHARGE, ABC_L_BTYPE, ABC_L_RHO, ABC_L_OMEGA, ABC_L_HS };
+ABC_API int abc_loss_partials(const AbcLossDesc* desc, void* stream);
+ABC_API int abc_loss_backward(const AbcLossDesc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABCNET_B200_H_ */

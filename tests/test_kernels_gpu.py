@@ -1,0 +1,208 @@
+"""GPU parity tests of the individual kernels, called through the C-ABI (ctypes), against CPU fp32/fp64 references.
+
+Tolerances: operands are rounded to bf16 before the reference computes in fp64, so the only differences are
+fp32 accumulation order (~1e-6 relative) and, for P8 outputs, the final bf16 rounding (2^-9 relative).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import detrand
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    import abcnet_b200
+    from abcnet_b200 import _lib
+    _lib.require_device()
+    return _lib
+
+
+def to_p8(x):
+    """NCHW fp32 -> P8 bf16 [N][C/8][H][W][8]"""
+    N, Cc, H, W = x.shape
+    return x.view(N, Cc // 8, 8, H, W).permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
+
+
+def from_p8(t):
+    N, P, H, W, _ = t.shape
+    return t.float().permute(0, 1, 4, 2, 3).reshape(N, P * 8, H, W)
+
+
+def rnd(seed, shape, lo=-1.0, hi=1.0):
+    return torch.from_numpy(detrand.uniform(detrand.key("k", seed), shape, lo, hi))
+
+
+def bf16_round(x):
+    return x.to(torch.bfloat16).float()
+
+
+def run_conv(x, w_taps, bias, taps, n_tile, act=0, out_mode=0, pool=False, out_planes_extra=0, out_plane_off=0,
+             in_plane_off=0, in_planes_extra=0, out_scale=(1, 0, 1, 0), out_hw=None, want_full=True):
+    """x: NCHW fp32 (bf16-representable). w_taps: [ntaps, cout, cin]. Returns (out NCHW fp32 or None, pooled or None)."""
+    L = _lib()
+    from abcnet_b200.unet import _Packed
+    dev = torch.device("cuda")
+    N, cin, H, W = x.shape
+    cout = w_taps.shape[1]
+    pk = _Packed(w_taps.to(dev), bias.to(dev), taps, n_tile, cout)
+    xin = x
+    if in_planes_extra or in_plane_off:
+        full = torch.full((N, cin + 8 * in_planes_extra, H, W), 7.0)
+        full[:, 8 * in_plane_off:8 * in_plane_off + cin] = x
+        xin = full
+    src = to_p8(xin).to(dev)
+    d = L.AbcConvDesc()
+    d.in_, d.N, d.H, d.W = src.data_ptr(), N, H, W
+    d.in_planes, d.in_plane_off, d.cin = src.shape[1], in_plane_off, cin
+    d.wpack, d.bias = pk.w.data_ptr(), pk.bias.data_ptr()
+    d.cout, d.n_tile, d.ntaps = cout, n_tile, len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i] = dy, dx
+    d.act, d.out_mode = act, out_mode
+    d.out_sy, d.out_oy, d.out_sx, d.out_ox = out_scale
+    oH, oW = out_hw or (H, W)
+    out = pooled = None
+    if want_full:
+        if out_mode == 0:
+            out = torch.full((N, cout // 8 + out_planes_extra, oH, oW, 8), -5.0, dtype=torch.bfloat16, device=dev)
+            d.out_planes, d.out_plane_off = out.shape[1], out_plane_off
+        else:
+            out = torch.full((N, cout, oH, oW), -5.0, dtype=torch.float32, device=dev)
+        d.out = out.data_ptr()
+    d.out_H, d.out_W = oH, oW
+    if pool:
+        pooled = torch.full((N, cout // 8, H // 2, W // 2, 8), -5.0, dtype=torch.bfloat16, device=dev)
+        d.pool_out, d.pool_planes, d.pool_plane_off = pooled.data_ptr(), pooled.shape[1], 0
+    L.check(L.lib.abc_conv_igemm(C.byref(d), torch.cuda.current_stream().cuda_stream), "abc_conv_igemm")
+    torch.cuda.synchronize()
+    o = None
+    if out is not None:
+        o = from_p8(out).cpu() if out_mode == 0 else out.cpu()
+    return o, (from_p8(pooled).cpu() if pooled is not None else None)
+
+
+def ref_conv3(x, w, b, act):
+    y = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if act == 1:
+        y = F.relu(y)
+    elif act == 2:
+        y = F.leaky_relu(y, 0.01)
+    return y.float()
+
+
+def assert_close(got, ref, rtol, atol, what=""):
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = err > bound
+    if bad.any():
+        idx = bad.nonzero()[:8].tolist()
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} elements off; max err {err.max():.4g} "
+                             f"(ref max {ref.abs().max():.4g}); first bad idx {idx}; got {got[bad][:8].tolist()} "
+                             f"ref {ref[bad][:8].tolist()}")
+
+
+TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+
+
+def test_first_conv():
+    L = _lib()
+    N, H, W = 2, 40, 72
+    img = (rnd(1, (N, 1, H, W), 0, 1) < 0.3).float()
+    w = rnd(2, (16, 1, 3, 3))
+    b = rnd(3, (16,))
+    out = torch.full((N, 3, H, W, 8), -5.0, dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib.abc_conv3x3_c1(img.cuda().data_ptr(), w.reshape(16, 9).contiguous().cuda().data_ptr(),
+                                 b.cuda().data_ptr(), out.data_ptr(), N, H, W, 3, 1, 0), "c1")
+    torch.cuda.synchronize()
+    got = from_p8(out).cpu()
+    ref = F.relu(F.conv2d(img, w, b, padding=1))
+    assert_close(got[:, 8:24], ref, 2 ** -8, 1e-6, "conv3x3_c1")
+    assert (got[:, :8] == -5.0).all()                      # plane 0 untouched (plane offset honoured)
+
+
+@pytest.mark.parametrize("cin,cout,n_tile", [(16, 16, 16), (64, 32, 32), (128, 64, 64)])
+def test_igemm_1x1_single_tile(cin, cout, n_tile):
+    """Smallest possible GEMM: one 16x8 tile, one tap, no halo -> isolates TMA box, descriptors, TMEM epilogue."""
+    x = bf16_round(rnd(10 + cin, (1, cin, 16, 8)))
+    w = bf16_round(rnd(20 + cin, (cout, cin)) * 0.25)
+    b = rnd(30, (cout,))
+    got, _ = run_conv(x, w.unsqueeze(0), b, [(0, 0)], n_tile)
+    ref = (torch.einsum("nchw,oc->nohw", x.double(), w.double()) + b.double().view(1, -1, 1, 1)).float()
+    assert_close(got, ref, 2 ** -7, 1e-3, f"1x1 cin={cin}")
+
+
+@pytest.mark.parametrize("cin,cout,n_tile,N,H,W,act", [
+    (16, 16, 16, 1, 16, 8, 0),          # single tile, halo reads only padding
+    (16, 16, 16, 2, 32, 32, 1),         # many tiles, resident weights
+    (32, 64, 64, 1, 48, 40, 1),
+    (64, 64, 64, 2, 32, 24, 2),
+    (128, 128, 128, 2, 32, 32, 1),      # weight ring (non-resident), two K chunks
+    (128, 128, 64, 1, 32, 32, 1),       # two N tiles, resident weights
+    (256, 256, 256, 2, 16, 16, 1),      # n_tile 256
+    (512, 256, 128, 1, 16, 16, 1),      # 8 K chunks, 2 N tiles
+    (64, 128, 128, 3, 6, 10, 1),        # partial tiles (H, W not multiples of the tile)
+])
+def test_igemm_conv3x3(cin, cout, n_tile, N, H, W, act):
+    x = bf16_round(rnd(cin + H, (N, cin, H, W)))
+    w = bf16_round(rnd(cout + W, (cout, cin, 3, 3)) * (2.0 / (cin * 9) ** 0.5))
+    b = rnd(5, (cout,))
+    wt = torch.stack([w[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
+    got, _ = run_conv(x, wt, b, TAPS3, n_tile, act=act)
+    ref = ref_conv3(x, w, b, act)
+    assert_close(got, ref, 2 ** -7, 2e-3, f"conv3x3 {cin}->{cout}")
+
+
+def test_igemm_pool_and_concat_slot():
+    cin, cout, N, H, W = 64, 64, 2, 32, 16
+    x = bf16_round(rnd(77, (N, cin, H, W)))
+    w = bf16_round(rnd(78, (cout, cin, 3, 3)) * 0.05)
+    b = rnd(79, (cout,))
+    wt = torch.stack([w[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
+    got, pooled = run_conv(x, wt, b, TAPS3, 64, act=1, pool=True, out_planes_extra=8, out_plane_off=3,
+                           in_plane_off=2, in_planes_extra=5)
+    ref = ref_conv3(x, w, b, 1)
+    assert_close(got[:, 24:24 + cout], ref, 2 ** -7, 2e-3, "concat slot")
+    assert (got[:, :24] == -5.0).all() and (got[:, 24 + cout:] == -5.0).all()
+    assert_close(pooled, F.max_pool2d(bf16_round(ref), 2), 2 ** -7, 2e-3, "fused pool")
+    # pooled-only launch (no full-resolution output)
+    _, pooled2 = run_conv(x, wt, b, TAPS3, 64, act=1, pool=True, want_full=False)
+    assert torch.equal(pooled2, pooled)
+
+
+def test_igemm_nchw_fp32_heads():
+    cin, N, H, W = 128, 2, 32, 24
+    x = bf16_round(rnd(81, (N, 256, H, W)))
+    for cout, n_tile, off in ((1, 16, 0), (14, 16, 16), (360, 128, 0), (60, 64, 16)):
+        w = bf16_round(rnd(82 + cout, (cout, cin)) * 0.1)
+        b = rnd(83, (cout,))
+        xs = x[:, off * 8: off * 8 + cin]
+        got, _ = run_conv(xs, w.unsqueeze(0), b, [(0, 0)], n_tile, out_mode=1, in_plane_off=off, in_planes_extra=16)
+        ref = (torch.einsum("nchw,oc->nohw", xs.double(), w.double()) + b.double().view(1, -1, 1, 1)).float()
+        assert_close(got, ref, 1e-4, 1e-4, f"1x1 NCHW cout={cout}")
+
+
+@pytest.mark.parametrize("crop_first", [True, False])
+def test_upsampling_conv_phases(crop_first):
+    """ConvTranspose2d(k3, s2) + crop as 4 sub-pixel GEMMs writing a concat slot (unet.py:44-59)."""
+    import abcnet_b200
+    cin, cout, N, H, W = 128, 64, 2, 16, 8
+    x = bf16_round(rnd(91, (N, cin, H, W)))
+    w = bf16_round(rnd(92, (cin, cout, 3, 3)) * 0.05)
+    b = rnd(93, (cout,))
+    U = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2).float()
+    ref = U[:, :, 1:, 1:] if crop_first else U[:, :, :-1, :-1]
+    m = abcnet_b200.UNet(1, [1], crop_first=crop_first)
+    out = torch.zeros(N, cout, 2 * H, 2 * W)
+    for py in (0, 1):
+        for px in (0, 1):
+            ys, xs = m._phase_taps(py), m._phase_taps(px)
+            taps = [(dy, dx) for (ky, dy) in ys for (kx, dx) in xs]
+            wt = torch.stack([w[:, :, ky, kx].t() for (ky, dy) in ys for (kx, dx) in xs]).contiguous()
+            got, _ = run_conv(x, wt, b, taps, 64, act=0, out_scale=(2, py, 2, px), out_hw=(2 * H, 2 * W))
+            out[:, :, py::2, px::2] = got[:, :, py::2, px::2]
+    assert_close(out, ref, 2 ** -7, 2e-3, "up-sampling conv")
