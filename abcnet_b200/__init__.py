@@ -8,6 +8,7 @@ All compute goes through ``libabcnet_b200.so`` (``include/abcnet_b200.h``); ther
 """
 from ._lib import LIB_PATH, launch_count, lib  # noqa: F401  (raises ImportError if the library is not built)
 from .decode import PeakDecoder, records_to_lists  # noqa: F401
+from .loss import HeatmapLoss  # noqa: F401
 from .unet import UNet  # noqa: F401
 
-__all__ = ["UNet", "PeakDecoder", "records_to_lists", "launch_count", "LIB_PATH"]
+__all__ = ["UNet", "HeatmapLoss", "PeakDecoder", "records_to_lists", "launch_count", "LIB_PATH"]

@@ -1,0 +1,105 @@
+"""Fused ABC-Net training losses through the C-ABI (``abc_loss_partials`` / ``abc_loss_backward``).
+
+Replaces ``/root/reference/src/train.py:95-137`` (``class_weights=True``) and
+``/root/reference/src/multi_gpu_train2.py:140-192`` (``class_weights=False``): activations, the eight losses, the
+learned uncertainty weighting with ``model.s`` and -- through ``torch.autograd.Function`` -- their gradients with
+respect to the eight logit maps and to ``s``. Two bandwidth-bound passes over logits + targets instead of ~120 ATen
+kernels; numerators / denominators are accumulated in fp64 on the device, no host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AbcLossDesc, check, lib
+
+ATOM_TYPE_WEIGHTS = [1, 0.1, 0.1, 0.1, 1, 1, 1, 1, 1, 10, 10, 10, 10, 10]          # train.py:16
+# kernel order: atom, bond, type, charge, btype, rho, omega, hs  ->  index into model.s (train.py:127-135)
+_S_INDEX = [0, 1, 2, 3, 4, 6, 7, 9]
+NAMES = ["atom_targets", "bond_targets", "atom_types", "atom_charges", "bond_types", "bond_rhos", "bond_omega_types", "atom_hs"]
+
+
+def _desc(logits, targets, type_w, sums, scale, dlogits):
+    d = AbcLossDesc()
+    N, _, H, W = logits[0].shape
+    n_omega = logits[7].shape[1]
+    for i in range(8):
+        d.logits[i] = logits[i].data_ptr()
+        d.targets[i] = targets[i].data_ptr()
+        d.dlogits[i] = dlogits[i].data_ptr() if dlogits is not None else None
+    d.tgt_f64 = 1 if targets[6].dtype == torch.float64 else 0
+    d.N, d.H, d.W = N, H, W
+    d.c_type, d.c_charge, d.c_hs = logits[1].shape[1], logits[2].shape[1], logits[3].shape[1]
+    d.n_omega, d.n_btype = n_omega, logits[5].shape[1] // n_omega
+    d.type_weights = type_w.data_ptr() if type_w is not None else None
+    d.sums = sums.data_ptr() if sums is not None else None
+    d.scale = scale.data_ptr() if scale is not None else None
+    return d
+
+
+class _HeatmapLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, type_w, targets, *logits):
+        _lib.require_device()
+        logits = [z.contiguous() for z in logits]
+        for z in logits:
+            if not (z.is_cuda and z.dtype == torch.float32):
+                raise ValueError("loss inputs must be fp32 CUDA tensors (no CPU fallback)")
+        # kernel target order: atom, type, charge, hs, bond, btype, rho, omega  (= the reference's argument order)
+        if targets[6].dtype != targets[7].dtype:
+            raise ValueError("rho / omega targets must share a dtype (fp32 or fp64, utils.py:91-92)")
+        for i, t in enumerate(targets):
+            want = (torch.float32, torch.float64) if i >= 6 else (torch.float32,)
+            if not (t.is_cuda and t.is_contiguous() and t.dtype in want):
+                raise ValueError(f"target {i}: contiguous CUDA tensor of dtype {want} required")
+        st = _lib.current_stream_ptr()
+        dev = logits[0].device
+        sums = torch.empty(16, dtype=torch.float64, device=dev)
+        check(lib.abc_loss_partials(C.byref(_desc(logits, targets, type_w, sums, None, None)), st), "abc_loss_partials")
+        num, den = sums[:8], sums[8:].clone()
+        den[7] = den[7] + 0.1                                                  # train.py:114
+        raw = num / den
+        sk = s.detach().double()[_S_INDEX]
+        half = torch.ones(8, dtype=torch.float64, device=dev)
+        half[5] = 0.5                                                          # train.py:133
+        u = half * torch.exp(-sk) + sk
+        total = (raw * u).sum()
+        scale = (u / den).float().contiguous()
+        dlogits = [torch.empty_like(z) for z in logits]
+        check(lib.abc_loss_backward(C.byref(_desc(logits, targets, type_w, None, scale, dlogits)), st), "abc_loss_backward")
+        ds = torch.zeros(10, dtype=torch.float64, device=dev)
+        ds[_S_INDEX] = raw * (1.0 - half * torch.exp(-sk))
+        ctx.save_for_backward(ds.to(s.dtype), *dlogits)
+        ctx.parts = (raw * u).detach()
+        return total
+
+    @staticmethod
+    def backward(ctx, g):
+        ds, *dlogits = ctx.saved_tensors
+        gf = g.float()
+        return (g.to(ds.dtype) * ds, None, None) + tuple(gf * d for d in dlogits)
+
+
+class HeatmapLoss(torch.nn.Module):
+    """loss = HeatmapLoss(class_weights=True)(outs, targets, model.s)
+
+    outs: the 8 tensors returned by UNet.forward; targets: (atom_targets, atom_types, atom_charges, atom_hs,
+    bond_targets, bond_types, bond_rhos, bond_omega_types) as produced by the reference's collate_fn
+    (utils.py:254-300). Returns the float64 scalar of train.py:137; ``.last_parts`` holds the 8 weighted terms."""
+
+    def __init__(self, class_weights: bool = True):
+        super().__init__()
+        self.class_weights = class_weights
+        self.register_buffer("type_w", torch.tensor(ATOM_TYPE_WEIGHTS, dtype=torch.float32), persistent=False)
+        self.last_parts = None
+
+    def forward(self, outs, targets, s):
+        tw = None
+        if self.class_weights:
+            if self.type_w.device != outs[0].device:
+                self.type_w = self.type_w.to(outs[0].device)
+            tw = self.type_w
+        total = _HeatmapLossFn.apply(s, tw, list(targets), *outs)
+        return total

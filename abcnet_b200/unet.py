@@ -100,6 +100,25 @@ def _default_n_tile(cin, cout):
     return 256 if (cout % 256 == 0 and cin >= 128) else 128
 
 
+class _LaunchTimer:
+    """Context manager recording CUDA events around a launch group when ``model.timing`` is a list."""
+
+    def __init__(self, sink, name):
+        self.sink, self.name = sink, name
+
+    def __enter__(self):
+        if self.sink is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.sink is not None:
+            self.b.record()
+            self.sink.append((self.name, self.a, self.b))
+        return False
+
+
 class UNet(nn.Module):
     def __init__(self, in_channels, heads=[1, 21, 5, 1, 4, 2], crop_first=True):
         super().__init__()
@@ -127,6 +146,7 @@ class UNet(nn.Module):
         self._packed = None
         self._packed_key = None
         self._bufs = {}
+        self.timing = None        # set to a list to collect (layer name, start event, end event) per launch group
 
     # ------------------------------------------------------------------ checkpoints
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -241,6 +261,9 @@ class UNet(nn.Module):
             d.pool_out, d.pool_planes, d.pool_plane_off = pool.data_ptr(), pool.shape[1], pool_plane_off
         check(lib.abc_conv_igemm(C.byref(d), stream), "abc_conv_igemm")
 
+    def _timed(self, name):
+        return _LaunchTimer(self.timing, name)
+
     # ------------------------------------------------------------------ forward
     def forward(self, x):
         if self.training:
@@ -263,69 +286,75 @@ class UNet(nn.Module):
         x = x.contiguous().float()
         B, _, H, W = x.shape
         st = _lib.current_stream_ptr()
-        cv = lambda *a, **k: self._conv(*a, stream=st, **k)   # noqa: E731
+
+        def cv(name, *a, **k):
+            with self._timed(name):
+                self._conv(P[name], *a, stream=st, **k)
 
         a = self._buf("a", (B, 2, H, W, 8))
         b = self._buf("b", (B, 2, H, W, 8))
         w0, b0 = P["inc1.0"]
-        check(lib.abc_conv3x3_c1(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), a.data_ptr(), B, H, W, 2, 0, st), "abc_conv3x3_c1")
-        cv(P["inc1.3"], a, 0, b)
-        cv(P["inc2.0"], b, 0, a)
+        with self._timed("inc1.0"):
+            check(lib.abc_conv3x3_c1(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), a.data_ptr(), B, H, W, 2, 0, st), "abc_conv3x3_c1")
+        cv("inc1.3", a, 0, b)
+        cv("inc2.0", b, 0, a)
         p1 = self._buf("p1", (B, 2, H // 2, W // 2, 8))
-        cv(P["inc2.3"], a, 0, None, pool=p1)                                   # x1 is never used as a skip
+        cv("inc2.3", a, 0, None, pool=p1)                                   # x1 is never used as a skip
         d1 = self._buf("d1", (B, 4, H // 2, W // 2, 8))
-        cv(P["down1.0"], p1, 0, d1)
+        cv("down1.0", p1, 0, d1)
         p2 = self._buf("p2", (B, 4, H // 4, W // 4, 8))
-        cv(P["down1.3"], d1, 0, None, pool=p2)                                 # x2 neither
+        cv("down1.3", d1, 0, None, pool=p2)                                 # x2 neither
         e1 = self._buf("e1", (B, 8, H // 4, W // 4, 8))
         e2 = self._buf("e2", (B, 8, H // 4, W // 4, 8))
         cat3 = self._buf("cat3", (B, 16, H // 4, W // 4, 8))
-        cv(P["down2.0"], p2, 0, e1)
-        cv(P["down2.3"], e1, 0, e2)
-        cv(P["inc3.0"], e2, 0, e1)
+        cv("down2.0", p2, 0, e1)
+        cv("down2.3", e1, 0, e2)
+        cv("inc3.0", e2, 0, e1)
         p3 = self._buf("p3", (B, 8, H // 8, W // 8, 8))
-        cv(P["inc3.3"], e1, 0, cat3, out_plane_off=0, pool=p3)                 # x3 -> concat slot [0, 64)
+        cv("inc3.3", e1, 0, cat3, out_plane_off=0, pool=p3)                 # x3 -> concat slot [0, 64)
         f1 = self._buf("f1", (B, 16, H // 8, W // 8, 8))
         cat2 = self._buf("cat2", (B, 32, H // 8, W // 8, 8))
         p4 = self._buf("p4", (B, 16, H // 16, W // 16, 8))
-        cv(P["down3.0"], p3, 0, f1)
-        cv(P["down3.3"], f1, 0, cat2, out_plane_off=0, pool=p4)                # x4
+        cv("down3.0", p3, 0, f1)
+        cv("down3.3", f1, 0, cat2, out_plane_off=0, pool=p4)                # x4
         g1 = self._buf("g1", (B, 32, H // 16, W // 16, 8))
         cat1 = self._buf("cat1", (B, 64, H // 16, W // 16, 8))
         p5 = self._buf("p5", (B, 32, H // 32, W // 32, 8))
-        cv(P["down4.0"], p4, 0, g1)
-        cv(P["down4.3"], g1, 0, cat1, out_plane_off=0, pool=p5)                # x5
+        cv("down4.0", p4, 0, g1)
+        cv("down4.3", g1, 0, cat1, out_plane_off=0, pool=p5)                # x5
         h1 = self._buf("h1", (B, 64, H // 32, W // 32, 8))
         h2 = self._buf("h2", (B, 64, H // 32, W // 32, 8))
-        cv(P["down5.0"], p5, 0, h1)
-        cv(P["down5.3"], h1, 0, h2)                                            # x6
+        cv("down5.0", p5, 0, h1)
+        cv("down5.3", h1, 0, h2)                                            # x6
 
         def up(name, src, cat, half_planes):
-            for py in (0, 1):
-                for px in (0, 1):
-                    cv(P[f"{name}.up.{py}{px}"], src, 0, cat, out_plane_off=half_planes, act=0, out_scale=(2, py, 2, px))
+            with self._timed(name + ".up"):
+                for py in (0, 1):
+                    for px in (0, 1):
+                        self._conv(P[f"{name}.up.{py}{px}"], src, 0, cat, out_plane_off=half_planes, act=0,
+                                   out_scale=(2, py, 2, px), stream=st)
 
         up("up1", h2, cat1, 32)
         i1 = self._buf("i1", (B, 32, H // 16, W // 16, 8))
         i2 = self._buf("i2", (B, 32, H // 16, W // 16, 8))
-        cv(P["up1.conv.0"], cat1, 0, i1)
-        cv(P["up1.conv.3"], i1, 0, i2)
+        cv("up1.conv.0", cat1, 0, i1)
+        cv("up1.conv.3", i1, 0, i2)
         up("up2", i2, cat2, 16)
         j1 = self._buf("j1", (B, 16, H // 8, W // 8, 8))
         j2 = self._buf("j2", (B, 16, H // 8, W // 8, 8))
-        cv(P["up2.conv.0"], cat2, 0, j1)
-        cv(P["up2.conv.3"], j1, 0, j2)
+        cv("up2.conv.0", cat2, 0, j1)
+        cv("up2.conv.3", j1, 0, j2)
         up("up3", j2, cat3, 8)
         k1 = self._buf("k1", (B, 16, H // 4, W // 4, 8))
         k2 = self._buf("k2", (B, 16, H // 4, W // 4, 8))
-        cv(P["up3.conv.0"], cat3, 0, k1)
-        cv(P["up3.conv.3"], k1, 0, k2)
-        cv(P["dconv1.0"], k2, 0, k1)
-        cv(P["dconv1.3"], k1, 0, k2)
-        cv(P["dconv2.0"], k2, 0, k1)
-        cv(P["dconv2.3"], k1, 0, k2)                                           # trunk
+        cv("up3.conv.0", cat3, 0, k1)
+        cv("up3.conv.3", k1, 0, k2)
+        cv("dconv1.0", k2, 0, k1)
+        cv("dconv1.3", k1, 0, k2)
+        cv("dconv2.0", k2, 0, k1)
+        cv("dconv2.3", k1, 0, k2)                                           # trunk
         hid = self._buf("hid", (B, 16 * len(self.heads), H // 4, W // 4, 8))
-        cv(P["heads.conv1"], k2, 0, hid, act=2)                                # BN fold + LeakyReLU(0.01); Dropout is identity in eval
+        cv("heads.conv1", k2, 0, hid, act=2)                                # BN fold + LeakyReLU(0.01); Dropout is identity in eval
         return k2, hid
 
     @torch.no_grad()
@@ -335,8 +364,9 @@ class UNet(nn.Module):
         st = _lib.current_stream_ptr()
         if outs is None:
             outs = [torch.empty((B, h, H4, W4), dtype=torch.float32, device=hid.device) for h in self.heads]
-        for i, _h in enumerate(self.heads):
-            self._conv(self._packed[f"heads.{i}.conv2"], hid, 16 * i, outs[i], act=0, out_mode=1, stream=st)
+        with self._timed("heads.conv2"):
+            for i, _h in enumerate(self.heads):
+                self._conv(self._packed[f"heads.{i}.conv2"], hid, 16 * i, outs[i], act=0, out_mode=1, stream=st)
         return outs
 
     def activation(self, name):

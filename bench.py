@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ABC-Net hot path (batched U-Net forward + heat-map decode) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 256]
+
+Workload (BASELINE.json configs[1]): v2 ABC-Net U-Net, 256 synthetic binary 1x512x512 images per GPU per step,
+bf16 activations / fp32 accumulation, followed by the fused peak-decode kernel. One "step" = one batch.
+  value  : images/s, inputs already resident in HBM, timed with CUDA events, max over ranks
+  e2e    : same metric through the public API with pinned HOST images (H2D inside the timed region) and a D2H read
+           of the decoded peak records every step
+  roofline: the dominant launch (the fused 8-head conv1 implicit GEMM) timed live with CUDA events inside the timed
+           steps; peak from MEASURED_PEAKS.json (sustained bf16, kernel timed inside a long step)
+  cpu_baseline: the CPU oracle port of the same path (fp32 torch on the host cores) on a bounded sample
+--impl reference times that CPU path alone (the reference ships no native code; /root/reference is absent on the
+GPU box, so the oracle port -- same ATen ops on a state_dict -- stands in; kind "port").
+Multi-GPU: one process per GPU (torchrun), images sharded, no data-path collective, weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HEADS = [1, 14, 3, 2, 1, 360, 60, 60]
+METRIC = "images_per_sec_unet_fwd_decode"
+UNIT = "images/s"
+FLOPS_PER_IMAGE = 93.98e9          # SURVEY.md section 6 (forward, v2 heads, 512x512)
+HEADS_CONV1_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 1024 * 1152      # fused 8-head 3x3 conv: M=16384, N=1024, K=1152
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_weights(seed=0):
+    from oracle import unet_ref
+    return unet_ref.make_state_dict(seed=seed, variant="W1")
+
+
+def make_images(seed, n, H=512, W=512):
+    from oracle import synth
+    return torch.from_numpy(synth.binary_images(seed, n, H, W, 0.05))
+
+
+# ----------------------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_path(sd, imgs, calib):
+    """The reference's path on the host: fp32 U-Net forward (oracle port of src/unet.py) + decode (img2smiles.py:62-193)."""
+    from oracle import decode_ref, unet_ref
+    with torch.no_grad():
+        outs = unet_ref.forward(imgs, sd)
+    outs = [o.numpy() for o in outs]
+    for k, v in calib.items():
+        outs[k] = outs[k] + np.float32(v)
+    recs = []
+    for j in range(imgs.shape[0]):
+        a, b = decode_ref.decode_records([o[j] for o in outs], -1.0, "nms")
+        recs.append(decode_ref.records_to_lists(a, b))
+    return recs
+
+
+def time_cpu(sd, calib, n_images, iters, warmup=1):
+    torch.set_num_threads(os.cpu_count() or 1)
+    imgs = make_images(100, n_images)
+    for _ in range(warmup):
+        cpu_path(sd, imgs, calib)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        cpu_path(sd, imgs, calib)
+    dt = time.perf_counter() - t0
+    return n_images * iters / dt, dt / iters
+
+
+def calibrate_offsets_cpu(sd):
+    """Constant logit offsets for the centre / omega heads so that a random-init network yields a realistic number of
+    peaks (~0.3 % of pixels above the -1 threshold); see DESIGN.md 'synthetic inputs'. CPU version for --impl reference."""
+    from oracle import unet_ref
+    with torch.no_grad():
+        outs = unet_ref.forward(make_images(99, 1), sd)
+    return {k: float(-1.0 - torch.quantile(outs[k].flatten(), 0.997)) for k in (0, 4, 7)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sd = make_weights()
+    calib = calibrate_offsets_cpu(sd)
+    n = 8                                        # BASELINE.json configs[0]: batch of 8 images
+    for _ in range(min(args.warmup, 1)):
+        cpu_path(sd, make_images(100, n), calib)
+    torch.set_num_threads(os.cpu_count() or 1)
+    imgs = make_images(100, n)
+    t0 = time.perf_counter()
+    steps = max(1, min(args.steps, 5))
+    for _ in range(steps):
+        cpu_path(sd, imgs, calib)
+    dt = time.perf_counter() - t0
+    v = n * steps / dt
+    cores = torch.get_num_threads()
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "ABC-Net v2 U-Net fwd + heat-map decode, 1x512x512 binary images, CPU fp32",
+                      "sample": f"{n} images per step (bounded sample of the 256-image batch)", "images_per_step": n},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{steps} x {n} images, oracle port of src/unet.py + img2smiles.py:62-193"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    import abcnet_b200
+    from abcnet_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+    B = args.batch
+    sd = make_weights()
+    model = abcnet_b200.UNet(1, HEADS).to(dev).eval()
+    model.load_state_dict(sd)
+    # synthetic images: a pool of 64 distinct images tiled to the batch (generation of 256 x 512^2 takes a while on the host)
+    pool = make_images(1000 + rank, 64)
+    host = pool.repeat((B + 63) // 64, 1, 1, 1)[:B].contiguous().pin_memory()
+    x = host.to(dev)
+    # calibrate constant offsets of the centre / omega heads for a realistic peak density, folded into the conv2 biases
+    outs = model(x[:8].contiguous())
+    torch.cuda.synchronize()
+    calib = {}
+    with torch.no_grad():
+        for k in (0, 4, 7):
+            off = -1.0 - torch.quantile(outs[k].flatten()[:4_000_000].float(), 0.997)
+            model.out_modules[k].conv2.bias += off
+            calib[k] = float(off)
+    dec = abcnet_b200.PeakDecoder(B, atom_cap=args.atom_cap, bond_cap=args.bond_cap, device=dev)
+    out_bufs = None
+
+    def step_device():
+        nonlocal out_bufs
+        out_bufs = model.infer(x, out_bufs)
+        dec.launch(out_bufs)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    counts = dec.fetch(B)
+    n_atoms = float(np.mean([len(a) for a, _, _ in counts]))
+    n_bonds = float(np.mean([len(b) for _, b, _ in counts]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed: device-resident inputs
+    model.timing = []                                    # (name, start_event, end_event) per launch, filled by the model
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    timing, model.timing = model.timing, None
+    # ---- timed: end to end through the public API with host buffers
+    def step_e2e():
+        nonlocal out_bufs
+        xd = host.to(dev, non_blocking=True)
+        out_bufs = model.infer(xd, out_bufs)
+        n = dec.launch(out_bufs)
+        return dec.fetch(n)
+
+    step_e2e()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        recs = step_e2e()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    d2h = int(sum(a.nbytes + b.nbytes for a, b, _ in recs) + 16 * B)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    if rank != 0:
+        return
+    pk, pk_src = peaks()
+    # per-layer breakdown (CUDA events recorded around every launch inside the timed steps)
+    agg = {}
+    for name, a, b in timing:
+        agg.setdefault(name, []).append(a.elapsed_time(b))
+    layers = {k: float(np.mean(v)) for k, v in agg.items()}
+    dom = "heads.conv1"
+    dom_ms = layers.get(dom)
+    roof = None
+    if dom_ms:
+        ach = HEADS_CONV1_FLOPS_PER_IMAGE * B / (dom_ms * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel[heads.conv1 128->1024 3x3 @128x128]", "achieved": ach,
+                "peak": peak, "peak_source": pk_src + " (sustained bf16)", "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "ms_per_launch": dom_ms, "flops_per_launch": HEADS_CONV1_FLOPS_PER_IMAGE * B}
+    total_tflops = FLOPS_PER_IMAGE * B * args.steps / (ms * 1e-3) / 1e12
+    cpu = None
+    if not args.no_cpu:
+        v, per = time_cpu(sd, calib, 8, 2)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "2 x 8 images (bounded sample of the 256-image batch), oracle port: fp32 U-Net + decode"}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": f"ABC-Net v2 U-Net fwd + fused peak decode, batch {B} x 1x512x512 per GPU (BASELINE configs[1])",
+                      "batch_per_gpu": B, "weights": "random-init (deterministic), BN folded, centre/omega biases calibrated",
+                      "l2": "inputs (268 MB / batch) and activations exceed the 126 MB L2; no explicit flush",
+                      "avg_atom_peaks": n_atoms, "avg_bond_records": n_bonds,
+                      "whole_forward_tflops": total_tflops, "layers_ms": layers},
+           "roofline": roof, "cpu_baseline": cpu,
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": d2h,
+                   "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--atom-cap", type=int, default=1024)
+    ap.add_argument("--bond-cap", type=int, default=4096)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun, one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -116,8 +116,8 @@ def test_first_conv():
     w = rnd(2, (16, 1, 3, 3))
     b = rnd(3, (16,))
     out = torch.full((N, 3, H, W, 8), -5.0, dtype=torch.bfloat16, device="cuda")
-    L.check(L.lib.abc_conv3x3_c1(img.cuda().data_ptr(), w.reshape(16, 9).contiguous().cuda().data_ptr(),
-                                 b.cuda().data_ptr(), out.data_ptr(), N, H, W, 3, 1, 0), "c1")
+    d_img, d_w, d_b = img.cuda(), w.reshape(16, 9).contiguous().cuda(), b.cuda()      # keep the device copies alive
+    L.check(L.lib.abc_conv3x3_c1(d_img.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), out.data_ptr(), N, H, W, 3, 1, 0), "c1")
     torch.cuda.synchronize()
     got = from_p8(out).cpu()
     ref = F.relu(F.conv2d(img, w, b, padding=1))

@@ -1,0 +1,209 @@
+"""GPU parity tests of the hot path proper: U-Net forward, heat-map decode, fused losses -- product path
+(abcnet_b200, through the C-ABI) against the CPU oracle and the golden vectors minted from the reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import assemble_ref, decode_ref, detrand, loss_ref, synth, unet_ref
+
+pytestmark = pytest.mark.gpu
+
+HEADS = list(unet_ref.V2_HEADS)
+# Logit tolerance of the bf16-activation / fp32-accumulate pipeline against the fp32 reference, per output map:
+#   max-abs error <= MAX_ABS_FRAC * max|ref| + MAX_ABS_FLOOR   and   relative L2 error <= REL_L2
+MAX_ABS_FRAC, MAX_ABS_FLOOR, REL_L2 = 0.04, 0.03, 0.02
+
+
+def _model(seed, variant="W1"):
+    import abcnet_b200
+    sd = unet_ref.make_state_dict(seed=seed, variant=variant)
+    m = abcnet_b200.UNet(1, HEADS).cuda().eval()
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def _check_logits(outs, refs, what):
+    report = []
+    for i, (o, r) in enumerate(zip(outs, refs)):
+        o = o.detach().float().cpu()
+        r = torch.as_tensor(r)
+        assert o.shape == r.shape and o.is_contiguous()
+        err = (o - r).abs().max().item()
+        scale = r.abs().max().item()
+        rel = ((o - r).norm() / (r.norm() + 1e-12)).item()
+        report.append((i, err, scale, rel))
+    print(what, " | ".join(f"h{i}: maxabs {e:.4f} (scale {s:.2f}) relL2 {r:.4f}" for i, e, s, r in report))
+    for i, err, scale, rel in report:
+        assert err <= MAX_ABS_FRAC * scale + MAX_ABS_FLOOR, f"{what} head {i}: max abs err {err} (scale {scale})"
+        assert rel <= REL_L2, f"{what} head {i}: rel L2 {rel}"
+
+
+@pytest.mark.parametrize("tag,B,H,W,seed", [("small", 2, 64, 96, 3), ("tiny", 2, 32, 32, 4)])
+def test_unet_forward_vs_golden(golden_dir, tag, B, H, W, seed):
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    m, _ = _model(seed)
+    x = torch.from_numpy(synth.binary_images(seed, B, H, W, 0.08)).cuda()
+    outs = m(x)
+    assert isinstance(outs, list) and len(outs) == 8
+    _check_logits(outs, [g[f"{tag}_out{i}"] for i in range(8)], f"golden[{tag}]")
+
+
+def test_unet_layer_by_layer_vs_oracle():
+    """Every intermediate activation against the oracle (localises a wrong layer)."""
+    m, sd = _model(3)
+    x = torch.from_numpy(synth.binary_images(3, 2, 64, 96, 0.08))
+    acts = {}
+    with torch.no_grad():
+        unet_ref.forward(x, sd, acts=acts)
+    m(x.cuda())
+    torch.cuda.synchronize()
+    pairs = [("k2", "dconv2.double_conv.3"), ("cat3", None), ("h2", "down5.maxpool_conv.1.double_conv.3")]
+    got = m.activation("k2").cpu()
+    ref = acts["dconv2.double_conv.3"]
+    rel = ((got - ref).norm() / ref.norm()).item()
+    print("trunk relL2", rel)
+    assert rel < 0.02
+    got = m.activation("h2").cpu()
+    ref = acts["down5.maxpool_conv.1.double_conv.3"]
+    assert ((got - ref).norm() / ref.norm()).item() < 0.02
+    cat3 = m.activation("cat3").cpu()
+    ref = torch.cat([acts["inc3.double_conv.3"], acts["up3.up"]], 1)
+    assert ((cat3 - ref).norm() / ref.norm()).item() < 0.02
+    hid = m.activation("hid").cpu()
+    ref = torch.cat([acts[f"out_modules.{i}.hidden"] for i in range(8)], 1)
+    assert ((hid - ref).norm() / ref.norm()).item() < 0.02
+    assert pairs
+
+
+def test_unet_full_resolution_vs_golden_samples(golden_dir):
+    g = np.load(os.path.join(golden_dir, "unet_full_samples.npz"))
+    m, _ = _model(1)
+    x = torch.from_numpy(synth.binary_images(1, 1, 512, 512, 0.05)).cuda()
+    outs = m(x)
+    r = detrand.integers(detrand.key("samplepos", 1), (256, 2), 0, 1 << 30)
+    px, py = r[:, 0] % 128, r[:, 1] % 128
+    _check_logits([o[0][:, px, py] for o in outs], [g[f"samples{i}"] for i in range(8)], "golden[full samples]")
+    _check_logits([outs[0][0, 0], outs[4][0, 0]], [g["atom_map"], g["bond_map"]], "golden[centre maps]")
+
+
+def test_unet_batch_invariance_and_module_prefix():
+    """Eval-mode results do not depend on batch composition (image sharding is exact), and DataParallel-style
+    'module.'-prefixed checkpoints load (train.py:435)."""
+    import abcnet_b200
+    m, sd = _model(2)
+    x = torch.from_numpy(synth.binary_images(2, 3, 64, 64, 0.08)).cuda()
+    full = [o.clone() for o in m(x)]
+    one = m(x[1:2].contiguous())
+    for a, b in zip(full, one):
+        assert torch.equal(a[1:2], b)
+    m2 = abcnet_b200.UNet(1, HEADS).cuda().eval()
+    m2.load_state_dict({"module." + k: v for k, v in sd.items()})
+    for a, b in zip(full, m2(x)):
+        assert torch.equal(a, b)
+
+
+def _recs_equal(got, ref_atoms, ref_bonds):
+    atoms, bonds, _ = got
+    ra, (rb_int, rb_rho) = ref_atoms, ref_bonds
+    a = np.stack([atoms["x"], atoms["y"], atoms["type"], atoms["charge"], atoms["hs"]], -1).astype(np.int32).reshape(-1, 5)
+    b = np.stack([bonds["x"], bonds["y"], bonds["omega"], bonds["type"]], -1).astype(np.int32).reshape(-1, 4)
+    assert np.array_equal(a, ra), "atom records differ"
+    assert np.array_equal(b, rb_int), "bond records differ"
+    assert np.array_equal(bonds["rho"], rb_rho), "rho differs"        # bit-exact
+
+
+@pytest.mark.parametrize("mode,suffix", [("nms", ""), ("raw", "_raw")])
+def test_decode_planted_batch_bit_exact(golden_dir, mode, suffix):
+    import abcnet_b200
+    gold = json.load(open(os.path.join(golden_dir, "decode_cases.json")))
+    planted = [synth.planted_logits(seed)[0] for seed in range(4)]
+    maps = [torch.from_numpy(np.stack([p[i] for p in planted])).cuda() for i in range(8)]
+    dec = abcnet_b200.PeakDecoder(4, atom_cap=256, bond_cap=4096)
+    res = dec(maps, thr=-1.0, omega_mode=mode)
+    for seed in range(4):
+        ra, rb = decode_ref.decode_records(planted[seed], -1.0, mode)
+        _recs_equal(res[seed], ra, rb)
+        # ... and through the product adapter + host assembly down to the reference's own MOL-block text
+        atoms, bonds, nbp = res[seed]
+        L = abcnet_b200.records_to_lists(atoms, bonds, nbp)
+        g = gold[f"planted{seed}{suffix}"]
+        for k in ("bonds_position_list", "bonds_property_list", "bonds_delta_list", "atoms_position_list",
+                  "atoms_charge_list", "atoms_hs_list"):
+            assert L[k] == g[k], k
+        assert assemble_ref.records_to_molblock(L) == g["molblock"]
+
+
+def test_decode_empty_and_capacity():
+    import abcnet_b200
+    outs, _ = synth.planted_logits(7, n_atoms=0, n_bonds=5, edge_cases=False)
+    maps = [torch.from_numpy(o[None]).cuda() for o in outs]
+    dec = abcnet_b200.PeakDecoder(1, atom_cap=64, bond_cap=64)
+    atoms, bonds, nbp = dec(maps)[0]
+    assert len(atoms) == 0 and nbp == 5
+    assert abcnet_b200.records_to_lists(atoms, bonds, nbp) is None          # img2smiles.py:126-129
+    dense = [torch.from_numpy(o[:1]).cuda() for o in synth.random_logits(11, 1)]
+    with pytest.raises(RuntimeError, match="capacity"):
+        dec(dense)
+    with pytest.raises(ValueError):
+        dec([m.cpu() for m in maps])                                           # no CPU fallback
+
+
+def test_decode_dense_random_logits_bit_exact():
+    """Worst case: thousands of peaks per map (random logits) -- ordering and compaction at scale."""
+    import abcnet_b200
+    logits = synth.random_logits(12, 2)
+    maps = [torch.from_numpy(o).cuda() for o in logits]
+    dec = abcnet_b200.PeakDecoder(2, atom_cap=4096, bond_cap=65536)
+    res = dec(maps, thr=-1.0)
+    for j in range(2):
+        ra, rb = decode_ref.decode_records([o[j] for o in logits], -1.0, "nms")
+        assert len(ra) > 500
+        _recs_equal(res[j], ra, rb)
+
+
+def test_decode_of_network_outputs_matches_oracle_decode():
+    """decode(CUDA logits) by the kernel == decode(CUDA logits) by the oracle, at the real 128x128 map size."""
+    import abcnet_b200
+    m, _ = _model(1)
+    x = torch.from_numpy(synth.binary_images(1, 2, 512, 512, 0.05)).cuda()
+    outs = m(x)
+    dec = abcnet_b200.PeakDecoder(2, atom_cap=16384, bond_cap=262144)
+    res = dec(outs)
+    host = [o.cpu().numpy() for o in outs]
+    for j in range(2):
+        ra, rb = decode_ref.decode_records([h[j] for h in host], -1.0, "nms")
+        _recs_equal(res[j], ra, rb)
+
+
+@pytest.mark.parametrize("key,cw,f64", [("train", True, True), ("train2", False, True), ("train", True, False)])
+def test_fused_loss_vs_reference(golden_dir, key, cw, f64):
+    import abcnet_b200
+    g = json.load(open(os.path.join(golden_dir, "loss_cases.json")))[key]
+    gg = np.load(os.path.join(golden_dir, "loss_grads.npz"))
+    tg = [torch.from_numpy(t) for t in synth.dense_targets(5, 1, 128, 128)]
+    if not f64:
+        tg = [t.float() for t in tg]
+    logits = synth.random_logits(5, 1, 128, 128)
+    outs = [torch.from_numpy(o).cuda().requires_grad_(True) for o in logits]
+    s = torch.from_numpy(detrand.normalish(detrand.key("s", 5), (10,), 0.3)).cuda().requires_grad_(True)
+    lossmod = abcnet_b200.HeatmapLoss(class_weights=cw)
+    total = lossmod(outs, [t.cuda().contiguous() for t in tg], s)
+    total.backward()
+    # tolerance: fp32 per-element math, fp64 accumulation -> 1e-5 relative on the losses, 1e-4 on gradients
+    assert total.dtype == torch.float64
+    assert abs(total.item() - g["loss"]) <= 2e-5 * abs(g["loss"]), (total.item(), g["loss"])
+    np.testing.assert_allclose(s.grad.cpu().numpy(), np.array(g["ds"], np.float32), rtol=1e-4, atol=1e-6)
+    ix, iy = gg["ix"], gg["iy"]
+    for i, o in enumerate(outs):
+        got = o.grad[0][:, ix, iy].cpu().numpy()
+        ref = gg[f"{key}_g{i}"]
+        np.testing.assert_allclose(got, ref, rtol=2e-3, atol=1e-7 + 1e-4 * np.abs(ref).max())
+        asum = o.grad.double().abs().sum().item()
+        assert abs(asum - g["grad_abssum"][i]) <= 1e-3 * g["grad_abssum"][i]
+    # against the fp64 oracle too
+    t64, _, _ = loss_ref.losses([torch.from_numpy(o) for o in logits], tg, s.detach().cpu(), class_weights=cw,
+                                compute_dtype=torch.float64)
+    assert abs(total.item() - t64.item()) <= 2e-5 * abs(t64.item())
