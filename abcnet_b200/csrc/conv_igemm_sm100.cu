@@ -20,6 +20,7 @@
 //   warp 1 : MMA issuer (one thread), accumulators double-buffered in TMEM
 //   warp 2 : TMEM allocation / release
 //   warps 4-7 : epilogue (tcgen05.ld -> bias + activation -> bf16 P8 / fp32 NCHW stores, optional fused max-pool)
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -36,9 +37,9 @@ constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
 
 struct ConvKParams {
-  int N, H, W, tiles_x, tiles_y, num_m_tiles;
-  int in_plane_off, kp, nkc, ntaps, halo, n_tile, resident_b, na, nb;
-  uint32_t a_stage_bytes, a_plane_bytes, a_row_bytes, b_block_bytes;
+  int N, H, W, tiles_x, tiles_y, groups_x, num_groups;   // a group = mt horizontally adjacent 16x8 tiles
+  int in_plane_off, kp, nkc, ntaps, halo, n_tile, resident_b, na, nb, mt;
+  uint32_t a_stage_bytes, a_tile_bytes, a_plane_bytes, a_row_bytes, b_block_bytes;
   uint32_t tap_off[9];
   uint32_t smem_a_off, smem_b_off;
   const uint8_t* wpack;
@@ -97,7 +98,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 128);
+      mbar_init(bar_acc_empty + 8 * i, 4);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmap);
@@ -109,7 +110,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int groups_per_img = p.groups_x * p.tiles_y;
   const uint32_t a_region = sbase + p.smem_a_off;
   const uint32_t b_region = sbase + p.smem_b_off;
   const int blocks_per_ntile = p.nkc * p.ntaps;
@@ -118,18 +119,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     // ------------------------------------------------------------------ A producer (TMA halo tiles)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-      const int n = tile / tiles_per_img;
-      const int rem = tile - n * tiles_per_img;
-      const int ty = rem / p.tiles_x;
-      const int tx = rem - ty * p.tiles_x;
-      const int c0 = (tx * 8 - p.halo) * 8;
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      const int n = g / groups_per_img;
+      const int rem = g - n * groups_per_img;
+      const int ty = rem / p.groups_x;
+      const int tx0 = (rem - ty * p.groups_x) * p.mt;
       const int c1 = ty * 16 - p.halo;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait(bar_a_empty + 8 * stage, phase ^ 1);
         mbar_arrive_expect_tx(bar_a_full + 8 * stage, p.a_stage_bytes);
-        tma_load_4d(a_region + stage * p.a_stage_bytes, &tmap, bar_a_full + 8 * stage, c0, c1,
-                    p.in_plane_off + kc * p.kp, n);
+        for (int i = 0; i < p.mt; ++i)
+          tma_load_4d(a_region + stage * p.a_stage_bytes + i * p.a_tile_bytes, &tmap, bar_a_full + 8 * stage,
+                      ((tx0 + i) * 8 - p.halo) * 8, c1, p.in_plane_off + kc * p.kp, n);
         if (++stage == p.na) {
           stage = 0;
           phase ^= 1;
@@ -140,7 +141,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     // ------------------------------------------------------------------ B producer (packed weight blocks)
     const uint8_t* wsrc = p.wpack + static_cast<size_t>(blockIdx.y) * blocks_per_ntile * p.b_block_bytes;
     if (p.resident_b) {
-      if (blockIdx.x < p.num_m_tiles) {
+      if (blockIdx.x < p.num_groups) {
         mbar_arrive_expect_tx(bar_b_full, static_cast<uint32_t>(blocks_per_ntile) * p.b_block_bytes);
         for (int blk = 0; blk < blocks_per_ntile; ++blk)
           bulk_load_1d(b_region + blk * p.b_block_bytes, wsrc + static_cast<size_t>(blk) * p.b_block_bytes,
@@ -149,7 +150,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     } else {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
         for (int blk = 0; blk < blocks_per_ntile; ++blk) {
           mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
           mbar_arrive_expect_tx(bar_b_full + 8 * stage, p.b_block_bytes);
@@ -170,15 +171,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const int ksteps = p.kp >> 1;
     int a_stage = 0, b_stage = 0, acc = 0;
     uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
-    if (p.resident_b && blockIdx.x < p.num_m_tiles) {
+    if (p.resident_b && blockIdx.x < p.num_groups) {
       mbar_wait(bar_b_full, 0);
       tc_fence_after();
     }
-    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
       mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * 256;
-      uint32_t first = 0;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait(bar_a_full + 8 * a_stage, a_phase);
         tc_fence_after();
@@ -193,10 +193,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
             b_base = b_region + b_stage * p.b_block_bytes;
           }
           const uint32_t a_tap = a_base + p.tap_off[t];
-          for (int j = 0; j < ksteps; ++j) {
-            umma_bf16(tmem_d, umma_desc(a_hi, a_tap + 2 * j * p.a_plane_bytes),
-                      umma_desc(b_hi, b_base + 2 * j * p.n_tile * 16), idesc, first);
-            first = 1;
+          for (int i = 0; i < p.mt; ++i) {
+            for (int j = 0; j < ksteps; ++j)
+              umma_bf16(tmem_d + i * p.n_tile, umma_desc(a_hi, a_tap + i * p.a_tile_bytes + 2 * j * p.a_plane_bytes),
+                        umma_desc(b_hi, b_base + 2 * j * p.n_tile * 16), idesc, (kc | t | j) != 0 ? 1u : 0u);
           }
           if (!p.resident_b) {
             umma_commit(bar_b_empty + 8 * b_stage);
@@ -226,60 +226,72 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const int n0 = blockIdx.y * p.n_tile;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-      const int n = tile / tiles_per_img;
-      const int rem = tile - n * tiles_per_img;
-      const int ty = rem / p.tiles_x;
-      const int tx = rem - ty * p.tiles_x;
-      const int y = ty * 16 + r, x = tx * 8 + c;
-      const bool valid = (y < p.H) && (x < p.W);
-      const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
+    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      const int n = g / groups_per_img;
+      const int rem = g - n * groups_per_img;
+      const int ty = rem / p.groups_x;
+      const int tx0 = (rem - ty * p.groups_x) * p.mt;
+      const int y = ty * 16 + r;
+      const int oy = y * p.out_sy + p.out_oy;
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(q * 32) << 16);
-      for (int col0 = 0; col0 < p.n_tile; col0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + col0, raw);
-        tmem_ld_wait();
-        float v[16];
+      for (int ti = 0; ti < p.mt; ++ti) {
+        const int tx = tx0 + ti;
+        if (tx >= p.tiles_x) break;                       // warp-uniform
+        const int x = tx * 8 + c;
+        const bool valid = (y < p.H) && (x < p.W);
+        const int ox = x * p.out_sx + p.out_ox;
+        const uint32_t taddr = tmem_base + acc * 256 + ti * p.n_tile + (static_cast<uint32_t>(q * 32) << 16);
+        for (int colb = 0; colb < p.n_tile; colb += 32) {
+          // two 16-column TMEM loads in flight before the wait
+          uint32_t raw[2][16];
+          const bool two = (colb + 16) < p.n_tile;
+          tmem_ld16(taddr + colb, raw[0]);
+          if (two) tmem_ld16(taddr + colb + 16, raw[1]);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[i]) + bias_s[col0 + i], p.act);
-        if (p.out_mode == 0) {
-          const int plane = (n0 + col0) >> 3;
-          if (p.out != nullptr && valid && (n0 + col0) < p.cout) {
-            uint4* o = reinterpret_cast<uint4*>(p.out);
-            const size_t px = (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * p.out_H + oy;
-            o[px * p.out_W + ox] = pack8_bf16(v);
-            if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(p.out_H)) * p.out_W + ox] = pack8_bf16(v + 8);
-          }
-          if (p.pool_out != nullptr) {
+          for (int half = 0; half < 2; ++half) {
+            if (half == 1 && !two) break;
+            const int col0 = colb + 16 * half;
+            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float t = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-              v[i] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
-            }
-            if (valid && !(c & 1) && !(r & 1) && (n0 + col0) < p.cout) {
-              const int ph = p.H >> 1, pw = p.W >> 1;
-              uint4* o = reinterpret_cast<uint4*>(p.pool_out);
-              const size_t px = (static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * ph + (y >> 1);
-              o[px * pw + (x >> 1)] = pack8_bf16(v);
-              if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = pack8_bf16(v + 8);
-            }
-          }
-        } else {
-          if (valid) {
-            float* o = reinterpret_cast<float*>(p.out);
+            for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[half][i]) + bias_s[col0 + i], p.act);
+            if (p.out_mode == 0) {
+              const int plane = (n0 + col0) >> 3;
+              if (p.out != nullptr && valid && (n0 + col0) < p.cout) {
+                uint4* o = reinterpret_cast<uint4*>(p.out);
+                const size_t px = (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * p.out_H + oy;
+                o[px * p.out_W + ox] = pack8_bf16(v);
+                if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(p.out_H)) * p.out_W + ox] = pack8_bf16(v + 8);
+              }
+              if (p.pool_out != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int co = n0 + col0 + i;
-              if (co < p.cout)
-                o[((static_cast<size_t>(n) * p.cout + co) * p.out_H + oy) * p.out_W + ox] = v[i];
+                for (int i = 0; i < 16; ++i) {
+                  float t = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                  v[i] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
+                }
+                if (valid && !(c & 1) && !(r & 1) && (n0 + col0) < p.cout) {
+                  const int ph = p.H >> 1, pw = p.W >> 1;
+                  uint4* o = reinterpret_cast<uint4*>(p.pool_out);
+                  const size_t px = (static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * ph + (y >> 1);
+                  o[px * pw + (x >> 1)] = pack8_bf16(v);
+                  if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = pack8_bf16(v + 8);
+                }
+              }
+            } else if (valid) {
+              float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int co = n0 + col0 + i;
+                if (co < p.cout) o[((static_cast<size_t>(n) * p.cout + co) * p.out_H + oy) * p.out_W + ox] = v[i];
+              }
             }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -368,9 +380,6 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.N = d->N; p.H = d->H; p.W = d->W;
   p.tiles_x = (d->W + 7) / 8;
   p.tiles_y = (d->H + 15) / 16;
-  const int64_t m_tiles = static_cast<int64_t>(d->N) * p.tiles_x * p.tiles_y;
-  ABC_REQUIRE(m_tiles < (1ll << 31), "abc_conv_igemm: too many tiles");
-  p.num_m_tiles = static_cast<int>(m_tiles);
   p.in_plane_off = d->in_plane_off;
   const int kc = conv_kc(d->cin);
   p.kp = kc / 8;
@@ -381,31 +390,49 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   const int rows = 16 + 2 * halo, cols = 8 + 2 * halo;
   p.a_row_bytes = cols * 16;
   p.a_plane_bytes = rows * p.a_row_bytes;
-  p.a_stage_bytes = p.kp * p.a_plane_bytes;
+  p.a_tile_bytes = p.kp * p.a_plane_bytes;
   p.b_block_bytes = static_cast<uint32_t>(d->n_tile) * kc * 2;
   for (int t = 0; t < d->ntaps; ++t)
     p.tap_off[t] = static_cast<uint32_t>(((d->tap_dy[t] + halo) * cols + (d->tap_dx[t] + halo)) * 16);
-  const uint32_t a_stage_al = (p.a_stage_bytes + 127u) & ~127u;
-  ABC_REQUIRE(a_stage_al == p.a_stage_bytes, "abc_conv_igemm: internal: A stage not 128-byte multiple");
+  ABC_REQUIRE((p.a_tile_bytes & 127u) == 0, "abc_conv_igemm: internal: A tile not a 128-byte multiple");
   const uint32_t total_b = static_cast<uint32_t>(p.nkc * p.ntaps) * p.b_block_bytes;
   p.smem_a_off = kHeaderBytes;
-  uint32_t smem_bytes;
-  if (kHeaderBytes + 2 * p.a_stage_bytes + total_b <= kSmemBudget && total_b < (1u << 20)) {
-    p.resident_b = 1;
-    p.nb = 1;
-    int na = static_cast<int>((kSmemBudget - kHeaderBytes - total_b) / p.a_stage_bytes);
-    p.na = na > kMaxNA ? kMaxNA : na;
-    p.smem_b_off = kHeaderBytes + p.na * p.a_stage_bytes;
-    smem_bytes = p.smem_b_off + total_b;
-  } else {
-    p.resident_b = 0;
-    p.na = 3;
-    p.smem_b_off = kHeaderBytes + p.na * p.a_stage_bytes;
-    int nb = static_cast<int>((kSmemBudget - p.smem_b_off) / p.b_block_bytes);
-    p.nb = nb > kMaxNB ? kMaxNB : nb;
-    ABC_REQUIRE(p.nb >= 2, "abc_conv_igemm: n_tile=%d too large for the weight ring", d->n_tile);
-    smem_bytes = p.smem_b_off + p.nb * p.b_block_bytes;
+  // mt = tiles per pipeline stage: amortises the per-stage barrier round trips and puts more bytes in flight per SM.
+  // Bounded by TMEM (two accumulator stages of mt * n_tile <= 256 columns each) and by shared memory.
+  int mt_max = 256 / d->n_tile;
+  if (mt_max > 8) mt_max = 8;
+  if (mt_max > p.tiles_x) mt_max = p.tiles_x;
+  if (const char* e = getenv("ABCNET_MT")) { int v = atoi(e); if (v >= 1 && v < mt_max) mt_max = v; }
+  uint32_t smem_bytes = 0;
+  p.mt = 0;
+  for (int mt = mt_max; mt >= 1 && !p.mt; --mt) {          // prefer resident weights
+    const uint32_t a_stage = mt * p.a_tile_bytes;
+    if (total_b < (1u << 20) && kHeaderBytes + 2 * a_stage + total_b <= kSmemBudget) {
+      p.mt = mt; p.resident_b = 1; p.nb = 1;
+      int na = static_cast<int>((kSmemBudget - kHeaderBytes - total_b) / a_stage);
+      p.na = na > kMaxNA ? kMaxNA : na;
+      p.a_stage_bytes = a_stage;
+      p.smem_b_off = kHeaderBytes + p.na * a_stage;
+      smem_bytes = p.smem_b_off + total_b;
+    }
   }
+  for (int mt = mt_max; mt >= 1 && !p.mt; --mt) {          // otherwise stream weight blocks through a ring
+    const uint32_t a_stage = mt * p.a_tile_bytes;
+    if (kHeaderBytes + 2 * a_stage + 4 * p.b_block_bytes <= kSmemBudget) {
+      p.mt = mt; p.resident_b = 0; p.na = 2;
+      if (kHeaderBytes + 3 * a_stage + 6 * p.b_block_bytes <= kSmemBudget) p.na = 3;
+      p.a_stage_bytes = a_stage;
+      p.smem_b_off = kHeaderBytes + p.na * a_stage;
+      int nb = static_cast<int>((kSmemBudget - p.smem_b_off) / p.b_block_bytes);
+      p.nb = nb > kMaxNB ? kMaxNB : nb;
+      smem_bytes = p.smem_b_off + p.nb * p.b_block_bytes;
+    }
+  }
+  ABC_REQUIRE(p.mt >= 1, "abc_conv_igemm: cin=%d n_tile=%d does not fit in shared memory", d->cin, d->n_tile);
+  p.groups_x = (p.tiles_x + p.mt - 1) / p.mt;
+  const int64_t groups = static_cast<int64_t>(d->N) * p.groups_x * p.tiles_y;
+  ABC_REQUIRE(groups < (1ll << 31), "abc_conv_igemm: too many tiles");
+  p.num_groups = static_cast<int>(groups);
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // keep 1 CTA / SM: the kernel owns all 512 TMEM columns
   p.wpack = static_cast<const uint8_t*>(d->wpack);
   p.bias = d->bias;
@@ -448,7 +475,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   if (sms <= 0) sms = 148;
   int gx = sms / n_tiles;
   if (gx < 1) gx = 1;
-  if (gx > p.num_m_tiles) gx = p.num_m_tiles;
+  if (gx > p.num_groups) gx = p.num_groups;
   dim3 grid(gx, n_tiles, 1);
   conv_igemm_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
   return launch_check("conv_igemm_kernel");

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Stand-alone timing of single conv_igemm launches (CUDA events, device-resident synthetic data).
+Usage: python tools/layer_bench.py  -> prints one line per (layer, variant): ms, TFLOP/s, GB/s (algorithmic bytes)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import abcnet_b200  # noqa: E402
+from abcnet_b200 import _lib  # noqa: E402
+from abcnet_b200.unet import _Packed  # noqa: E402
+
+TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+
+
+def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, mt=None, iters=5, act=1):
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    src = (torch.rand((B, cin // 8, H, W, 8), device=dev, generator=g) - 0.5).to(torch.bfloat16)
+    w = (torch.rand((len(taps), cout, cin), device=dev, generator=g) - 0.5) * 0.05
+    pk = _Packed(w, torch.zeros(cout, device=dev), taps, n_tile, cout)
+    d = _lib.AbcConvDesc()
+    d.in_, d.N, d.H, d.W = src.data_ptr(), B, H, W
+    d.in_planes, d.in_plane_off, d.cin = cin // 8, 0, cin
+    d.wpack, d.bias = pk.w.data_ptr(), pk.bias.data_ptr()
+    d.cout, d.n_tile, d.ntaps = cout, n_tile, len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i] = dy, dx
+    d.act, d.out_mode = act, out_mode
+    d.out_sy, d.out_oy, d.out_sx, d.out_ox = 1, 0, 1, 0
+    d.out_H, d.out_W = H, W
+    if out_mode == 0:
+        out = torch.empty((B, (cout + 7) // 8, H, W, 8), dtype=torch.bfloat16, device=dev)
+        d.out_planes = out.shape[1]
+        out_bytes = out.numel() * 2
+    else:
+        out = torch.empty((B, cout, H, W), dtype=torch.float32, device=dev)
+        out_bytes = out.numel() * 4
+    d.out = out.data_ptr()
+    if pool:
+        po = torch.empty((B, cout // 8, H // 2, W // 2, 8), dtype=torch.bfloat16, device=dev)
+        d.pool_out, d.pool_planes = po.data_ptr(), po.shape[1]
+    if mt is not None:
+        os.environ["ABCNET_MT"] = str(mt)
+    else:
+        os.environ.pop("ABCNET_MT", None)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        _lib.check(_lib.lib.abc_conv_igemm(C.byref(d), st))
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        _lib.check(_lib.lib.abc_conv_igemm(C.byref(d), st))
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    flops = 2.0 * B * H * W * cout * cin * len(taps)
+    byts = src.numel() * 2 + out_bytes
+    print(f"{name:28s} B={B:3d} {cin:4d}->{cout:4d} @{H}x{W} n_tile={n_tile:3d} mt={mt}  {ms:8.3f} ms  "
+          f"{flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s", flush=True)
+    return ms
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "shallow"):
+        for mt in (1, 2, 4, 8):
+            bench("16->16@512", 64, 16, 16, 512, 512, 16, mt=mt)
+        bench("16->16@512 pool", 64, 16, 16, 512, 512, 16, pool=True)
+        for mt in (1, 2, 4, 8):
+            bench("32->32@256", 64, 32, 32, 256, 256, 32, mt=mt)
+        for mt in (1, 2, 4):
+            bench("64->64@128", 256, 64, 64, 128, 128, 64, mt=mt)
+    if which in ("all", "mid"):
+        for nt, mt in ((128, 1), (128, 2), (64, 1), (64, 2)):
+            bench("128->128@128", 256, 128, 128, 128, 128, nt, mt=mt)
+        for nt, mt in ((128, 1), (128, 2), (64, 1), (256, 1)):
+            bench("heads 128->1024@128", 128, 128, 1024, 128, 128, nt, mt=mt, act=2)
+        bench("256->256@32", 256, 256, 256, 32, 32, 256)
+        bench("256->256@32", 256, 256, 256, 32, 32, 128)
+        bench("512->512@16", 256, 512, 512, 16, 16, 256)
+        bench("512->256@32", 256, 512, 256, 32, 32, 256)
+    if which in ("all", "heads2"):
+        for cout, nt in ((1, 16), (14, 16), (360, 128), (60, 64)):
+            bench(f"1x1 128->{cout} NCHW", 128, 128, cout, 128, 128, nt, taps=[(0, 0)], out_mode=1, act=0)
