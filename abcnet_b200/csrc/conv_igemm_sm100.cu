@@ -70,6 +70,7 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   return r;
 }
 
+template <int KSTEPS>   // K-steps of 16 channels per pipeline stage = kp / 2 (1, 2, 3 or 4)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -166,9 +167,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
-    const uint64_t a_hi = umma_desc_hi(p.a_plane_bytes, p.a_row_bytes);   // LBO = plane pitch, SBO = tile-row pitch
-    const uint64_t b_hi = umma_desc_hi(p.n_tile * 16, 128);              // LBO = plane pitch, SBO = 8 rows * 16 B
-    const int ksteps = p.kp >> 1;
+    // descriptors as (lo, hi) halves: hi is constant, lo = (smem address >> 4) advances by plain 32-bit adds
+    const uint64_t a_hi64 = umma_desc_hi(p.a_plane_bytes, p.a_row_bytes);   // LBO = plane pitch, SBO = tile-row pitch
+    const uint64_t b_hi64 = umma_desc_hi(p.n_tile * 16, 128);              // LBO = plane pitch, SBO = 8 rows * 16 B
+    const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), b_hi = static_cast<uint32_t>(b_hi64 >> 32);
+    const uint32_t a_lo0 = static_cast<uint32_t>(a_hi64) | (a_region >> 4);
+    const uint32_t b_lo0 = static_cast<uint32_t>(b_hi64) | (b_region >> 4);
+    const uint32_t a_kstep = (2 * p.a_plane_bytes) >> 4, b_kstep = (2 * p.n_tile * 16) >> 4;
+    const uint32_t a_tile16 = p.a_tile_bytes >> 4, a_stage16 = p.a_stage_bytes >> 4, b_block16 = p.b_block_bytes >> 4;
     int a_stage = 0, b_stage = 0, acc = 0;
     uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
     if (p.resident_b && blockIdx.x < p.num_groups) {
@@ -182,21 +188,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait(bar_a_full + 8 * a_stage, a_phase);
         tc_fence_after();
-        const uint32_t a_base = a_region + a_stage * p.a_stage_bytes;
+        const uint32_t a_base = a_lo0 + a_stage * a_stage16;
         for (int t = 0; t < p.ntaps; ++t) {
           uint32_t b_base;
           if (p.resident_b) {
-            b_base = b_region + (kc * p.ntaps + t) * p.b_block_bytes;
+            b_base = b_lo0 + (kc * p.ntaps + t) * b_block16;
           } else {
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
             tc_fence_after();
-            b_base = b_region + b_stage * p.b_block_bytes;
+            b_base = b_lo0 + b_stage * b_block16;
           }
-          const uint32_t a_tap = a_base + p.tap_off[t];
+          const uint32_t a_tap = a_base + (p.tap_off[t] >> 4);
+          const uint32_t acc0 = (kc | t) != 0 ? 1u : 0u;
+#pragma unroll 2
           for (int i = 0; i < p.mt; ++i) {
-            for (int j = 0; j < ksteps; ++j)
-              umma_bf16(tmem_d + i * p.n_tile, umma_desc(a_hi, a_tap + i * p.a_tile_bytes + 2 * j * p.a_plane_bytes),
-                        umma_desc(b_hi, b_base + 2 * j * p.n_tile * 16), idesc, (kc | t | j) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < KSTEPS; ++j)
+              umma_bf16_lohi(tmem_d + i * p.n_tile, a_tap + i * a_tile16 + j * a_kstep, a_hi, b_base + j * b_kstep, b_hi,
+                             idesc, j != 0 ? 1u : acc0);
           }
           if (!p.resident_b) {
             umma_commit(bar_b_empty + 8 * b_stage);
@@ -278,6 +287,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
                   if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = pack8_bf16(v + 8);
                 }
               }
+            } else if (p.out_mode == 2) {
+              // fp32 planar-8 logits [N][planes][H][W][8]: 32 contiguous bytes per thread and plane
+              if (valid && (n0 + col0) < p.cout) {
+                float4* o = reinterpret_cast<float4*>(p.out);
+                const size_t px = ((static_cast<size_t>(n) * p.out_planes + p.out_plane_off + ((n0 + col0) >> 3)) * p.out_H + oy) *
+                                      p.out_W + ox;
+                o[px * 2] = make_float4(v[0], v[1], v[2], v[3]);
+                o[px * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+                if ((n0 + col0 + 8) < p.cout) {
+                  const size_t px2 = px + static_cast<size_t>(p.out_H) * p.out_W;
+                  o[px2 * 2] = make_float4(v[8], v[9], v[10], v[11]);
+                  o[px2 * 2 + 1] = make_float4(v[12], v[13], v[14], v[15]);
+                }
+              }
             } else if (valid) {
               float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
@@ -351,7 +374,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   ABC_REQUIRE(d->n_tile >= 16 && d->n_tile <= 256 && d->n_tile % 16 == 0, "abc_conv_igemm: n_tile=%d", d->n_tile);
   ABC_REQUIRE(d->ntaps >= 1 && d->ntaps <= 9, "abc_conv_igemm: ntaps=%d", d->ntaps);
   ABC_REQUIRE(d->cout >= 1, "abc_conv_igemm: cout=%d", d->cout);
-  ABC_REQUIRE(d->out_mode == 0 || d->out_mode == 1, "abc_conv_igemm: out_mode=%d", d->out_mode);
+  ABC_REQUIRE(d->out_mode >= 0 && d->out_mode <= 2, "abc_conv_igemm: out_mode=%d", d->out_mode);
   ABC_REQUIRE((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->wpack) & 15) == 0,
               "abc_conv_igemm: input / weights must be 16-byte aligned");
   int halo = 0;
@@ -364,7 +387,10 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
     ABC_REQUIRE(d->cout % 8 == 0, "abc_conv_igemm: P8 output needs cout %% 8 == 0 (got %d)", d->cout);
     if (d->out) ABC_REQUIRE(d->out_plane_off >= 0 && d->out_plane_off + d->cout / 8 <= d->out_planes, "abc_conv_igemm: output plane range");
   } else {
-    ABC_REQUIRE(d->out != nullptr && d->pool_out == nullptr, "abc_conv_igemm: NCHW mode needs out and no pool_out");
+    ABC_REQUIRE(d->out != nullptr && d->pool_out == nullptr, "abc_conv_igemm: fp32 output modes need out and no pool_out");
+    if (d->out_mode == 2)
+      ABC_REQUIRE(d->out_plane_off >= 0 && d->out_plane_off + (d->cout + 7) / 8 <= d->out_planes,
+                  "abc_conv_igemm: planar fp32 output plane range");
   }
   if (d->out) {
     ABC_REQUIRE(d->out_sy >= 1 && d->out_sx >= 1 && d->out_oy >= 0 && d->out_ox >= 0 &&
@@ -465,11 +491,16 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
     return ABC_ERR_CUDA;
   }
 
+  typedef void (*KernelFn)(const CUtensorMap, const ConvKParams);
+  KernelFn kernels[5] = {nullptr, conv_igemm_kernel<1>, conv_igemm_kernel<2>, conv_igemm_kernel<3>, conv_igemm_kernel<4>};
   static bool attr_set = false;
   if (!attr_set) {
-    ABC_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    for (int k = 1; k <= 4; ++k)
+      ABC_CUDA(cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
+  const int ksteps = p.kp / 2;
+  ABC_REQUIRE(ksteps >= 1 && ksteps <= 4, "abc_conv_igemm: internal: ksteps=%d", ksteps);
   const int n_tiles = (d->cout + d->n_tile - 1) / d->n_tile;
   int sms = sm_count();
   if (sms <= 0) sms = 148;
@@ -477,6 +508,6 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   if (gx < 1) gx = 1;
   if (gx > p.num_groups) gx = p.num_groups;
   dim3 grid(gx, n_tiles, 1);
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
+  kernels[ksteps]<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
   return launch_check("conv_igemm_kernel");
 }

@@ -22,7 +22,29 @@ struct DecParams {
   AbcBondRec* bonds;
   int bond_cap;
   int32_t* counts;
+  int p8f_mask;
 };
+
+// Element (image n, channel ch, pixel pix) of map k with C channels: NCHW fp32, or planar-8 fp32 [N][ceil(C/8)][HW][8].
+__device__ __forceinline__ float ldmap(const DecParams& p, int k, int n, int ch, int pix, int C) {
+  const size_t hw = static_cast<size_t>(p.H) * p.W;
+  if ((p.p8f_mask >> k) & 1)
+    return p.maps[k][((static_cast<size_t>(n) * ((C + 7) >> 3) + (ch >> 3)) * hw + pix) * 8 + (ch & 7)];
+  return p.maps[k][(static_cast<size_t>(n) * C + ch) * hw + pix];
+}
+
+__device__ __forceinline__ int argmax_map(const DecParams& p, int k, int n, int ch0, int chstride, int C, int Ctot, int pix) {
+  float best = ldmap(p, k, n, ch0, pix, Ctot);
+  int bi = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = ldmap(p, k, n, ch0 + c * chstride, pix, Ctot);
+    if (v > best) {                               // first maximum wins (torch.argmax)
+      best = v;
+      bi = c;
+    }
+  }
+  return bi;
+}
 
 // Exclusive block scan of one int per thread (1024 threads). Returns the exclusive prefix; *total = block sum.
 __device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
@@ -62,19 +84,6 @@ __device__ __forceinline__ bool is_peak(const float* m, int y, int x, int H, int
     for (int xx = x0; xx <= x1; ++xx)
       if (m[yy * W + xx] > v) return false;     // max_pool2d(z) == z  <=>  no neighbour is larger
   return true;
-}
-
-__device__ __forceinline__ int argmax_gather(const float* base, int C, size_t cstride) {
-  float best = base[0];
-  int bi = 0;
-  for (int c = 1; c < C; ++c) {
-    const float v = base[c * cstride];
-    if (v > best) {                               // first maximum wins (torch.argmax)
-      best = v;
-      bi = c;
-    }
-  }
-  return bi;
 }
 
 // Survivor mask of the omega bins of one bond peak, evaluated by a full warp on the n_omega (<= 64) logits in `z`.
@@ -122,20 +131,15 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per = (HW + kDecThreads - 1) / kDecThreads;
   const int p0 = tid * per, p1 = min(p0 + per, HW);
-  const size_t hw = static_cast<size_t>(HW);
 
   // ------------------------------------------------------------------ atoms
-  const float* za = p.maps[0] + static_cast<size_t>(n) * HW;
-  for (int i = tid; i < HW; i += kDecThreads) map[i] = za[i];
+  for (int i = tid; i < HW; i += kDecThreads) map[i] = ldmap(p, 0, n, 0, i, 1);
   __syncthreads();
   int cnt = 0;
   for (int i = p0; i < p1; ++i) cnt += is_peak(map, i / p.W, i % p.W, p.H, p.W, p.thr) ? 1 : 0;
   int total_atoms;
   int idx = block_exscan(cnt, warp_sums, &total_atoms);
   if (cnt) {
-    const float* zt = p.maps[1] + static_cast<size_t>(n) * p.c_type * hw;
-    const float* zc = p.maps[2] + static_cast<size_t>(n) * p.c_charge * hw;
-    const float* zh = p.maps[3] + static_cast<size_t>(n) * p.c_hs * hw;
     for (int i = p0; i < p1; ++i) {
       const int y = i / p.W, x = i % p.W;
       if (!is_peak(map, y, x, p.H, p.W, p.thr)) continue;
@@ -143,9 +147,9 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
         AbcAtomRec r;
         r.x = static_cast<uint16_t>(y);          // reference naming: x = row, y = column (img2smiles.py:178)
         r.y = static_cast<uint16_t>(x);
-        r.type = static_cast<uint8_t>(argmax_gather(zt + i, p.c_type, hw));
-        r.charge = static_cast<uint8_t>(argmax_gather(zc + i, p.c_charge, hw));
-        r.hs = static_cast<uint8_t>(argmax_gather(zh + i, p.c_hs, hw));
+        r.type = static_cast<uint8_t>(argmax_map(p, 1, n, 0, 1, p.c_type, p.c_type, i));
+        r.charge = static_cast<uint8_t>(argmax_map(p, 2, n, 0, 1, p.c_charge, p.c_charge, i));
+        r.hs = static_cast<uint8_t>(argmax_map(p, 3, n, 0, 1, p.c_hs, p.c_hs, i));
         r.pad = 0;
         p.atoms[static_cast<size_t>(n) * p.atom_cap + idx] = r;
       }
@@ -155,8 +159,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
   __syncthreads();
 
   // ------------------------------------------------------------------ bond peaks (ordered list in smem)
-  const float* zb = p.maps[4] + static_cast<size_t>(n) * HW;
-  for (int i = tid; i < HW; i += kDecThreads) map[i] = zb[i];
+  for (int i = tid; i < HW; i += kDecThreads) map[i] = ldmap(p, 4, n, 0, i, 1);
   __syncthreads();
   cnt = 0;
   for (int i = p0; i < p1; ++i) cnt += is_peak(map, i / p.W, i % p.W, p.H, p.W, p.thr) ? 1 : 0;
@@ -167,11 +170,10 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
   __syncthreads();
 
   // ------------------------------------------------------------------ pass A: survivors per bond peak
-  const float* zw = p.maps[7] + static_cast<size_t>(n) * p.n_omega * hw;
   for (int b = warp; b < total_bpeaks; b += kDecWarps) {
     const int pix = bpix[b];
-    if (lane < p.n_omega) wz[warp][lane] = zw[lane * hw + pix];
-    if (lane + 32 < p.n_omega) wz[warp][lane + 32] = zw[(lane + 32) * hw + pix];
+    if (lane < p.n_omega) wz[warp][lane] = ldmap(p, 7, n, lane, pix, p.n_omega);
+    if (lane + 32 < p.n_omega) wz[warp][lane + 32] = ldmap(p, 7, n, lane + 32, pix, p.n_omega);
     __syncwarp();
     uint32_t lo, hi;
     omega_survivors(wz[warp], p.n_omega, p.thr, p.omega_mode, &lo, &hi);
@@ -195,13 +197,11 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
   __syncthreads();
 
   // ------------------------------------------------------------------ pass B: emit bond records
-  const float* zr = p.maps[6] + static_cast<size_t>(n) * p.n_omega * hw;
-  const float* zbt = p.maps[5] + static_cast<size_t>(n) * p.n_btype * p.n_omega * hw;
   for (int b = warp; b < total_bpeaks; b += kDecWarps) {
     if (bcnt[b] == 0) continue;
     const int pix = bpix[b];
-    if (lane < p.n_omega) wz[warp][lane] = zw[lane * hw + pix];
-    if (lane + 32 < p.n_omega) wz[warp][lane + 32] = zw[(lane + 32) * hw + pix];
+    if (lane < p.n_omega) wz[warp][lane] = ldmap(p, 7, n, lane, pix, p.n_omega);
+    if (lane + 32 < p.n_omega) wz[warp][lane + 32] = ldmap(p, 7, n, lane + 32, pix, p.n_omega);
     __syncwarp();
     uint32_t lo, hi;
     omega_survivors(wz[warp], p.n_omega, p.thr, p.omega_mode, &lo, &hi);
@@ -218,9 +218,9 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
           r.x = static_cast<uint16_t>(pix / p.W);
           r.y = static_cast<uint16_t>(pix % p.W);
           r.omega = static_cast<uint8_t>(w);
-          r.type = static_cast<uint8_t>(argmax_gather(zbt + w * hw + pix, p.n_btype, hw * p.n_omega));
+          r.type = static_cast<uint8_t>(argmax_map(p, 5, n, w, p.n_omega, p.n_btype, p.n_btype * p.n_omega, pix));
           r.pad = 0;
-          r.rho = fabsf(zr[w * hw + pix]);
+          r.rho = fabsf(ldmap(p, 6, n, w, pix, p.n_omega));
           p.bonds[static_cast<size_t>(n) * p.bond_cap + o] = r;
         }
       }
@@ -258,6 +258,7 @@ extern "C" int abc_decode_peaks(const AbcDecodeDesc* d, void* stream) {
   p.N = d->N; p.H = d->H; p.W = d->W;
   p.c_type = d->c_type; p.c_charge = d->c_charge; p.c_hs = d->c_hs; p.n_omega = d->n_omega; p.n_btype = d->n_btype;
   p.thr = d->thr; p.omega_mode = d->omega_mode;
+  p.p8f_mask = d->p8f_mask & 0xff;
   p.atoms = d->atoms; p.atom_cap = d->atom_cap; p.bonds = d->bonds; p.bond_cap = d->bond_cap; p.counts = d->counts;
   const size_t smem = static_cast<size_t>(d->H) * d->W * 7;       // 4 B map + 2 B pixel list + 1 B survivor counts
   static size_t smem_set = 0;

@@ -41,18 +41,30 @@ class PeakDecoder:
             raise ValueError("decode needs the 8 head outputs of the v2 model")
         for o in outs:
             if not (o.is_cuda and o.dtype == torch.float32 and o.is_contiguous()):
-                raise ValueError("decode inputs must be contiguous fp32 CUDA tensors (NCHW) -- there is no CPU path")
+                raise ValueError("decode inputs must be contiguous fp32 CUDA tensors -- there is no CPU path")
         _lib.require_device()
-        N, _, H, W = outs[0].shape
+        # NCHW tensors [N,C,H,W] (the reference's format) or planar-8 maps [N,ceil(C/8),H,W,8] from UNet.infer(layout="p8f")
+        heads = getattr(outs, "heads", None)
+        mask, chans = 0, []
+        for i, o in enumerate(outs):
+            if o.dim() == 5:
+                if heads is None:
+                    raise ValueError("planar-8 maps need the channel counts (use the HeadMaps returned by UNet.infer)")
+                mask |= 1 << i
+                chans.append(heads[i])
+            else:
+                chans.append(o.shape[1])
+        N, H, W = outs[0].shape[0], outs[0].shape[2], outs[0].shape[3]
         if N > self.batch:
             raise ValueError(f"batch {N} exceeds decoder capacity {self.batch}")
-        n_omega = outs[7].shape[1]
+        n_omega = chans[7]
         d = AbcDecodeDesc()
         for i, o in enumerate(outs):
             d.maps[i] = o.data_ptr()
         d.N, d.H, d.W = N, H, W
-        d.c_type, d.c_charge, d.c_hs = outs[1].shape[1], outs[2].shape[1], outs[3].shape[1]
-        d.n_omega, d.n_btype = n_omega, outs[5].shape[1] // n_omega
+        d.c_type, d.c_charge, d.c_hs = chans[1], chans[2], chans[3]
+        d.n_omega, d.n_btype = n_omega, chans[5] // n_omega
+        d.p8f_mask = mask
         d.thr = float(thr)
         d.omega_mode = {"nms": 0, "raw": 1}[omega_mode]
         d.atoms, d.atom_cap = self.d_atoms.data_ptr(), self.atom_cap

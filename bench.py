@@ -192,7 +192,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step_device():
         nonlocal out_bufs
-        out_bufs = model.infer(x, out_bufs)
+        out_bufs = model.infer(x, out_bufs, layout="p8f")
         dec.launch(out_bufs)
 
     for _ in range(max(args.warmup, 3)):
@@ -227,7 +227,7 @@ def run_ours(args, rank, world, local_rank):
     def step_e2e():
         nonlocal out_bufs
         xd = host.to(dev, non_blocking=True)
-        out_bufs = model.infer(xd, out_bufs)
+        out_bufs = model.infer(xd, out_bufs, layout="p8f")
         n = dec.launch(out_bufs)
         return dec.fetch(n)
 

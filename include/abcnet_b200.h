@@ -82,7 +82,7 @@ typedef struct AbcConvDesc {
   int tap_dy[9];
   int tap_dx[9];         /* each in [-1, 1] */
   int act;               /* 0 none, 1 ReLU, 2 LeakyReLU(0.01) */
-  int out_mode;          /* 0: P8 bf16, 1: NCHW fp32 [N][cout][out_H][out_W] */
+  int out_mode;          /* 0: P8 bf16, 1: NCHW fp32 [N][cout][out_H][out_W], 2: planar-8 fp32 [N][out_planes][out_H][out_W][8] */
   void* out;             /* may be NULL when only the pooled output is wanted */
   int out_planes;        /* P8: planes of the output buffer */
   int out_plane_off;     /* P8: first plane written (concat slot) */
@@ -138,6 +138,9 @@ typedef struct AbcDecodeDesc {
   AbcBondRec* bonds;
   int bond_cap;
   int32_t* counts;
+  int p8f_mask;            /* bit k set: maps[k] is planar-8 fp32 [N][ceil(C/8)][H][W][8] (abc_conv_igemm out_mode 2)
+                              instead of NCHW: 8 channels of a pixel share one 32-byte sector, so the per-peak gathers
+                              of the fused inference+decode path touch ~8x fewer sectors */
 } AbcDecodeDesc;
 ABC_API int abc_decode_peaks(const AbcDecodeDesc* desc, void* stream);
 

@@ -170,8 +170,11 @@ def test_decode_of_network_outputs_matches_oracle_decode():
     m, _ = _model(1)
     x = torch.from_numpy(synth.binary_images(1, 2, 512, 512, 0.05)).cuda()
     outs = m(x)
+    for k in (0, 4, 7):          # random-init logits sit below the -1 threshold: shift for a realistic peak density
+        outs[k] += -1.0 - torch.quantile(outs[k].flatten()[:1_000_000], 0.995)
     dec = abcnet_b200.PeakDecoder(2, atom_cap=16384, bond_cap=262144)
     res = dec(outs)
+    assert sum(len(a) for a, _, _ in res) > 10
     host = [o.cpu().numpy() for o in outs]
     for j in range(2):
         ra, rb = decode_ref.decode_records([h[j] for h in host], -1.0, "nms")
@@ -207,3 +210,27 @@ def test_fused_loss_vs_reference(golden_dir, key, cw, f64):
     t64, _, _ = loss_ref.losses([torch.from_numpy(o) for o in logits], tg, s.detach().cpu(), class_weights=cw,
                                 compute_dtype=torch.float64)
     assert abs(total.item() - t64.item()) <= 2e-5 * abs(t64.item())
+
+
+def test_planar_logits_layout_is_equivalent():
+    """layout='p8f' (planar-8 fp32 maps, the fused inference+decode format) carries exactly the NCHW values, and the
+    decoder returns identical records from either layout."""
+    import abcnet_b200
+    m, _ = _model(1)
+    x = torch.from_numpy(synth.binary_images(5, 2, 512, 512, 0.05)).cuda()
+    nchw = [o.clone() for o in m.infer(x, layout="nchw")]
+    p8f = m.infer(x, layout="p8f")
+    assert p8f[5].dim() == 5 and p8f[0].dim() == 4
+    for a, b in zip(nchw, p8f.to_nchw()):
+        assert torch.equal(a, b)
+    # shift the centre / omega maps so that there are peaks to decode
+    for k in (0, 4, 7):
+        off = -1.0 - torch.quantile(nchw[k].flatten()[:1_000_000], 0.995)
+        nchw[k] += off
+        p8f[k] += off
+    dec = abcnet_b200.PeakDecoder(2, atom_cap=16384, bond_cap=262144)
+    r1 = dec(nchw)
+    r2 = dec(p8f)
+    assert sum(len(a) for a, _, _ in r1) > 10
+    for (a1, b1, n1), (a2, b2, n2) in zip(r1, r2):
+        assert n1 == n2 and np.array_equal(a1, a2) and np.array_equal(b1, b2)

@@ -32,10 +32,10 @@ def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, 
     d.act, d.out_mode = act, out_mode
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = 1, 0, 1, 0
     d.out_H, d.out_W = H, W
-    if out_mode == 0:
-        out = torch.empty((B, (cout + 7) // 8, H, W, 8), dtype=torch.bfloat16, device=dev)
+    if out_mode in (0, 2):
+        out = torch.empty((B, (cout + 7) // 8, H, W, 8), dtype=torch.bfloat16 if out_mode == 0 else torch.float32, device=dev)
         d.out_planes = out.shape[1]
-        out_bytes = out.numel() * 2
+        out_bytes = out.numel() * (2 if out_mode == 0 else 4)
     else:
         out = torch.empty((B, cout, H, W), dtype=torch.float32, device=dev)
         out_bytes = out.numel() * 4
@@ -87,3 +87,5 @@ if __name__ == "__main__":
     if which in ("all", "heads2"):
         for cout, nt in ((1, 16), (14, 16), (360, 128), (60, 64)):
             bench(f"1x1 128->{cout} NCHW", 128, 128, cout, 128, 128, nt, taps=[(0, 0)], out_mode=1, act=0)
+        for cout, nt in ((14, 16), (360, 128), (360, 192), (60, 64)):
+            bench(f"1x1 128->{cout} P8F", 128, 128, cout, 128, 128, nt, taps=[(0, 0)], out_mode=2, act=0)
