@@ -8,7 +8,8 @@
 
 namespace abc {
 
-__global__ void __launch_bounds__(256) conv3x3_c1_kernel(const float* __restrict__ img, const float* __restrict__ w,
+template <typename T>
+__global__ void __launch_bounds__(256) conv3x3_c1_kernel(const T* __restrict__ img, const float* __restrict__ w,
                                                          const float* __restrict__ b, uint4* __restrict__ out, int H, int W,
                                                          int out_planes, int out_plane_off) {
   __shared__ float ws[16 * 9 + 16];
@@ -20,14 +21,14 @@ __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const float* __restrict
   const int y = blockIdx.y * 8 + threadIdx.y;
   const int n = blockIdx.z;
   if (x >= W || y >= H) return;
-  const float* im = img + static_cast<size_t>(n) * H * W;
+  const T* im = img + static_cast<size_t>(n) * H * W;
   float t[9];
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
       const int yy = y + dy - 1, xx = x + dx - 1;
-      t[dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + static_cast<size_t>(yy) * W + xx) : 0.f;
+      t[dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? static_cast<float>(__ldg(im + static_cast<size_t>(yy) * W + xx)) : 0.f;
     }
   float v[16];
 #pragma unroll
@@ -54,8 +55,9 @@ __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const float* __restrict
 
 }  // namespace abc
 
-extern "C" int abc_conv3x3_c1(const float* img, const float* w, const float* b, void* out, int N, int H, int W,
-                              int out_planes, int out_plane_off, void* stream) {
+template <typename T>
+static int conv3x3_c1_launch(const T* img, const float* w, const float* b, void* out, int N, int H, int W, int out_planes,
+                             int out_plane_off, void* stream) {
   using namespace abc;
   if (int rc = device_check()) return rc;
   ABC_REQUIRE(img && w && b && out, "abc_conv3x3_c1: null pointer");
@@ -63,7 +65,17 @@ extern "C" int abc_conv3x3_c1(const float* img, const float* w, const float* b, 
   ABC_REQUIRE(out_plane_off >= 0 && out_plane_off + 2 <= out_planes, "abc_conv3x3_c1: output plane range");
   ABC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "abc_conv3x3_c1: output must be 16-byte aligned");
   dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, N);
-  conv3x3_c1_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(img, w, b, static_cast<uint4*>(out), H, W,
-                                                                            out_planes, out_plane_off);
+  conv3x3_c1_kernel<T><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(img, w, b, static_cast<uint4*>(out), H, W,
+                                                                               out_planes, out_plane_off);
   return launch_check("conv3x3_c1_kernel");
+}
+
+extern "C" int abc_conv3x3_c1(const float* img, const float* w, const float* b, void* out, int N, int H, int W,
+                              int out_planes, int out_plane_off, void* stream) {
+  return conv3x3_c1_launch<float>(img, w, b, out, N, H, W, out_planes, out_plane_off, stream);
+}
+
+extern "C" int abc_conv3x3_c1_u8(const uint8_t* img, const float* w, const float* b, void* out, int N, int H, int W,
+                                 int out_planes, int out_plane_off, void* stream) {
+  return conv3x3_c1_launch<uint8_t>(img, w, b, out, N, H, W, out_planes, out_plane_off, stream);
 }

@@ -300,7 +300,13 @@ class UNet(nn.Module):
         if self._packed is None or self._packed_key != self._param_key():
             self.prepare()
         P = self._packed
-        x = x.contiguous().float()
+        # fp32 {0,1} images as the reference's DataLoader delivers them, or the same bits as uint8 / bool
+        if x.dtype in (torch.uint8, torch.bool):
+            x = x.contiguous().view(torch.uint8)
+            first = lib.abc_conv3x3_c1_u8
+        else:
+            x = x.contiguous().float()
+            first = lib.abc_conv3x3_c1
         B, _, H, W = x.shape
         st = _lib.current_stream_ptr()
 
@@ -312,7 +318,7 @@ class UNet(nn.Module):
         b = self._buf("b", (B, 2, H, W, 8))
         w0, b0 = P["inc1.0"]
         with self._timed("inc1.0"):
-            check(lib.abc_conv3x3_c1(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), a.data_ptr(), B, H, W, 2, 0, st), "abc_conv3x3_c1")
+            check(first(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), a.data_ptr(), B, H, W, 2, 0, st), "abc_conv3x3_c1")
         cv("inc1.3", a, 0, b)
         cv("inc2.0", b, 0, a)
         p1 = self._buf("p1", (B, 2, H // 2, W // 2, 8))

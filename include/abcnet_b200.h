@@ -54,6 +54,10 @@ ABC_API int64_t abc_launch_count(void);
  */
 ABC_API int abc_conv3x3_c1(const float* img, const float* w, const float* b, void* out, int N, int H, int W,
                            int out_planes, int out_plane_off, void* stream);
+/* Same with the binarised image held as uint8 {0,1} (what src/utils_for_test.py:22-24 computes before its float cast):
+ * 4x fewer bytes over PCIe and HBM. */
+ABC_API int abc_conv3x3_c1_u8(const uint8_t* img, const float* w, const float* b, void* out, int N, int H, int W,
+                              int out_planes, int out_plane_off, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 in TMEM).
