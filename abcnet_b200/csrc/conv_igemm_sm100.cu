@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5;
+  const int warp = static_cast<int>(warp_id_uniform());   // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   // barrier slots (8 bytes each)
@@ -116,7 +116,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   const uint32_t b_region = sbase + p.smem_b_off;
   const int blocks_per_ntile = p.nkc * p.ntaps;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------------ A producer (TMA halo tiles)
     int stage = 0;
     uint32_t phase = 0;
@@ -128,35 +128,42 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       const int c1 = ty * 16 - p.halo;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait(bar_a_empty + 8 * stage, phase ^ 1);
-        mbar_arrive_expect_tx(bar_a_full + 8 * stage, p.a_stage_bytes);
-        for (int i = 0; i < p.mt; ++i)
-          tma_load_4d(a_region + stage * p.a_stage_bytes + i * p.a_tile_bytes, &tmap, bar_a_full + 8 * stage,
-                      ((tx0 + i) * 8 - p.halo) * 8, c1, p.in_plane_off + kc * p.kp, n);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_a_full + 8 * stage, p.a_stage_bytes);
+          for (int i = 0; i < p.mt; ++i)
+            tma_load_4d(a_region + stage * p.a_stage_bytes + i * p.a_tile_bytes, &tmap, bar_a_full + 8 * stage,
+                        ((tx0 + i) * 8 - p.halo) * 8, c1, p.in_plane_off + kc * p.kp, n);
+        }
+        __syncwarp();
         if (++stage == p.na) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (packed weight blocks)
     const uint8_t* wsrc = p.wpack + static_cast<size_t>(blockIdx.y) * blocks_per_ntile * p.b_block_bytes;
     if (p.resident_b) {
-      if (blockIdx.x < p.num_groups) {
+      if (blockIdx.x < p.num_groups && elect_one()) {
         mbar_arrive_expect_tx(bar_b_full, static_cast<uint32_t>(blocks_per_ntile) * p.b_block_bytes);
         for (int blk = 0; blk < blocks_per_ntile; ++blk)
           bulk_load_1d(b_region + blk * p.b_block_bytes, wsrc + static_cast<size_t>(blk) * p.b_block_bytes,
                        p.b_block_bytes, bar_b_full);
       }
+      __syncwarp();
     } else {
       int stage = 0;
       uint32_t phase = 0;
       for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
         for (int blk = 0; blk < blocks_per_ntile; ++blk) {
           mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
-          mbar_arrive_expect_tx(bar_b_full + 8 * stage, p.b_block_bytes);
-          bulk_load_1d(b_region + stage * p.b_block_bytes, wsrc + static_cast<size_t>(blk) * p.b_block_bytes,
-                       p.b_block_bytes, bar_b_full + 8 * stage);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_b_full + 8 * stage, p.b_block_bytes);
+            bulk_load_1d(b_region + stage * p.b_block_bytes, wsrc + static_cast<size_t>(blk) * p.b_block_bytes,
+                         p.b_block_bytes, bar_b_full + 8 * stage);
+          }
+          __syncwarp();
           if (++stage == p.nb) {
             stage = 0;
             phase ^= 1;
@@ -164,7 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
     // descriptors as (lo, hi) halves: hi is constant, lo = (smem address >> 4) advances by plain 32-bit adds
@@ -200,28 +207,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
           }
           const uint32_t a_tap = a_base + (p.tap_off[t] >> 4);
           const uint32_t acc0 = (kc | t) != 0 ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll 2
-          for (int i = 0; i < p.mt; ++i) {
+            for (int i = 0; i < p.mt; ++i) {
 #pragma unroll
-            for (int j = 0; j < KSTEPS; ++j)
-              umma_bf16_lohi(tmem_d + i * p.n_tile, a_tap + i * a_tile16 + j * a_kstep, a_hi, b_base + j * b_kstep, b_hi,
-                             idesc, j != 0 ? 1u : acc0);
+              for (int j = 0; j < KSTEPS; ++j)
+                umma_bf16_lohi(tmem_d + i * p.n_tile, a_tap + i * a_tile16 + j * a_kstep, a_hi, b_base + j * b_kstep, b_hi,
+                               idesc, j != 0 ? 1u : acc0);
+            }
+            if (!p.resident_b) umma_commit(bar_b_empty + 8 * b_stage);
           }
+          __syncwarp();
           if (!p.resident_b) {
-            umma_commit(bar_b_empty + 8 * b_stage);
             if (++b_stage == p.nb) {
               b_stage = 0;
               b_phase ^= 1;
             }
           }
         }
-        umma_commit(bar_a_empty + 8 * a_stage);
+        if (elect_one()) umma_commit(bar_a_empty + 8 * a_stage);
+        __syncwarp();
         if (++a_stage == p.na) {
           a_stage = 0;
           a_phase ^= 1;
         }
       }
-      umma_commit(bar_acc_full + 8 * acc);
+      if (elect_one()) umma_commit(bar_acc_full + 8 * acc);
+      __syncwarp();
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
