@@ -16,6 +16,8 @@ EXPORTS = (
     "abc_last_error", "abc_version", "abc_device_ok", "abc_sm_count", "abc_launch_count",
     "abc_conv3x3_c1", "abc_conv3x3_c1_u8", "abc_conv_igemm", "abc_conv_wpack_bytes", "abc_decode_peaks",
     "abc_loss_partials", "abc_loss_backward",
+    "abc_bn_stats", "abc_bn_finalize", "abc_bn_act", "abc_bn_act_backward", "abc_nchw_to_p8", "abc_channel_sum",
+    "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
 )
 
 
@@ -31,6 +33,7 @@ class AbcConvDesc(C.Structure):
         ("out_H", C.c_int), ("out_W", C.c_int),
         ("out_sy", C.c_int), ("out_oy", C.c_int), ("out_sx", C.c_int), ("out_ox", C.c_int),
         ("pool_out", C.c_void_p), ("pool_planes", C.c_int), ("pool_plane_off", C.c_int),
+        ("k_segments", C.c_int), ("seg_tap0", C.c_int * 4), ("seg_ntaps", C.c_int * 4),
     ]
 
 
@@ -52,6 +55,40 @@ class AbcDecodeDesc(C.Structure):
         ("atoms", C.c_void_p), ("atom_cap", C.c_int),
         ("bonds", C.c_void_p), ("bond_cap", C.c_int),
         ("counts", C.c_void_p), ("p8f_mask", C.c_int),
+    ]
+
+
+class AbcBnActDesc(C.Structure):
+    _fields_ = [
+        ("z", C.c_void_p), ("z_planes", C.c_int), ("z_plane_off", C.c_int),
+        ("out", C.c_void_p), ("out_planes", C.c_int), ("out_plane_off", C.c_int),
+        ("pool", C.c_void_p), ("pool_planes", C.c_int), ("pool_plane_off", C.c_int),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("act", C.c_int), ("drop_p", C.c_float), ("seed", C.c_uint64),
+    ]
+
+
+class AbcBnActBwdDesc(C.Structure):
+    _fields_ = [
+        ("z", C.c_void_p), ("z_planes", C.c_int), ("z_plane_off", C.c_int),
+        ("dA", C.c_void_p), ("dA_planes", C.c_int), ("dA_plane_off", C.c_int),
+        ("dP", C.c_void_p), ("dP_planes", C.c_int), ("dP_plane_off", C.c_int),
+        ("dz", C.c_void_p), ("dz_planes", C.c_int), ("dz_plane_off", C.c_int),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+        ("act", C.c_int), ("drop_p", C.c_float), ("seed", C.c_uint64),
+        ("s1", C.c_void_p), ("s2", C.c_void_p),
+    ]
+
+
+class AbcWgradDesc(C.Structure):
+    _fields_ = [
+        ("dz", C.c_void_p), ("dz_planes", C.c_int), ("dz_plane_off", C.c_int), ("cout", C.c_int),
+        ("in_", C.c_void_p), ("in_planes", C.c_int), ("in_plane_off", C.c_int), ("cin", C.c_int),
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("ntaps", C.c_int), ("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9),
+        ("dw", C.c_void_p),
     ]
 
 
@@ -85,6 +122,17 @@ def _load():
     lib.abc_decode_peaks.argtypes = [C.POINTER(AbcDecodeDesc), C.c_void_p]
     lib.abc_loss_partials.argtypes = [C.POINTER(AbcLossDesc), C.c_void_p]
     lib.abc_loss_backward.argtypes = [C.POINTER(AbcLossDesc), C.c_void_p]
+    vp, ci = C.c_void_p, C.c_int
+    lib.abc_bn_stats.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]
+    lib.abc_channel_sum.argtypes = lib.abc_bn_stats.argtypes
+    lib.abc_bn_finalize.argtypes = [vp, vp, ci, C.c_double, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]
+    lib.abc_bn_act.argtypes = [C.POINTER(AbcBnActDesc), vp]
+    lib.abc_bn_act_backward.argtypes = [C.POINTER(AbcBnActBwdDesc), vp]
+    lib.abc_nchw_to_p8.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    lib.abc_deinterleave2.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, vp]
+    lib.abc_conv_wgrad.argtypes = [C.POINTER(AbcWgradDesc), vp]
+    lib.abc_conv3x3_c1_wgrad.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, vp, vp]
+    lib.abc_conv3x3_c1_raw.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp]
     return lib
 
 

@@ -11,7 +11,7 @@ namespace abc {
 template <typename T>
 __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const T* __restrict__ img, const float* __restrict__ w,
                                                          const float* __restrict__ b, uint4* __restrict__ out, int H, int W,
-                                                         int out_planes, int out_plane_off) {
+                                                         int out_planes, int out_plane_off, int relu) {
   __shared__ float ws[16 * 9 + 16];
   const int tid = threadIdx.y * 32 + threadIdx.x;
   if (tid < 144) ws[tid] = w[tid];
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const T* __restrict__ i
     float a = ws[144 + co];
 #pragma unroll
     for (int k = 0; k < 9; ++k) a = fmaf(t[k], ws[co * 9 + k], a);
-    v[co] = fmaxf(a, 0.f);
+    v[co] = relu ? fmaxf(a, 0.f) : a;
   }
 #pragma unroll
   for (int pl = 0; pl < 2; ++pl) {
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const T* __restrict__ i
 
 template <typename T>
 static int conv3x3_c1_launch(const T* img, const float* w, const float* b, void* out, int N, int H, int W, int out_planes,
-                             int out_plane_off, void* stream) {
+                             int out_plane_off, void* stream, int relu = 1) {
   using namespace abc;
   if (int rc = device_check()) return rc;
   ABC_REQUIRE(img && w && b && out, "abc_conv3x3_c1: null pointer");
@@ -66,7 +66,7 @@ static int conv3x3_c1_launch(const T* img, const float* w, const float* b, void*
   ABC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "abc_conv3x3_c1: output must be 16-byte aligned");
   dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, N);
   conv3x3_c1_kernel<T><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(img, w, b, static_cast<uint4*>(out), H, W,
-                                                                               out_planes, out_plane_off);
+                                                                               out_planes, out_plane_off, relu);
   return launch_check("conv3x3_c1_kernel");
 }
 
@@ -78,4 +78,12 @@ extern "C" int abc_conv3x3_c1(const float* img, const float* w, const float* b, 
 extern "C" int abc_conv3x3_c1_u8(const uint8_t* img, const float* w, const float* b, void* out, int N, int H, int W,
                                  int out_planes, int out_plane_off, void* stream) {
   return conv3x3_c1_launch<uint8_t>(img, w, b, out, N, H, W, out_planes, out_plane_off, stream);
+}
+
+// Training mode: raw convolution + bias (no activation); BatchNorm with batch statistics and ReLU follow in abc_bn_act.
+extern "C" int abc_conv3x3_c1_raw(const void* img, int img_is_u8, const float* w, const float* b, void* out, int N, int H, int W,
+                                  int out_planes, int out_plane_off, void* stream) {
+  if (img_is_u8)
+    return conv3x3_c1_launch<uint8_t>(static_cast<const uint8_t*>(img), w, b, out, N, H, W, out_planes, out_plane_off, stream, 0);
+  return conv3x3_c1_launch<float>(static_cast<const float*>(img), w, b, out, N, H, W, out_planes, out_plane_off, stream, 0);
 }

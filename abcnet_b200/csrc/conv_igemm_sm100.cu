@@ -39,6 +39,8 @@ constexpr int kTmemCols = 512;
 struct ConvKParams {
   int N, H, W, tiles_x, tiles_y, groups_x, num_groups;   // a group = mt horizontally adjacent 16x8 tiles
   int in_plane_off, kp, nkc, ntaps, halo, n_tile, resident_b, na, nb, mt;
+  int chunks_per_seg, blocks_per_ntile;      // K segments: chunk kc uses taps [seg_tap0[s], seg_tap0[s] + seg_ntaps[s]), s = kc / chunks_per_seg
+  int seg_tap0[4], seg_ntaps[4];
   uint32_t a_stage_bytes, a_tile_bytes, a_plane_bytes, a_row_bytes, b_block_bytes;
   uint32_t tap_off[9];
   uint32_t smem_a_off, smem_b_off;
@@ -114,7 +116,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   const int groups_per_img = p.groups_x * p.tiles_y;
   const uint32_t a_region = sbase + p.smem_a_off;
   const uint32_t b_region = sbase + p.smem_b_off;
-  const int blocks_per_ntile = p.nkc * p.ntaps;
+  const int blocks_per_ntile = p.blocks_per_ntile;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer (TMA halo tiles)
@@ -192,21 +194,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * 256;
+      int blk = 0;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait(bar_a_full + 8 * a_stage, a_phase);
         tc_fence_after();
         const uint32_t a_base = a_lo0 + a_stage * a_stage16;
-        for (int t = 0; t < p.ntaps; ++t) {
+        const int seg = kc / p.chunks_per_seg;
+        const int t_begin = p.seg_tap0[seg], t_end = t_begin + p.seg_ntaps[seg];
+        for (int t = t_begin; t < t_end; ++t, ++blk) {
           uint32_t b_base;
           if (p.resident_b) {
-            b_base = b_lo0 + (kc * p.ntaps + t) * b_block16;
+            b_base = b_lo0 + blk * b_block16;
           } else {
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
             tc_fence_after();
             b_base = b_lo0 + b_stage * b_block16;
           }
           const uint32_t a_tap = a_base + (p.tap_off[t] >> 4);
-          const uint32_t acc0 = (kc | t) != 0 ? 1u : 0u;
+          const uint32_t acc0 = (kc | (t - t_begin)) != 0 ? 1u : 0u;
           if (elect_one()) {
 #pragma unroll 2
             for (int i = 0; i < p.mt; ++i) {
@@ -433,7 +438,18 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   for (int t = 0; t < d->ntaps; ++t)
     p.tap_off[t] = static_cast<uint32_t>(((d->tap_dy[t] + halo) * cols + (d->tap_dx[t] + halo)) * 16);
   ABC_REQUIRE((p.a_tile_bytes & 127u) == 0, "abc_conv_igemm: internal: A tile not a 128-byte multiple");
-  const uint32_t total_b = static_cast<uint32_t>(p.nkc * p.ntaps) * p.b_block_bytes;
+  const int nseg = d->k_segments > 1 ? d->k_segments : 1;
+  ABC_REQUIRE(nseg <= 4 && p.nkc % nseg == 0, "abc_conv_igemm: k_segments=%d must divide the %d K chunks (<= 4)", nseg, p.nkc);
+  p.chunks_per_seg = p.nkc / nseg;
+  p.blocks_per_ntile = 0;
+  for (int sgi = 0; sgi < nseg; ++sgi) {
+    p.seg_tap0[sgi] = nseg > 1 ? d->seg_tap0[sgi] : 0;
+    p.seg_ntaps[sgi] = nseg > 1 ? d->seg_ntaps[sgi] : d->ntaps;
+    ABC_REQUIRE(p.seg_tap0[sgi] >= 0 && p.seg_ntaps[sgi] >= 1 && p.seg_tap0[sgi] + p.seg_ntaps[sgi] <= d->ntaps,
+                "abc_conv_igemm: segment %d tap range", sgi);
+    p.blocks_per_ntile += p.chunks_per_seg * p.seg_ntaps[sgi];
+  }
+  const uint32_t total_b = static_cast<uint32_t>(p.blocks_per_ntile) * p.b_block_bytes;
   p.smem_a_off = kHeaderBytes;
   // mt = tiles per pipeline stage: amortises the per-stage barrier round trips and puts more bytes in flight per SM.
   // Bounded by TMEM (two accumulator stages of mt * n_tile <= 256 columns each) and by shared memory.

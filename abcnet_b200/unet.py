@@ -164,6 +164,9 @@ class UNet(nn.Module):
         self._packed_key = None
         self._bufs = {}
         self.timing = None        # set to a list to collect (layer name, start event, end event) per launch group
+        self.dropout_p = 0.2      # nn.Dropout(0.2) of OutConv (unet.py:69); train mode only
+        self.grad_buckets = None  # optional abcnet_b200.ddp.GradBuckets: gradients are accumulated into its buckets
+        self._engine = None
 
     # ------------------------------------------------------------------ checkpoints
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -284,10 +287,15 @@ class UNet(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, x):
         if self.training:
-            raise NotImplementedError(
-                "abcnet_b200.UNet: the training-mode forward (batch-statistics BatchNorm, dropout, backward) is not built "
-                "in this round; call .eval() -- there is deliberately no PyTorch fallback")
+            from .train import _UNetTrainFn
+            return list(_UNetTrainFn.apply(self, x, *self.parameters()))
         return self.infer(x)
+
+    def _train_engine(self):
+        if self._engine is None:
+            from .train import TrainEngine
+            self._engine = TrainEngine(self)
+        return self._engine
 
     @torch.no_grad()
     def trunk_and_hidden(self, x):

@@ -94,6 +94,13 @@ typedef struct AbcConvDesc {
   int out_sy, out_oy, out_sx, out_ox;
   void* pool_out;        /* optional fused MaxPool2d(2) (src/unet.py:30): P8 bf16 [N][pool_planes][H/2][W/2][8] */
   int pool_planes, pool_plane_off;
+  /* Optional K segmentation (0 / 1 = off): the cin channels are split into k_segments equal segments and segment s only
+   * uses taps [seg_tap0[s], seg_tap0[s] + seg_ntaps[s]); packed weights then hold, per n-tile, the blocks in consumption
+   * order (chunk-major, that chunk's taps). Used for the data gradient of the up-sampling convolution, whose four
+   * sub-pixel phases (stacked on the plane axis by abc_deinterleave2) each see their own taps. */
+  int k_segments;
+  int seg_tap0[4];
+  int seg_ntaps[4];
 } AbcConvDesc;
 
 ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);
@@ -171,6 +178,66 @@ typedef struct AbcLossDesc {
 enum AbcLossIndex { ABC_L_ATOM = 0, ABC_L_BOND, ABC_L_TYPE, ABC_L_CHARGE, ABC_L_BTYPE, ABC_L_RHO, ABC_L_OMEGA, ABC_L_HS };
 ABC_API int abc_loss_partials(const AbcLossDesc* desc, void* stream);
 ABC_API int abc_loss_backward(const AbcLossDesc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Training-mode building blocks (autograd of src/unet.py as used by src/train.py:94,139-140).
+ *
+ * BatchNorm2d in train mode (unet.py:13,16,67): abc_bn_stats accumulates per-channel sum / sum-of-squares of a conv
+ * output z (P8 bf16) in fp64; abc_bn_finalize turns them into scale = gamma * invstd, shift = beta - mean * scale and
+ * updates the running statistics (momentum 0.1, unbiased variance); abc_bn_act applies
+ * a = act(z * scale + shift) [* dropout mask / (1 - p), unet.py:69] with an optional fused MaxPool2d(2) output (:30).
+ * abc_bn_act_backward is the backward of that chain: the incoming gradient is dA (full resolution) and / or dP
+ * (gradient of the pooled output, routed to the first maximum of each 2x2 window); outputs dz (P8 bf16),
+ * s1[c] = sum g = dL/dbeta and s2[c] = sum g * xhat = dL/dgamma.
+ */
+ABC_API int abc_bn_stats(const void* z, int N, int H, int W, int planes, int plane_off, int C, double* sum, double* sumsq, void* stream);
+ABC_API int abc_bn_finalize(const double* sum, const double* sumsq, int C, double count, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                            float* mean, float* invstd, void* stream);
+typedef struct AbcBnActDesc {
+  const void* z; int z_planes, z_plane_off;
+  void* out; int out_planes, out_plane_off;        /* may be NULL */
+  void* pool; int pool_planes, pool_plane_off;     /* may be NULL; [N][pool_planes][H/2][W/2][8] */
+  int N, H, W, C;
+  const float* scale; const float* shift;
+  int act;                                         /* 0 none, 1 ReLU, 2 LeakyReLU(0.01) */
+  float drop_p; uint64_t seed;                     /* counter-based dropout, p = 0 disables */
+} AbcBnActDesc;
+ABC_API int abc_bn_act(const AbcBnActDesc* desc, void* stream);
+typedef struct AbcBnActBwdDesc {
+  const void* z; int z_planes, z_plane_off;
+  const void* dA; int dA_planes, dA_plane_off;     /* may be NULL */
+  const void* dP; int dP_planes, dP_plane_off;     /* may be NULL */
+  void* dz; int dz_planes, dz_plane_off;
+  int N, H, W, C;
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  int act; float drop_p; uint64_t seed;
+  double* s1; double* s2;                          /* [C] each */
+} AbcBnActBwdDesc;
+ABC_API int abc_bn_act_backward(const AbcBnActBwdDesc* desc, void* stream);
+/* fp32 NCHW -> bf16 P8 with zero-padded channels (dlogits -> tensor-core operand). */
+ABC_API int abc_nchw_to_p8(const float* src, void* dst, int N, int C, int H, int W, void* stream);
+/* per-channel sum of a P8 tensor (bias gradients of convolutions that are not followed by BatchNorm). */
+ABC_API int abc_channel_sum(const void* x, int N, int H, int W, int planes, int plane_off, int C, double* sum, double* scratch, void* stream);
+/* P8 [N][planes][2H][2W][8] -> [N][4*C/8][H][W][8], phase (py, px) stacked on the plane axis (backward of the
+ * sub-pixel phases of the up-sampling convolution, unet.py:44). */
+ABC_API int abc_deinterleave2(const void* src, int src_planes, int src_plane_off, int C, void* dst, int N, int H, int W, void* stream);
+/* Weight gradient of a convolution on tcgen05 tensor cores (cuDNN backward-filter of the reference's autograd):
+ * dw[tap][co][ci] (fp32, caller-zeroed, accumulated with atomicAdd) = sum_pixels dz[co](y, x) * in[ci](y + dy, x + dx). */
+typedef struct AbcWgradDesc {
+  const void* dz; int dz_planes, dz_plane_off; int cout;    /* P8 bf16 gradient of the conv output */
+  const void* in; int in_planes, in_plane_off; int cin;     /* P8 bf16 conv input */
+  int N, H, W;
+  int ntaps; int tap_dy[9]; int tap_dx[9];
+  float* dw;
+} AbcWgradDesc;
+ABC_API int abc_conv_wgrad(const AbcWgradDesc* desc, void* stream);
+/* First convolution without folded BN / activation (training mode): z = conv(img) + b. */
+ABC_API int abc_conv3x3_c1_raw(const void* img, int img_is_u8, const float* w, const float* b, void* out, int N, int H, int W,
+                               int out_planes, int out_plane_off, void* stream);
+/* dw[16][9] of the first 1 -> 16 convolution (img fp32 or uint8). */
+ABC_API int abc_conv3x3_c1_wgrad(const void* img, int img_is_u8, const void* dz, int dz_planes, int dz_plane_off, int N, int H, int W,
+                                 float* dw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     # AbcConvDesc: 8-byte pointers interleaved with ints exactly as declared (checked against the compiler by the
     # GPU tests; here: field order / count sanity)
     names = [f[0] for f in _lib.AbcConvDesc._fields_]
-    assert names[:7] == ["in_", "N", "H", "W", "in_planes", "in_plane_off", "cin"] and names[-1] == "pool_plane_off"
+    assert names[:7] == ["in_", "N", "H", "W", "in_planes", "in_plane_off", "cin"] and names[-1] == "seg_ntaps"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")

@@ -1,0 +1,80 @@
+"""GPU parity of the training-mode U-Net pass (forward with batch statistics + full backward) against the CPU oracle
+(torch autograd on oracle/unet_ref.py, fp32). Tolerance: bf16 activations and gradients through ~35 layers ->
+relative L2 error per parameter gradient <= 6e-2 (weights) and logits within the eval tolerances."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, unet_ref
+
+pytestmark = pytest.mark.gpu
+HEADS = list(unet_ref.V2_HEADS)
+
+
+def _setup(seed, B, H, W):
+    import abcnet_b200
+    sd = unet_ref.make_state_dict(seed=seed, variant="W1")
+    m = abcnet_b200.UNet(1, HEADS).cuda()
+    m.load_state_dict(sd)
+    m.train()
+    m.dropout_p = 0.0
+    x = torch.from_numpy(synth.binary_images(seed, B, H, W, 0.08))
+    return m, sd, x
+
+
+@pytest.mark.parametrize("tag,B,H,W,seed", [("small", 2, 64, 96, 3), ("tiny", 2, 32, 32, 4)])
+def test_train_forward_vs_golden(golden_dir, tag, B, H, W, seed):
+    from tests.test_path_gpu import _check_logits
+    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    m, sd, x = _setup(seed, B, H, W)
+    outs = m(x.cuda())
+    _check_logits([o.detach() for o in outs], [g[f"{tag}_train_out{i}"] for i in range(8)], f"golden-train[{tag}]")
+    # running statistics moved towards the batch statistics (momentum 0.1)
+    bn = m.inc2.double_conv[1]
+    assert not torch.allclose(bn.running_mean.cpu(), sd["inc2.double_conv.1.running_mean"])
+    assert int(bn.num_batches_tracked) == 1
+
+
+def test_train_backward_vs_oracle_autograd():
+    B, H, W, seed = 2, 64, 64, 5
+    m, sd, x = _setup(seed, B, H, W)
+    outs = m(x.cuda())
+    R = [torch.from_numpy(synth.detrand.uniform(100 + i, tuple(o.shape), -1, 1)) for i, o in enumerate(outs)]
+    loss = sum((o * r.cuda()).sum() for o, r in zip(outs, R))
+    loss.backward()
+    # oracle
+    sdr = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
+    ro = unet_ref.forward(x, sdr, training=True)
+    sum((o * r).sum() for o, r in zip(ro, R)).backward()
+    worst = []
+    for name, p in m.named_parameters():
+        if name == "s":
+            continue
+        ref = sdr[name].grad
+        got = p.grad.detach().cpu()
+        assert got.shape == ref.shape, name
+        denom = ref.norm().item()
+        if name.endswith("bias") and (".0.bias" in name or ".3.bias" in name or "conv1.bias" in name) and "bn" not in name:
+            # conv bias feeding a train-mode BatchNorm: true gradient is 0 (autograd returns round-off noise)
+            assert got.abs().max().item() == 0.0 and ref.abs().max().item() < 1e-3 * max(1.0, ref.numel() ** 0.5), name
+            continue
+        rel = (got - ref).norm().item() / (denom + 1e-12)
+        worst.append((rel, name, denom))
+    worst.sort(reverse=True)
+    print("largest relative L2 gradient errors:", [(round(r, 4), n) for r, n, _ in worst[:8]])
+    for rel, name, denom in worst:
+        tol = 0.06 if name.endswith("weight") and "bn" not in name and ".1." not in name and ".4." not in name else 0.10
+        assert rel <= tol, f"{name}: rel L2 {rel} (|ref| {denom})"
+
+
+def test_dropout_is_consistent_between_forward_and_backward():
+    m, sd, x = _setup(6, 2, 32, 32)
+    m.dropout_p = 0.2
+    outs = m(x.cuda())
+    hid = m._engine.bufs["a:hid"].float()
+    keep = (hid != 0).float().mean().item()
+    assert 0.70 < keep < 0.90, keep                      # ~80 % kept (LeakyReLU output is never exactly 0 otherwise)
+    sum(o.sum() for o in outs).backward()
+    assert all(torch.isfinite(p.grad).all() for n, p in m.named_parameters() if n != "s")

@@ -1,0 +1,169 @@
+"""GPU parity tests of the training-mode kernels (C-ABI via ctypes) against torch autograd in fp64 on bf16-rounded
+operands. Tolerances: outputs stored in bf16 -> 2^-7 relative; fp32 accumulations -> 1e-3 relative to the max."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.test_kernels_gpu import TAPS3, _lib, assert_close, bf16_round, from_p8, rnd, to_p8
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def bn_forward(z, gamma, beta, act, pool, rm=None, rv=None):
+    L = _lib()
+    N, Cc, H, W = z.shape
+    dev = "cuda"
+    zp = to_p8(z).to(dev)
+    s = torch.zeros(Cc, dtype=torch.float64, device=dev)
+    q = torch.zeros_like(s)
+    L.check(L.lib.abc_bn_stats(zp.data_ptr(), N, H, W, Cc // 8, 0, Cc, s.data_ptr(), q.data_ptr(), _st()))
+    bufs = [torch.empty(Cc, device=dev) for _ in range(4)]
+    g, b = gamma.to(dev), beta.to(dev)
+    L.check(L.lib.abc_bn_finalize(s.data_ptr(), q.data_ptr(), Cc, float(N * H * W), g.data_ptr(), b.data_ptr(), 1e-5, 0.1,
+                                  rm.data_ptr() if rm is not None else None, rv.data_ptr() if rv is not None else None,
+                                  *[t.data_ptr() for t in bufs], _st()))
+    d = L.AbcBnActDesc()
+    d.z, d.z_planes, d.z_plane_off = zp.data_ptr(), Cc // 8, 0
+    out = torch.empty_like(zp)
+    d.out, d.out_planes, d.out_plane_off = out.data_ptr(), Cc // 8, 0
+    po = None
+    if pool:
+        po = torch.empty((N, Cc // 8, H // 2, W // 2, 8), dtype=torch.bfloat16, device=dev)
+        d.pool, d.pool_planes, d.pool_plane_off = po.data_ptr(), Cc // 8, 0
+    d.N, d.H, d.W, d.C = N, H, W, Cc
+    d.scale, d.shift = bufs[0].data_ptr(), bufs[1].data_ptr()
+    d.act, d.drop_p, d.seed = act, 0.0, 0
+    L.check(L.lib.abc_bn_act(C.byref(d), _st()))
+    torch.cuda.synchronize()
+    return zp, bufs, from_p8(out).cpu(), (from_p8(po).cpu() if pool else None)
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_bn_train_forward_and_backward(act):
+    N, Cc, H, W = 3, 32, 12, 20
+    z = bf16_round(rnd(1, (N, Cc, H, W)) * 2 + rnd(2, (1, Cc, 1, 1)))
+    gamma, beta = rnd(3, (Cc,), 0.5, 1.5), rnd(4, (Cc,), -0.3, 0.3)
+    rm = torch.zeros(Cc, device="cuda")
+    rv = torch.ones(Cc, device="cuda")
+    zp, bufs, out, pooled = bn_forward(z, gamma, beta, act, True, rm, rv)
+    # reference (fp64)
+    zz = z.double().requires_grad_(True)
+    gg, bb = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    y = F.batch_norm(zz, None, None, gg, bb, True, 0.1, 1e-5)
+    a = F.relu(y) if act == 1 else F.leaky_relu(y, 0.01)
+    assert_close(out, a.detach().float(), 2 ** -7, 1e-3, "bn_act out")
+    assert_close(pooled, F.max_pool2d(bf16_round(out), 2), 0, 0, "bn_act pool")
+    mean, var = z.double().mean((0, 2, 3)), z.double().var((0, 2, 3), unbiased=True)
+    assert_close(rm.cpu(), (0.1 * mean).float(), 1e-4, 1e-5, "running_mean")
+    assert_close(rv.cpu(), (0.9 + 0.1 * var).float(), 1e-4, 1e-5, "running_var")
+    # backward: loss = <dA, a> + <dP, maxpool(a)>  (pool routing evaluated on the bf16 activation, as the kernel stores it)
+    dA = bf16_round(rnd(5, (N, Cc, H, W)))
+    dP = bf16_round(rnd(6, (N, Cc, H // 2, W // 2)))
+    a_b = a + (bf16_round(a.detach().float()).double() - a.detach())        # value = bf16(a), gradient = identity
+    loss = (a * dA.double()).sum() + (F.max_pool2d(a_b, 2) * dP.double()).sum()
+    loss.backward()
+    L = _lib()
+    d = L.AbcBnActBwdDesc()
+    dev = "cuda"
+    dAp, dPp = to_p8(dA).to(dev), to_p8(dP).to(dev)
+    dz = torch.empty_like(zp)
+    s1 = torch.zeros(Cc, dtype=torch.float64, device=dev)
+    s2 = torch.zeros_like(s1)
+    d.z, d.z_planes, d.z_plane_off = zp.data_ptr(), Cc // 8, 0
+    d.dA, d.dA_planes, d.dA_plane_off = dAp.data_ptr(), Cc // 8, 0
+    d.dP, d.dP_planes, d.dP_plane_off = dPp.data_ptr(), Cc // 8, 0
+    d.dz, d.dz_planes, d.dz_plane_off = dz.data_ptr(), Cc // 8, 0
+    d.N, d.H, d.W, d.C = N, H, W, Cc
+    d.scale, d.shift, d.mean, d.invstd = [t.data_ptr() for t in bufs]
+    d.act, d.drop_p, d.seed = act, 0.0, 0
+    d.s1, d.s2 = s1.data_ptr(), s2.data_ptr()
+    L.check(L.lib.abc_bn_act_backward(C.byref(d), _st()))
+    torch.cuda.synchronize()
+    ref = zz.grad.float()
+    assert_close(from_p8(dz).cpu(), ref, 2 ** -6, 2e-3 * ref.abs().max().item(), "dz")
+    assert_close(s1.cpu().float(), bb.grad.float(), 1e-3, 1e-3, "dbeta")
+    assert_close(s2.cpu().float(), gg.grad.float(), 1e-3, 1e-3, "dgamma")
+
+
+def run_wgrad(dz, a, taps):
+    L = _lib()
+    dev = "cuda"
+    N, cout, H, W = dz.shape
+    cin = a.shape[1]
+    dzp, ap = to_p8(dz).to(dev), to_p8(a).to(dev)
+    dw = torch.zeros((len(taps), cout, cin), dtype=torch.float32, device=dev)
+    d = L.AbcWgradDesc()
+    d.dz, d.dz_planes, d.dz_plane_off, d.cout = dzp.data_ptr(), cout // 8, 0, cout
+    d.in_, d.in_planes, d.in_plane_off, d.cin = ap.data_ptr(), cin // 8, 0, cin
+    d.N, d.H, d.W, d.ntaps = N, H, W, len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i] = dy, dx
+    d.dw = dw.data_ptr()
+    L.check(L.lib.abc_conv_wgrad(C.byref(d), _st()), "abc_conv_wgrad")
+    torch.cuda.synchronize()
+    return dw.cpu()
+
+
+@pytest.mark.parametrize("cin,cout,N,H,W", [
+    (16, 16, 2, 32, 32), (32, 64, 2, 32, 24), (128, 128, 2, 32, 32), (256, 256, 2, 16, 16), (128, 1024, 1, 32, 16),
+    (512, 256, 1, 16, 16), (64, 128, 3, 6, 10),
+])
+def test_wgrad_conv3x3(cin, cout, N, H, W):
+    a = bf16_round(rnd(cin, (N, cin, H, W)))
+    dz = bf16_round(rnd(cout + 1, (N, cout, H, W)))
+    w = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(a.double(), w, padding=1) * dz.double()).sum().backward()
+    got = run_wgrad(dz, a, TAPS3)                                  # [9][cout][cin]
+    ref = torch.stack([w.grad[:, :, dy + 1, dx + 1] for dy, dx in TAPS3]).float()
+    assert_close(got, ref, 1e-3, 1e-3 * ref.abs().max().item(), f"wgrad {cin}->{cout}")
+
+
+def test_wgrad_1x1_and_padded_cout():
+    a = bf16_round(rnd(7, (2, 128, 32, 24)))
+    for cout in (8, 16, 64, 360):
+        dz = bf16_round(rnd(8 + cout, (2, cout, 32, 24)))
+        got = run_wgrad(dz, a, [(0, 0)])[0]
+        ref = torch.einsum("nohw,nchw->oc", dz.double(), a.double()).float()
+        assert_close(got, ref, 1e-3, 1e-3 * ref.abs().max().item(), f"wgrad 1x1 cout={cout}")
+
+
+def test_first_conv_wgrad():
+    L = _lib()
+    N, H, W = 2, 40, 72
+    img = (rnd(1, (N, 1, H, W), 0, 1) < 0.3).float()
+    dz = bf16_round(rnd(2, (N, 16, H, W)))
+    w = torch.zeros(16, 1, 3, 3, dtype=torch.float64, requires_grad=True)
+    (F.conv2d(img.double(), w, padding=1) * dz.double()).sum().backward()
+    d_img, dzp = img.cuda(), to_p8(dz).cuda()
+    dw = torch.zeros(144, device="cuda")
+    L.check(L.lib.abc_conv3x3_c1_wgrad(d_img.data_ptr(), 0, dzp.data_ptr(), 2, 0, N, H, W, dw.data_ptr(), _st()))
+    torch.cuda.synchronize()
+    ref = w.grad.reshape(144).float()
+    assert_close(dw.cpu(), ref, 1e-3, 1e-3 * ref.abs().max().item(), "c1 wgrad")
+
+
+@pytest.mark.parametrize("crop_first", [True, False])
+def test_upsampling_conv_backward(crop_first):
+    """dgrad (one K-segmented igemm over the de-interleaved phases) and wgrad (per phase) of ConvTranspose2d + crop."""
+    import abcnet_b200
+    from abcnet_b200 import train as T
+    cin, cout, N, H, W = 128, 64, 2, 16, 8
+    x = bf16_round(rnd(91, (N, cin, H, W)))
+    w = bf16_round(rnd(92, (cin, cout, 3, 3)) * 0.05)
+    du = bf16_round(rnd(93, (N, cout, 2 * H, 2 * W)))
+    xx = x.double().requires_grad_(True)
+    ww = w.double().requires_grad_(True)
+    U = F.conv_transpose2d(xx, ww, None, stride=2)
+    kept = U[:, :, 1:, 1:] if crop_first else U[:, :, :-1, :-1]
+    (kept * du.double()).sum().backward()
+    dev = "cuda"
+    dx, dw = T.upconv_backward(to_p8(du).to(dev), 0, cout, to_p8(x).to(dev), w.to(dev), crop_first)
+    torch.cuda.synchronize()
+    assert_close(from_p8(dx).cpu(), xx.grad.float(), 2 ** -6, 2e-3 * xx.grad.abs().max().item(), "upconv dgrad")
+    assert_close(dw.cpu(), ww.grad.float(), 1e-3, 1e-3 * ww.grad.abs().max().item(), "upconv wgrad")
