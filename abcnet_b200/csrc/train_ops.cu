@@ -134,8 +134,9 @@ struct BnActParams {
 };
 
 __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
-  // one thread per (n, plane, 2x2 pixel block)
-  const int hw2 = (p.H >> 1) * (p.W >> 1);
+  // one thread per (n, plane, 2x2 pixel block); partial blocks at odd H / W are masked
+  const int bw = (p.W + 1) >> 1;
+  const int hw2 = ((p.H + 1) >> 1) * bw;
   const long long total = static_cast<long long>(p.N) * p.planes * hw2;
   const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (t >= total) return;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
   const long long r = t / hw2;
   const int plane = static_cast<int>(r % p.planes);
   const int n = static_cast<int>(r / p.planes);
-  const int by = b / (p.W >> 1), bx = b - by * (p.W >> 1);
+  const int by = b / bw, bx = b - by * bw;
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int y = 2 * by + (k >> 1), x = 2 * bx + (k & 1);
+    if (y >= p.H || x >= p.W) continue;
     const size_t pix = static_cast<size_t>(y) * p.W + x;
     float v[8];
     unpack8(p.z.ptr[(static_cast<size_t>(n) * p.z.planes + p.z.plane_off + plane) * HW + pix], v);
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
     }
     if (p.out) p.out[(static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * HW + pix] = pack8(v);
   }
-  if (p.pool)
+  if (p.pool)   // even H, W guaranteed by the host check
     p.pool[(static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * hw2 + b] = pack8(mx);
 }
 
@@ -203,6 +205,13 @@ __device__ __forceinline__ void bwd_block(const BnActBwdParams& p, int n, int pl
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int y = 2 * by + (k >> 1), x = 2 * bx + (k & 1);
+    if (y >= p.H || x >= p.W) {                      // masked pixel of a partial block: contributes nothing
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a[k][i] = -INFINITY; pre[k][i] = 0.f; dsc[k][i] = 0.f; g[k][i] = 0.f; xh[k][i] = 0.f;
+      }
+      continue;
+    }
     const size_t pix = static_cast<size_t>(y) * p.W + x;
     float v[8];
     unpack8(p.z.ptr[(static_cast<size_t>(n) * p.z.planes + p.z.plane_off + plane) * HW + pix], v);
@@ -242,7 +251,8 @@ __device__ __forceinline__ void bwd_block(const BnActBwdParams& p, int n, int pl
 
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwdParams p) {
   const int plane = blockIdx.x;
-  const int hw2 = (p.H >> 1) * (p.W >> 1);
+  const int bw = (p.W + 1) >> 1;
+  const int hw2 = ((p.H + 1) >> 1) * bw;
   const long long total = static_cast<long long>(p.N) * hw2;
   float s1[8], s2[8];
 #pragma unroll
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwdPa
   for (long long e = static_cast<long long>(blockIdx.y) * 256 + threadIdx.x; e < total; e += static_cast<long long>(gridDim.y) * 256) {
     const int n = static_cast<int>(e / hw2);
     const int b = static_cast<int>(e - static_cast<long long>(n) * hw2);
-    const int by = b / (p.W >> 1), bx = b - by * (p.W >> 1);
+    const int by = b / bw, bx = b - by * bw;
     float g[4][8], xh[4][8];
     bwd_block(p, n, plane, by, bx, g, xh);
 #pragma unroll
@@ -279,7 +289,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwdPa
 }
 
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnActBwdParams p) {
-  const int hw2 = (p.H >> 1) * (p.W >> 1);
+  const int bw = (p.W + 1) >> 1;
+  const int hw2 = ((p.H + 1) >> 1) * bw;
   const long long total = static_cast<long long>(p.N) * p.planes * hw2;
   const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (t >= total) return;
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnActBwdPar
   const long long r = t / hw2;
   const int plane = static_cast<int>(r % p.planes);
   const int n = static_cast<int>(r / p.planes);
-  const int by = b / (p.W >> 1), bx = b - by * (p.W >> 1);
+  const int by = b / bw, bx = b - by * bw;
   float g[4][8], xh[4][8];
   bwd_block(p, n, plane, by, bx, g, xh);
   float m1[8], m2[8], sc[8];
@@ -302,6 +313,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnActBwdPar
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int y = 2 * by + (k >> 1), x = 2 * bx + (k & 1);
+    if (y >= p.H || x >= p.W) continue;
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = sc[i] * (g[k][i] - m1[i] - xh[k][i] * m2[i]);
@@ -428,8 +440,8 @@ extern "C" int abc_bn_finalize(const double* sum, const double* sumsq, int C, do
 extern "C" int abc_bn_act(const AbcBnActDesc* d, void* stream) {
   if (int rc = device_check()) return rc;
   ABC_REQUIRE(d && d->scale && d->shift, "abc_bn_act: null descriptor / scale / shift");
-  ABC_REQUIRE(d->C >= 8 && d->C % 8 == 0 && d->N > 0 && d->H > 0 && d->W > 0 && d->H % 2 == 0 && d->W % 2 == 0,
-              "abc_bn_act: C %% 8 == 0 and even H, W required (C=%d H=%d W=%d)", d->C, d->H, d->W);
+  ABC_REQUIRE(d->C >= 8 && d->C % 8 == 0 && d->N > 0 && d->H > 0 && d->W > 0, "abc_bn_act: bad geometry (C=%d H=%d W=%d)", d->C, d->H, d->W);
+  ABC_REQUIRE(!d->pool || (d->H % 2 == 0 && d->W % 2 == 0), "abc_bn_act: fused max-pool needs even H, W");
   ABC_REQUIRE(d->out || d->pool, "abc_bn_act: no output");
   if (int rc = p8_check(d->z, d->z_planes, d->z_plane_off, d->C / 8, "abc_bn_act(z)")) return rc;
   if (d->out) if (int rc = p8_check(d->out, d->out_planes, d->out_plane_off, d->C / 8, "abc_bn_act(out)")) return rc;
@@ -440,7 +452,7 @@ extern "C" int abc_bn_act(const AbcBnActDesc* d, void* stream) {
   p.pool = static_cast<uint4*>(d->pool); p.pool_planes = d->pool_planes; p.pool_plane_off = d->pool_plane_off;
   p.N = d->N; p.H = d->H; p.W = d->W; p.planes = d->C / 8;
   p.scale = d->scale; p.shift = d->shift; p.act = d->act; p.drop_p = d->drop_p; p.seed = d->seed;
-  const long long total = static_cast<long long>(d->N) * p.planes * (d->H / 2) * (d->W / 2);
+  const long long total = static_cast<long long>(d->N) * p.planes * ((d->H + 1) / 2) * ((d->W + 1) / 2);
   bn_act_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return launch_check("bn_act_kernel");
 }
@@ -448,8 +460,8 @@ extern "C" int abc_bn_act(const AbcBnActDesc* d, void* stream) {
 extern "C" int abc_bn_act_backward(const AbcBnActBwdDesc* d, void* stream) {
   if (int rc = device_check()) return rc;
   ABC_REQUIRE(d && d->scale && d->shift && d->mean && d->invstd && d->s1 && d->s2 && d->dz, "abc_bn_act_backward: null argument");
-  ABC_REQUIRE(d->C >= 8 && d->C % 8 == 0 && d->N > 0 && d->H % 2 == 0 && d->W % 2 == 0 && d->H > 0 && d->W > 0,
-              "abc_bn_act_backward: C %% 8 == 0 and even H, W required");
+  ABC_REQUIRE(d->C >= 8 && d->C % 8 == 0 && d->N > 0 && d->H > 0 && d->W > 0, "abc_bn_act_backward: bad geometry");
+  ABC_REQUIRE(!d->dP || (d->H % 2 == 0 && d->W % 2 == 0), "abc_bn_act_backward: pooled gradient needs even H, W");
   ABC_REQUIRE(d->dA || d->dP, "abc_bn_act_backward: no incoming gradient");
   const int cp = d->C / 8;
   if (int rc = p8_check(d->z, d->z_planes, d->z_plane_off, cp, "abc_bn_act_backward(z)")) return rc;
@@ -469,7 +481,7 @@ extern "C" int abc_bn_act_backward(const AbcBnActBwdDesc* d, void* stream) {
   p.count = static_cast<double>(d->N) * d->H * d->W;
   ABC_CUDA(cudaMemsetAsync(d->s1, 0, d->C * sizeof(double), st));
   ABC_CUDA(cudaMemsetAsync(d->s2, 0, d->C * sizeof(double), st));
-  const long long blocks2 = static_cast<long long>(d->N) * (d->H / 2) * (d->W / 2);
+  const long long blocks2 = static_cast<long long>(d->N) * ((d->H + 1) / 2) * ((d->W + 1) / 2);
   int gy = static_cast<int>((blocks2 + 256 * 4 - 1) / (256 * 4));
   const int max_gy = (148 * 8 + cp - 1) / cp;
   if (gy > max_gy) gy = max_gy;

@@ -6,7 +6,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.test_kernels_gpu import TAPS3, _lib, assert_close, bf16_round, from_p8, rnd, to_p8
+from test_kernels_gpu import TAPS3, _lib, assert_close, bf16_round, from_p8, rnd, to_p8
 
 pytestmark = pytest.mark.gpu
 
