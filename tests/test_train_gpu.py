@@ -24,21 +24,53 @@ def _setup(seed, B, H, W):
     return m, sd, x
 
 
-@pytest.mark.parametrize("tag,B,H,W,seed", [("small", 2, 64, 96, 3), ("tiny", 2, 32, 32, 4)])
-def test_train_forward_vs_golden(golden_dir, tag, B, H, W, seed):
+def _p8_to_nchw(t):
+    N, P, H, W, _ = t.shape
+    return t.float().permute(0, 1, 4, 2, 3).reshape(N, P * 8, H, W).cpu()
+
+
+def test_train_forward_layer_by_layer_vs_oracle():
+    """Train-mode forward (batch statistics) against the oracle, layer by layer. The input is large enough (4 x 128 x 128)
+    for every BatchNorm to see >= 64 samples per channel: with a handful of samples (e.g. 2 x 1 x 1 at the deepest level of a
+    32 x 32 input) the normalisation is ill-conditioned and bf16 rounding of the conv output can flip signs."""
     from test_path_gpu import _check_logits
-    g = np.load(os.path.join(golden_dir, "unet_small.npz"))
+    B, H, W, seed = 4, 128, 128, 3
     m, sd, x = _setup(seed, B, H, W)
     outs = m(x.cuda())
-    _check_logits([o.detach() for o in outs], [g[f"{tag}_train_out{i}"] for i in range(8)], f"golden-train[{tag}]")
-    # running statistics moved towards the batch statistics (momentum 0.1)
+    acts = {}
+    with torch.no_grad():
+        ref = unet_ref.forward(x, sd, training=True, acts=acts)
+    eng = m._engine
+    names = {"inc1.0": "inc1.double_conv.0", "inc1.3": "inc1.double_conv.3", "inc2.0": "inc2.double_conv.0",
+             "down1.0": "down1.maxpool_conv.1.double_conv.0", "down2.0": "down2.maxpool_conv.1.double_conv.0",
+             "down2.3": "down2.maxpool_conv.1.double_conv.3", "inc3.0": "inc3.double_conv.0",
+             "down3.0": "down3.maxpool_conv.1.double_conv.0", "down4.0": "down4.maxpool_conv.1.double_conv.0",
+             "down5.0": "down5.maxpool_conv.1.double_conv.0", "down5.3": "down5.maxpool_conv.1.double_conv.3",
+             "up1.conv.0": "up1.conv.double_conv.0", "up1.conv.3": "up1.conv.double_conv.3",
+             "up2.conv.3": "up2.conv.double_conv.3", "up3.conv.3": "up3.conv.double_conv.3",
+             "dconv1.3": "dconv1.double_conv.3", "dconv2.3": "dconv2.double_conv.3"}
+    report = []
+    for k, rk in names.items():
+        got = _p8_to_nchw(eng.bufs["a:" + k])
+        r = acts[rk]
+        report.append((k, ((got - r).norm() / r.norm()).item()))
+    cat3 = _p8_to_nchw(eng.bufs["cat:3"])
+    r = torch.cat([acts["inc3.double_conv.3"], acts["up3.up"]], 1)
+    report.append(("cat3", ((cat3 - r).norm() / r.norm()).item()))
+    hid = _p8_to_nchw(eng.bufs["a:hid"])
+    r = torch.cat([acts[f"out_modules.{i}.hidden"] for i in range(8)], 1)
+    report.append(("hid", ((hid - r).norm() / r.norm()).item()))
+    print("train forward relative L2 per layer:", [(k, round(v, 4)) for k, v in report])
+    for k, v in report:
+        assert v < 0.03, (k, v)
+    _check_logits([o.detach() for o in outs], ref, "train logits")
     bn = m.inc2.double_conv[1]
     assert not torch.allclose(bn.running_mean.cpu(), sd["inc2.double_conv.1.running_mean"])
     assert int(bn.num_batches_tracked) == 1
 
 
 def test_train_backward_vs_oracle_autograd():
-    B, H, W, seed = 2, 64, 64, 5
+    B, H, W, seed = 4, 128, 128, 5
     m, sd, x = _setup(seed, B, H, W)
     outs = m(x.cuda())
     R = [torch.from_numpy(synth.detrand.uniform(100 + i, tuple(o.shape), -1, 1)) for i, o in enumerate(outs)]
