@@ -147,20 +147,33 @@ def _bn(x, sd, p, training, stats_out=None):
                         sd[p + ".bias"], False, 0.1, BN_EPS)
 
 
-def _double_conv(x, sd, p, training, acts=None):
-    x = F.conv2d(x, sd[p + ".0.weight"], sd[p + ".0.bias"], padding=1)
-    x = F.relu(_bn(x, sd, p + ".1", training))
+def bf16_ste(t):
+    """Round to bf16 (value) with a straight-through gradient -- used to EMULATE the storage precision of the CUDA path
+    (bf16 conv outputs / activations / weights, fp32 accumulation) inside the fp32 oracle. Train-mode BatchNorm makes a
+    randomly initialised net amplify perturbations ~370x from the first layer to the trunk (fp32 vs fp64 oracle: 5e-8 ->
+    2e-5), so bf16 storage noise (2e-3) cannot be compared end-to-end against the unrounded oracle; rounding at the same
+    points removes the storage noise from the comparison and leaves accumulation-order effects only."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def _id(t):
+    return t
+
+
+def _double_conv(x, sd, p, training, acts=None, rnd=_id):
+    x = rnd(F.conv2d(x, rnd(sd[p + ".0.weight"]), sd[p + ".0.bias"], padding=1))
+    x = rnd(F.relu(_bn(x, sd, p + ".1", training)))
     if acts is not None:
         acts[p + ".0"] = x
-    x = F.conv2d(x, sd[p + ".3.weight"], sd[p + ".3.bias"], padding=1)
-    x = F.relu(_bn(x, sd, p + ".4", training))
+    x = rnd(F.conv2d(x, rnd(sd[p + ".3.weight"]), sd[p + ".3.bias"], padding=1))
+    x = rnd(F.relu(_bn(x, sd, p + ".4", training)))
     if acts is not None:
         acts[p + ".3"] = x
     return x
 
 
-def _up(x1, x2, sd, name, training, crop_first, acts=None):
-    x1 = F.conv_transpose2d(x1, sd[name + ".up.weight"], sd[name + ".up.bias"], stride=2)
+def _up(x1, x2, sd, name, training, crop_first, acts=None, rnd=_id):
+    x1 = rnd(F.conv_transpose2d(x1, rnd(sd[name + ".up.weight"]), sd[name + ".up.bias"], stride=2))
     dy = x1.shape[2] - x2.shape[2]
     dx = x1.shape[3] - x2.shape[3]
     if crop_first:
@@ -170,41 +183,45 @@ def _up(x1, x2, sd, name, training, crop_first, acts=None):
     if acts is not None:
         acts[name + ".up"] = x1
     x = torch.cat([x2, x1], dim=1)
-    return _double_conv(x, sd, name + ".conv.double_conv", training, acts)
+    return _double_conv(x, sd, name + ".conv.double_conv", training, acts, rnd)
 
 
-def trunk(x, sd, training=False, crop_first=True, acts=None):
+def trunk(x, sd, training=False, crop_first=True, acts=None, rnd=_id):
     """unet.py:101-115 -- everything before the heads."""
     sd = _strip(sd)
-    x1 = _double_conv(x, sd, "inc1.double_conv", training, acts)
-    x1 = _double_conv(x1, sd, "inc2.double_conv", training, acts)
-    x2 = _double_conv(F.max_pool2d(x1, 2), sd, "down1.maxpool_conv.1.double_conv", training, acts)
-    x3 = _double_conv(F.max_pool2d(x2, 2), sd, "down2.maxpool_conv.1.double_conv", training, acts)
-    x3 = _double_conv(x3, sd, "inc3.double_conv", training, acts)
-    x4 = _double_conv(F.max_pool2d(x3, 2), sd, "down3.maxpool_conv.1.double_conv", training, acts)
-    x5 = _double_conv(F.max_pool2d(x4, 2), sd, "down4.maxpool_conv.1.double_conv", training, acts)
-    x6 = _double_conv(F.max_pool2d(x5, 2), sd, "down5.maxpool_conv.1.double_conv", training, acts)
-    x = _up(x6, x5, sd, "up1", training, crop_first, acts)
-    x = _up(x, x4, sd, "up2", training, crop_first, acts)
-    x = _up(x, x3, sd, "up3", training, crop_first, acts)
-    x = _double_conv(x, sd, "dconv1.double_conv", training, acts)
-    x = _double_conv(x, sd, "dconv2.double_conv", training, acts)
+    x1 = _double_conv(x, sd, "inc1.double_conv", training, acts, rnd)
+    x1 = _double_conv(x1, sd, "inc2.double_conv", training, acts, rnd)
+    x2 = _double_conv(F.max_pool2d(x1, 2), sd, "down1.maxpool_conv.1.double_conv", training, acts, rnd)
+    x3 = _double_conv(F.max_pool2d(x2, 2), sd, "down2.maxpool_conv.1.double_conv", training, acts, rnd)
+    x3 = _double_conv(x3, sd, "inc3.double_conv", training, acts, rnd)
+    x4 = _double_conv(F.max_pool2d(x3, 2), sd, "down3.maxpool_conv.1.double_conv", training, acts, rnd)
+    x5 = _double_conv(F.max_pool2d(x4, 2), sd, "down4.maxpool_conv.1.double_conv", training, acts, rnd)
+    x6 = _double_conv(F.max_pool2d(x5, 2), sd, "down5.maxpool_conv.1.double_conv", training, acts, rnd)
+    x = _up(x6, x5, sd, "up1", training, crop_first, acts, rnd)
+    x = _up(x, x4, sd, "up2", training, crop_first, acts, rnd)
+    x = _up(x, x3, sd, "up3", training, crop_first, acts, rnd)
+    x = _double_conv(x, sd, "dconv1.double_conv", training, acts, rnd)
+    x = _double_conv(x, sd, "dconv2.double_conv", training, acts, rnd)
     return x
 
 
-def forward(x, sd, heads=V2_HEADS, training=False, crop_first=True, acts=None, dropout_masks=None):
+def forward(x, sd, heads=V2_HEADS, training=False, crop_first=True, acts=None, dropout_masks=None, emulate_bf16=False):
     """UNet.forward (unet.py:100-119). ``dropout_masks`` (list of 0/1 tensors [B,128,H,W] or None)
-    replaces nn.Dropout(0.2) in training mode so that tests are deterministic (scale 1/0.8)."""
+    replaces nn.Dropout(0.2) in training mode so that tests are deterministic (scale 1/0.8).
+    ``emulate_bf16`` rounds weights, conv outputs and activations to bf16 (straight-through) exactly where the CUDA
+    training path stores bf16 -- see ``bf16_ste``."""
     sd = _strip(sd)
-    t = trunk(x, sd, training, crop_first, acts)
+    rnd = bf16_ste if emulate_bf16 else _id
+    t = trunk(x, sd, training, crop_first, acts, rnd)
     outs = []
     for i, _ in enumerate(heads):
         p = f"out_modules.{i}"
-        h = F.conv2d(t, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"], padding=1)
+        h = rnd(F.conv2d(t, rnd(sd[p + ".conv1.weight"]), sd[p + ".conv1.bias"], padding=1))
         h = F.leaky_relu(_bn(h, sd, p + ".bn", training), LEAKY)
         if training and dropout_masks is not None:
             h = h * dropout_masks[i] / 0.8
+        h = rnd(h)
         if acts is not None:
             acts[p + ".hidden"] = h
-        outs.append(F.conv2d(h, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"]))
+        outs.append(F.conv2d(h, rnd(sd[p + ".conv2.weight"]), sd[p + ".conv2.bias"]))
     return outs

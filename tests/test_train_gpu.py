@@ -30,16 +30,18 @@ def _p8_to_nchw(t):
 
 
 def test_train_forward_layer_by_layer_vs_oracle():
-    """Train-mode forward (batch statistics) against the oracle, layer by layer. The input is large enough (4 x 128 x 128)
-    for every BatchNorm to see >= 64 samples per channel: with a handful of samples (e.g. 2 x 1 x 1 at the deepest level of a
-    32 x 32 input) the normalisation is ill-conditioned and bf16 rounding of the conv output can flip signs."""
+    """Train-mode forward (batch statistics) against the oracle, layer by layer. A randomly initialised net in train mode
+    amplifies perturbations ~370x between the first layer and the trunk (oracle fp32 vs fp64: 5e-8 -> 2e-5; BatchNorm removes
+    the DC part of the signal but not of the noise), so bf16 storage noise (2e-3) saturates when compared with the unrounded
+    oracle. The comparison therefore uses the oracle with bf16 rounding EMULATED at the storage points of the CUDA path
+    (oracle/unet_ref.bf16_ste): what remains is accumulation order. The unrounded comparison is reported, not asserted."""
     from test_path_gpu import _check_logits
     B, H, W, seed = 4, 128, 128, 3
     m, sd, x = _setup(seed, B, H, W)
     outs = m(x.cuda())
     acts = {}
     with torch.no_grad():
-        ref = unet_ref.forward(x, sd, training=True, acts=acts)
+        ref = unet_ref.forward(x, sd, training=True, acts=acts, emulate_bf16=True)
     eng = m._engine
     names = {"inc1.0": "inc1.double_conv.0", "inc1.3": "inc1.double_conv.3", "inc2.0": "inc2.double_conv.0",
              "down1.0": "down1.maxpool_conv.1.double_conv.0", "down2.0": "down2.maxpool_conv.1.double_conv.0",
@@ -78,7 +80,7 @@ def test_train_backward_vs_oracle_autograd():
     loss.backward()
     # oracle
     sdr = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
-    ro = unet_ref.forward(x, sdr, training=True)
+    ro = unet_ref.forward(x, sdr, training=True, emulate_bf16=True)
     sum((o * r).sum() for o, r in zip(ro, R)).backward()
     worst = []
     for name, p in m.named_parameters():
