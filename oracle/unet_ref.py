@@ -160,8 +160,10 @@ def _id(t):
     return t
 
 
-def _double_conv(x, sd, p, training, acts=None, rnd=_id):
-    x = rnd(F.conv2d(x, rnd(sd[p + ".0.weight"]), sd[p + ".0.bias"], padding=1))
+def _double_conv(x, sd, p, training, acts=None, rnd=_id, first_fp32=False):
+    # first_fp32: the CUDA path keeps the 1 -> 16 stem convolution's weights in fp32 (direct kernel, not tensor cores)
+    w0 = sd[p + ".0.weight"] if first_fp32 else rnd(sd[p + ".0.weight"])
+    x = rnd(F.conv2d(x, w0, sd[p + ".0.bias"], padding=1))
     x = rnd(F.relu(_bn(x, sd, p + ".1", training)))
     if acts is not None:
         acts[p + ".0"] = x
@@ -189,7 +191,7 @@ def _up(x1, x2, sd, name, training, crop_first, acts=None, rnd=_id):
 def trunk(x, sd, training=False, crop_first=True, acts=None, rnd=_id):
     """unet.py:101-115 -- everything before the heads."""
     sd = _strip(sd)
-    x1 = _double_conv(x, sd, "inc1.double_conv", training, acts, rnd)
+    x1 = _double_conv(x, sd, "inc1.double_conv", training, acts, rnd, first_fp32=True)
     x1 = _double_conv(x1, sd, "inc2.double_conv", training, acts, rnd)
     x2 = _double_conv(F.max_pool2d(x1, 2), sd, "down1.maxpool_conv.1.double_conv", training, acts, rnd)
     x3 = _double_conv(F.max_pool2d(x2, 2), sd, "down2.maxpool_conv.1.double_conv", training, acts, rnd)
