@@ -58,41 +58,73 @@ __device__ __forceinline__ float drop_scale(unsigned long long seed, unsigned lo
   return u >= p ? 1.f / (1.f - p) : 0.f;
 }
 
-// ------------------------------------------------------------------------------------------- statistics
-__global__ void __launch_bounds__(256) bn_stats_kernel(P8View z, int N, int HW, double* __restrict__ sum,
-                                                       double* __restrict__ sumsq) {
-  const int plane = blockIdx.x;
-  float s[8], q[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  const long long total = static_cast<long long>(N) * HW;
-  for (long long e = static_cast<long long>(blockIdx.y) * 256 + threadIdx.x; e < total; e += static_cast<long long>(gridDim.y) * 256) {
-    const int n = static_cast<int>(e / HW);
-    const int pix = static_cast<int>(e - static_cast<long long>(n) * HW);
-    float v[8];
-    unpack8(z.ptr[(static_cast<size_t>(n) * z.planes + z.plane_off + plane) * HW + pix], v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i] += v[i];
-      q[i] += v[i] * v[i];
-    }
-  }
-  __shared__ double red[16][8];
+// ------------------------------------------------------------------------------------------- common pieces
+// All BatchNorm-side kernels use the same decomposition: blockIdx.y = 8-channel plane, blockIdx.z = image, blockIdx.x
+// strides over the pixels (or 2x2 pixel blocks) of that plane. Consecutive threads touch consecutive 16-byte vectors
+// (512 contiguous bytes per warp and load), the per-channel constants are block-uniform, and no integer division is
+// needed on the per-pixel path.
+__device__ __forceinline__ void unpack8u(const uint4& u, float* v) {   // bf16 -> fp32 is a 16-bit shift
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+  v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ void load8f(const float* __restrict__ src, float* dst) {
+  const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+  dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w; dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+}
+
+// block-wide sum of 16 per-thread fp32 partials (8 channels x 2 statistics) -> fp64 atomics
+__device__ __forceinline__ void block_reduce16(const float* a, const float* b, double* __restrict__ ga, double* __restrict__ gb,
+                                               int c0, double (*red)[8]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    double v = static_cast<double>(i < 8 ? s[i] : q[i - 8]);
+    float v = i < 8 ? a[i] : b[i - 8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[i][warp] = v;
+    if (lane == 0) red[i][warp] = static_cast<double>(v);
   }
   __syncthreads();
   if (threadIdx.x < 16) {
     double v = 0.0;
+#pragma unroll
     for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
-    const int c = plane * 8 + (threadIdx.x & 7);
-    atomicAdd((threadIdx.x < 8 ? sum : sumsq) + c, v);
+    atomicAdd((threadIdx.x < 8 ? ga : gb) + c0 + (threadIdx.x & 7), v);
   }
+}
+
+// ------------------------------------------------------------------------------------------- statistics
+__global__ void __launch_bounds__(256) bn_stats_kernel(P8View z, int HW, double* __restrict__ sum, double* __restrict__ sumsq) {
+  const int plane = blockIdx.y, n = blockIdx.z;
+  const uint4* __restrict__ zb = z.ptr + (static_cast<size_t>(n) * z.planes + z.plane_off + plane) * HW;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  const int stride = gridDim.x * 256;
+  int e = blockIdx.x * 256 + threadIdx.x;
+  for (; e + stride < HW; e += 2 * stride) {          // two independent 16-byte loads in flight per thread
+    const uint4 u0 = zb[e], u1 = zb[e + stride];
+    float v[8], w[8];
+    unpack8u(u0, v);
+    unpack8u(u1, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] += v[i] + w[i];
+      q[i] = fmaf(v[i], v[i], fmaf(w[i], w[i], q[i]));
+    }
+  }
+  if (e < HW) {
+    float v[8];
+    unpack8u(zb[e], v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] += v[i];
+      q[i] = fmaf(v[i], v[i], q[i]);
+    }
+  }
+  __shared__ double red[16][8];
+  block_reduce16(s, q, sum, sumsq, plane * 8, red);
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, int C, double count,
@@ -131,49 +163,57 @@ struct BnActParams {
   int act;
   float drop_p;
   unsigned long long seed;
+  const unsigned long long* seed_dev;
 };
 
+template <bool POOL>
 __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
-  // one thread per (n, plane, 2x2 pixel block); partial blocks at odd H / W are masked
-  const int bw = (p.W + 1) >> 1;
-  const int hw2 = ((p.H + 1) >> 1) * bw;
-  const long long total = static_cast<long long>(p.N) * p.planes * hw2;
-  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (t >= total) return;
-  const int b = static_cast<int>(t % hw2);
-  const long long r = t / hw2;
-  const int plane = static_cast<int>(r % p.planes);
-  const int n = static_cast<int>(r / p.planes);
-  const int by = b / bw, bx = b - by * bw;
+  const int plane = blockIdx.y, n = blockIdx.z;
+  const int HW = p.H * p.W;
   float sc[8], sh[8];
+  load8f(p.scale + plane * 8, sc);
+  load8f(p.shift + plane * 8, sh);
+  const uint4* __restrict__ zb = p.z.ptr + (static_cast<size_t>(n) * p.z.planes + p.z.plane_off + plane) * HW;
+  uint4* __restrict__ ob = p.out ? p.out + (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * HW : nullptr;
+  const int stride = gridDim.x * 256;
+  if (!POOL) {
+    const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
+    const unsigned long long ebase = (static_cast<unsigned long long>(n) * p.planes + plane) * 8;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < HW; e += stride) {
+      float v[8];
+      unpack8u(zb[e], v);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    sc[i] = p.scale[plane * 8 + i];
-    sh[i] = p.shift[plane * 8 + i];
-  }
-  float mx[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
-  const size_t HW = static_cast<size_t>(p.H) * p.W;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int y = 2 * by + (k >> 1), x = 2 * bx + (k & 1);
-    if (y >= p.H || x >= p.W) continue;
-    const size_t pix = static_cast<size_t>(y) * p.W + x;
-    float v[8];
-    unpack8(p.z.ptr[(static_cast<size_t>(n) * p.z.planes + p.z.plane_off + plane) * HW + pix], v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float a = act_fwd(v[i] * sc[i] + sh[i], p.act);
-      if (p.drop_p > 0.f)
-        a *= drop_scale(p.seed, ((static_cast<unsigned long long>(n) * p.planes + plane) * 8 + i) * HW + pix, p.drop_p);
-      v[i] = bf16r(a);
-      mx[i] = fmaxf(mx[i], v[i]);
+      for (int i = 0; i < 8; ++i) {
+        float a = act_fwd(fmaf(v[i], sc[i], sh[i]), p.act);
+        if (p.drop_p > 0.f) a *= drop_scale(seed, (ebase + i) * HW + e, p.drop_p);
+        v[i] = a;
+      }
+      ob[e] = pack8(v);
     }
-    if (p.out) p.out[(static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * HW + pix] = pack8(v);
+  } else {
+    const int bw = p.W >> 1, hw2 = (p.H >> 1) * bw;
+    uint4* __restrict__ pb = p.pool + (static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * hw2;
+    for (int b = blockIdx.x * 256 + threadIdx.x; b < hw2; b += stride) {
+      const int by = b / bw, bx = b - by * bw;
+      const int i00 = 2 * by * p.W + 2 * bx;
+      const uint4 u[4] = {zb[i00], zb[i00 + 1], zb[i00 + p.W], zb[i00 + p.W + 1]};
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v[8];
+        unpack8u(u[k], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = bf16r(act_fwd(fmaf(v[i], sc[i], sh[i]), p.act));
+          mx[i] = fmaxf(mx[i], v[i]);
+        }
+        if (ob) ob[i00 + (k >> 1) * p.W + (k & 1)] = pack8(v);
+      }
+      pb[b] = pack8(mx);
+    }
   }
-  if (p.pool)   // even H, W guaranteed by the host check
-    p.pool[(static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * hw2 + b] = pack8(mx);
 }
 
 // ------------------------------------------------------------------------------------------- backward
@@ -189,6 +229,7 @@ struct BnActBwdParams {
   int act;
   float drop_p;
   unsigned long long seed;
+  const unsigned long long* seed_dev;
   double* s1;               // [C] sum g          (reduce: out, apply: in)
   double* s2;               // [C] sum g * xhat
   uint4* dz;                // apply: output
@@ -196,128 +237,175 @@ struct BnActBwdParams {
   double count;
 };
 
-// g (gradient wrt the pre-activation BN output) and xhat for the 2x2 block handled by this thread
-__device__ __forceinline__ void bwd_block(const BnActBwdParams& p, int n, int plane, int by, int bx, float (&g)[4][8],
-                                          float (&xh)[4][8]) {
-  const size_t HW = static_cast<size_t>(p.H) * p.W;
-  const int hw2w = p.W >> 1;
-  float a[4][8], pre[4][8], dsc[4][8];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int y = 2 * by + (k >> 1), x = 2 * bx + (k & 1);
-    if (y >= p.H || x >= p.W) {                      // masked pixel of a partial block: contributes nothing
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a[k][i] = -INFINITY; pre[k][i] = 0.f; dsc[k][i] = 0.f; g[k][i] = 0.f; xh[k][i] = 0.f;
-      }
-      continue;
-    }
-    const size_t pix = static_cast<size_t>(y) * p.W + x;
-    float v[8];
-    unpack8(p.z.ptr[(static_cast<size_t>(n) * p.z.planes + p.z.plane_off + plane) * HW + pix], v);
-    float d[8];
-    if (p.dA.ptr) unpack8(p.dA.ptr[(static_cast<size_t>(n) * p.dA.planes + p.dA.plane_off + plane) * HW + pix], d);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = plane * 8 + i;
-      pre[k][i] = v[i] * p.scale[c] + p.shift[c];
-      xh[k][i] = (v[i] - p.mean[c]) * p.invstd[c];
-      dsc[k][i] = p.drop_p > 0.f
-                      ? drop_scale(p.seed, ((static_cast<unsigned long long>(n) * p.planes + plane) * 8 + i) * HW + pix, p.drop_p)
-                      : 1.f;
-      a[k][i] = bf16r(act_fwd(pre[k][i], p.act) * dsc[k][i]);
-      g[k][i] = p.dA.ptr ? d[i] : 0.f;
-    }
-  }
-  if (p.dP.ptr) {
-    float dp[8];
-    unpack8(p.dP.ptr[(static_cast<size_t>(n) * p.dP.planes + p.dP.plane_off + plane) * (HW >> 2) + static_cast<size_t>(by) * hw2w + bx], dp);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int best = 0;                                   // first maximum in window order (torch max_pool2d)
-#pragma unroll
-      for (int k = 1; k < 4; ++k)
-        if (a[k][i] > a[best][i]) best = k;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k == best) g[k][i] += dp[i];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[k][i] *= act_grad(pre[k][i], p.act) * dsc[k][i];
-}
-
-__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwdParams p) {
-  const int plane = blockIdx.x;
-  const int bw = (p.W + 1) >> 1;
-  const int hw2 = ((p.H + 1) >> 1) * bw;
-  const long long total = static_cast<long long>(p.N) * hw2;
-  float s1[8], s2[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  for (long long e = static_cast<long long>(blockIdx.y) * 256 + threadIdx.x; e < total; e += static_cast<long long>(gridDim.y) * 256) {
-    const int n = static_cast<int>(e / hw2);
-    const int b = static_cast<int>(e - static_cast<long long>(n) * hw2);
-    const int by = b / bw, bx = b - by * bw;
-    float g[4][8], xh[4][8];
-    bwd_block(p, n, plane, by, bx, g, xh);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s1[i] += g[k][i];
-        s2[i] += g[k][i] * xh[k][i];
-      }
-  }
-  __shared__ double red[16][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    double v = static_cast<double>(i < 8 ? s1[i] : s2[i - 8]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[i][warp] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 16) {
-    double v = 0.0;
-    for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
-    atomicAdd((threadIdx.x < 8 ? p.s1 : p.s2) + plane * 8 + (threadIdx.x & 7), v);
-  }
-}
-
-__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnActBwdParams p) {
-  const int bw = (p.W + 1) >> 1;
-  const int hw2 = ((p.H + 1) >> 1) * bw;
-  const long long total = static_cast<long long>(p.N) * p.planes * hw2;
-  const long long t = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (t >= total) return;
-  const int b = static_cast<int>(t % hw2);
-  const long long r = t / hw2;
-  const int plane = static_cast<int>(r % p.planes);
-  const int n = static_cast<int>(r / p.planes);
-  const int by = b / bw, bx = b - by * bw;
-  float g[4][8], xh[4][8];
-  bwd_block(p, n, plane, by, bx, g, xh);
-  float m1[8], m2[8], sc[8];
+// Gradient g wrt the BatchNorm output for one pixel (8 channels): g = dA * act'(pre) * dropout scale.
+__device__ __forceinline__ void bwd_pixel(const BnActBwdParams& p, const float* v, const float* d, const float* sc, const float* sh,
+                                          unsigned long long seed, unsigned long long ebase, int HW, int e, float* g) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = plane * 8 + i;
-    m1[i] = static_cast<float>(p.s1[c] / p.count);
-    m2[i] = static_cast<float>(p.s2[c] / p.count);
-    sc[i] = p.scale[c];
+    const float pre = fmaf(v[i], sc[i], sh[i]);
+    float m = act_grad(pre, p.act);
+    if (p.drop_p > 0.f) m *= drop_scale(seed, (ebase + i) * HW + e, p.drop_p);
+    g[i] = d[i] * m;
   }
-  const size_t HW = static_cast<size_t>(p.H) * p.W;
+}
+
+// Same for a 2x2 block whose pooled gradient dp is routed to the first maximum of the (bf16) activation.
+__device__ __forceinline__ void bwd_block4(const BnActBwdParams& p, const float (&v)[4][8], const float (&d)[4][8], const float* dp,
+                                           const float* sc, const float* sh, float (&g)[4][8]) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int y = 2 * by + (k >> 1), x = 2 * bx + (k & 1);
-    if (y >= p.H || x >= p.W) continue;
-    float o[8];
+  for (int i = 0; i < 8; ++i) {
+    float pre[4], a[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = sc[i] * (g[k][i] - m1[i] - xh[k][i] * m2[i]);
-    p.dz[(static_cast<size_t>(n) * p.dz_planes + p.dz_plane_off + plane) * HW + static_cast<size_t>(y) * p.W + x] = pack8(o);
+    for (int k = 0; k < 4; ++k) {
+      pre[k] = fmaf(v[k][i], sc[i], sh[i]);
+      a[k] = bf16r(act_fwd(pre[k], p.act));
+    }
+    // first maximum in window order (torch max_pool2d): strict > when moving to a later element
+    const bool b1 = a[1] > a[0];
+    const float m01 = b1 ? a[1] : a[0];
+    const bool b3 = a[3] > a[2];
+    const float m23 = b3 ? a[3] : a[2];
+    const bool hi = m23 > m01;
+    const int best = hi ? (b3 ? 3 : 2) : (b1 ? 1 : 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k][i] = (d[k][i] + (best == k ? dp[i] : 0.f)) * act_grad(pre[k], p.act);
+  }
+}
+
+// reduce: s1 = sum g, s2 = sum g * xhat (xhat = (z - mean) * invstd, accumulated as sum g*z and combined per block)
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwdParams p) {
+  const int plane = blockIdx.y, n = blockIdx.z;
+  const int HW = p.H * p.W;
+  float sc[8], sh[8];
+  load8f(p.scale + plane * 8, sc);
+  load8f(p.shift + plane * 8, sh);
+  const uint4* __restrict__ zb = p.z.ptr + (static_cast<size_t>(n) * p.z.planes + p.z.plane_off + plane) * HW;
+  const uint4* __restrict__ db = p.dA.ptr ? p.dA.ptr + (static_cast<size_t>(n) * p.dA.planes + p.dA.plane_off + plane) * HW : nullptr;
+  float s1[8], t2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = t2[i] = 0.f;
+  const int stride = gridDim.x * 256;
+  if (!POOL) {
+    const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
+    const unsigned long long ebase = (static_cast<unsigned long long>(n) * p.planes + plane) * 8;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < HW; e += stride) {
+      float v[8], d[8], g[8];
+      const uint4 zu = zb[e], du = db[e];
+      unpack8u(zu, v);
+      unpack8u(du, d);
+      bwd_pixel(p, v, d, sc, sh, seed, ebase, HW, e, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += g[i];
+        t2[i] = fmaf(g[i], v[i], t2[i]);
+      }
+    }
+  } else {
+    const int bw = p.W >> 1, hw2 = (p.H >> 1) * bw;
+    const uint4* __restrict__ pb = p.dP.ptr + (static_cast<size_t>(n) * p.dP.planes + p.dP.plane_off + plane) * hw2;
+    for (int b = blockIdx.x * 256 + threadIdx.x; b < hw2; b += stride) {
+      const int by = b / bw, bx = b - by * bw;
+      const int i00 = 2 * by * p.W + 2 * bx;
+      float v[4][8], d[4][8], g[4][8], dp[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = i00 + (k >> 1) * p.W + (k & 1);
+        unpack8u(zb[e], v[k]);
+        if (db) {
+          unpack8u(db[e], d[k]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[k][i] = 0.f;
+        }
+      }
+      unpack8u(pb[b], dp);
+      bwd_block4(p, v, d, dp, sc, sh, g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += g[k][i];
+          t2[i] = fmaf(g[k][i], v[k][i], t2[i]);
+        }
+    }
+  }
+  // sum g * xhat = invstd * (sum g*z - mean * sum g): linear, so every block adds its own share
+  float mean[8], istd[8], s2[8];
+  load8f(p.mean + plane * 8, mean);
+  load8f(p.invstd + plane * 8, istd);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s2[i] = istd[i] * (t2[i] - mean[i] * s1[i]);
+  __shared__ double red[16][8];
+  block_reduce16(s1, s2, p.s1, p.s2, plane * 8, red);
+}
+
+// apply: dz = scale * (g - s1/M - xhat * s2/M) = scale * g + cb * z + ca  with per-channel constants ca, cb
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnActBwdParams p) {
+  const int plane = blockIdx.y, n = blockIdx.z;
+  const int HW = p.H * p.W;
+  __shared__ float cst[2][8];
+  if (threadIdx.x < 8) {
+    const int c = plane * 8 + threadIdx.x;
+    const float m1 = static_cast<float>(p.s1[c] / p.count), m2 = static_cast<float>(p.s2[c] / p.count);
+    const float sc = p.scale[c], is = p.invstd[c], mu = p.mean[c];
+    cst[0][threadIdx.x] = sc * (m2 * is * mu - m1);
+    cst[1][threadIdx.x] = -sc * m2 * is;
+  }
+  __syncthreads();
+  float sc[8], sh[8], ca[8], cb[8];
+  load8f(p.scale + plane * 8, sc);
+  load8f(p.shift + plane * 8, sh);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ca[i] = cst[0][i];
+    cb[i] = cst[1][i];
+  }
+  const uint4* __restrict__ zb = p.z.ptr + (static_cast<size_t>(n) * p.z.planes + p.z.plane_off + plane) * HW;
+  const uint4* __restrict__ db = p.dA.ptr ? p.dA.ptr + (static_cast<size_t>(n) * p.dA.planes + p.dA.plane_off + plane) * HW : nullptr;
+  uint4* __restrict__ ob = p.dz + (static_cast<size_t>(n) * p.dz_planes + p.dz_plane_off + plane) * HW;
+  const int stride = gridDim.x * 256;
+  if (!POOL) {
+    const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
+    const unsigned long long ebase = (static_cast<unsigned long long>(n) * p.planes + plane) * 8;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < HW; e += stride) {
+      float v[8], d[8], g[8];
+      const uint4 zu = zb[e], du = db[e];
+      unpack8u(zu, v);
+      unpack8u(du, d);
+      bwd_pixel(p, v, d, sc, sh, seed, ebase, HW, e, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], sc[i], fmaf(v[i], cb[i], ca[i]));
+      ob[e] = pack8(g);
+    }
+  } else {
+    const int bw = p.W >> 1, hw2 = (p.H >> 1) * bw;
+    const uint4* __restrict__ pb = p.dP.ptr + (static_cast<size_t>(n) * p.dP.planes + p.dP.plane_off + plane) * hw2;
+    for (int b = blockIdx.x * 256 + threadIdx.x; b < hw2; b += stride) {
+      const int by = b / bw, bx = b - by * bw;
+      const int i00 = 2 * by * p.W + 2 * bx;
+      float v[4][8], d[4][8], g[4][8], dp[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = i00 + (k >> 1) * p.W + (k & 1);
+        unpack8u(zb[e], v[k]);
+        if (db) {
+          unpack8u(db[e], d[k]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[k][i] = 0.f;
+        }
+      }
+      unpack8u(pb[b], dp);
+      bwd_block4(p, v, d, dp, sc, sh, g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[k][i] = fmaf(g[k][i], sc[i], fmaf(v[k][i], cb[i], ca[i]));
+        ob[i00 + (k >> 1) * p.W + (k & 1)] = pack8(g[k]);
+      }
+    }
   }
 }
 
@@ -409,21 +497,27 @@ static int p8_check(const void* ptr, int planes, int plane_off, int cplanes, con
   return ABC_OK;
 }
 
+// grid.x for the (pixels, plane, image) decomposition: enough blocks to fill the machine, few enough that every
+// thread streams several vectors and the per-block atomics stay negligible
+static int plane_grid_x(long long items, int planes, int N, int per_thread = 1) {
+  long long need = (items + 256ll * per_thread - 1) / (256ll * per_thread);
+  long long cap = (148ll * 16 + static_cast<long long>(planes) * N - 1) / (static_cast<long long>(planes) * N);
+  if (cap < 1) cap = 1;
+  if (need > cap) need = cap;
+  return need < 1 ? 1 : static_cast<int>(need);
+}
+
 extern "C" int abc_bn_stats(const void* z, int N, int H, int W, int planes, int plane_off, int C, double* sum, double* sumsq,
                             void* stream) {
   if (int rc = device_check()) return rc;
-  ABC_REQUIRE(C >= 8 && C % 8 == 0 && N > 0 && H > 0 && W > 0 && sum && sumsq, "abc_bn_stats: bad arguments");
+  ABC_REQUIRE(C >= 8 && C % 8 == 0 && N > 0 && N <= 65535 && H > 0 && W > 0 && sum && sumsq, "abc_bn_stats: bad arguments");
+  ABC_REQUIRE(static_cast<long long>(H) * W < (1ll << 30), "abc_bn_stats: image too large");
   if (int rc = p8_check(z, planes, plane_off, C / 8, "abc_bn_stats")) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ABC_CUDA(cudaMemsetAsync(sum, 0, C * sizeof(double), st));
   ABC_CUDA(cudaMemsetAsync(sumsq, 0, C * sizeof(double), st));
-  const long long total = static_cast<long long>(N) * H * W;
-  int gy = static_cast<int>((total + 256 * 16 - 1) / (256 * 16));
-  const int max_gy = (148 * 8 + C / 8 - 1) / (C / 8);
-  if (gy > max_gy) gy = max_gy;
-  if (gy < 1) gy = 1;
   P8View v{static_cast<const uint4*>(z), planes, plane_off};
-  bn_stats_kernel<<<dim3(C / 8, gy), 256, 0, st>>>(v, N, H * W, sum, sumsq);
+  bn_stats_kernel<<<dim3(plane_grid_x(static_cast<long long>(H) * W, C / 8, N, 4), C / 8, N), 256, 0, st>>>(v, H * W, sum, sumsq);
   return launch_check("bn_stats_kernel");
 }
 
@@ -446,14 +540,25 @@ extern "C" int abc_bn_act(const AbcBnActDesc* d, void* stream) {
   if (int rc = p8_check(d->z, d->z_planes, d->z_plane_off, d->C / 8, "abc_bn_act(z)")) return rc;
   if (d->out) if (int rc = p8_check(d->out, d->out_planes, d->out_plane_off, d->C / 8, "abc_bn_act(out)")) return rc;
   if (d->pool) if (int rc = p8_check(d->pool, d->pool_planes, d->pool_plane_off, d->C / 8, "abc_bn_act(pool)")) return rc;
+  ABC_REQUIRE(d->N <= 65535 && static_cast<long long>(d->H) * d->W < (1ll << 30), "abc_bn_act: N or image too large");
+  ABC_REQUIRE(!(d->pool && d->drop_p > 0.f), "abc_bn_act: dropout and fused max-pool are not combined");
+  ABC_REQUIRE((reinterpret_cast<uintptr_t>(d->scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->shift) & 15) == 0,
+              "abc_bn_act: scale / shift must be 16-byte aligned");
   BnActParams p;
   p.z = P8View{static_cast<const uint4*>(d->z), d->z_planes, d->z_plane_off};
   p.out = static_cast<uint4*>(d->out); p.out_planes = d->out_planes; p.out_plane_off = d->out_plane_off;
   p.pool = static_cast<uint4*>(d->pool); p.pool_planes = d->pool_planes; p.pool_plane_off = d->pool_plane_off;
   p.N = d->N; p.H = d->H; p.W = d->W; p.planes = d->C / 8;
   p.scale = d->scale; p.shift = d->shift; p.act = d->act; p.drop_p = d->drop_p; p.seed = d->seed;
-  const long long total = static_cast<long long>(d->N) * p.planes * ((d->H + 1) / 2) * ((d->W + 1) / 2);
-  bn_act_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  p.seed_dev = reinterpret_cast<const unsigned long long*>(d->seed_dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->pool) {
+    const long long items = static_cast<long long>(d->H / 2) * (d->W / 2);
+    bn_act_kernel<true><<<dim3(plane_grid_x(items, p.planes, d->N), p.planes, d->N), 256, 0, st>>>(p);
+  } else {
+    const long long items = static_cast<long long>(d->H) * d->W;
+    bn_act_kernel<false><<<dim3(plane_grid_x(items, p.planes, d->N, 2), p.planes, d->N), 256, 0, st>>>(p);
+  }
   return launch_check("bn_act_kernel");
 }
 
@@ -468,6 +573,10 @@ extern "C" int abc_bn_act_backward(const AbcBnActBwdDesc* d, void* stream) {
   if (d->dA) if (int rc = p8_check(d->dA, d->dA_planes, d->dA_plane_off, cp, "abc_bn_act_backward(dA)")) return rc;
   if (d->dP) if (int rc = p8_check(d->dP, d->dP_planes, d->dP_plane_off, cp, "abc_bn_act_backward(dP)")) return rc;
   if (int rc = p8_check(d->dz, d->dz_planes, d->dz_plane_off, cp, "abc_bn_act_backward(dz)")) return rc;
+  ABC_REQUIRE(d->N <= 65535 && static_cast<long long>(d->H) * d->W < (1ll << 30), "abc_bn_act_backward: N or image too large");
+  ABC_REQUIRE(!(d->dP && d->drop_p > 0.f), "abc_bn_act_backward: dropout and max-pool routing are not combined");
+  for (const float* q : {d->scale, d->shift, d->mean, d->invstd})
+    ABC_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "abc_bn_act_backward: per-channel vectors must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   BnActBwdParams p;
   p.z = P8View{static_cast<const uint4*>(d->z), d->z_planes, d->z_plane_off};
@@ -476,20 +585,25 @@ extern "C" int abc_bn_act_backward(const AbcBnActBwdDesc* d, void* stream) {
   p.N = d->N; p.H = d->H; p.W = d->W; p.planes = cp;
   p.scale = d->scale; p.shift = d->shift; p.mean = d->mean; p.invstd = d->invstd;
   p.act = d->act; p.drop_p = d->drop_p; p.seed = d->seed;
+  p.seed_dev = reinterpret_cast<const unsigned long long*>(d->seed_dev);
   p.s1 = d->s1; p.s2 = d->s2;
   p.dz = static_cast<uint4*>(d->dz); p.dz_planes = d->dz_planes; p.dz_plane_off = d->dz_plane_off;
   p.count = static_cast<double>(d->N) * d->H * d->W;
   ABC_CUDA(cudaMemsetAsync(d->s1, 0, d->C * sizeof(double), st));
   ABC_CUDA(cudaMemsetAsync(d->s2, 0, d->C * sizeof(double), st));
-  const long long blocks2 = static_cast<long long>(d->N) * ((d->H + 1) / 2) * ((d->W + 1) / 2);
-  int gy = static_cast<int>((blocks2 + 256 * 4 - 1) / (256 * 4));
-  const int max_gy = (148 * 8 + cp - 1) / cp;
-  if (gy > max_gy) gy = max_gy;
-  if (gy < 1) gy = 1;
-  bn_act_bwd_reduce_kernel<<<dim3(cp, gy), 256, 0, st>>>(p);
-  if (int rc = launch_check("bn_act_bwd_reduce_kernel")) return rc;
-  const long long total = blocks2 * cp;
-  bn_act_bwd_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(p);
+  if (d->dP) {
+    const long long items = static_cast<long long>(d->H / 2) * (d->W / 2);
+    const dim3 grid(plane_grid_x(items, cp, d->N), cp, d->N);
+    bn_act_bwd_reduce_kernel<true><<<grid, 256, 0, st>>>(p);
+    if (int rc = launch_check("bn_act_bwd_reduce_kernel")) return rc;
+    bn_act_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(p);
+  } else {
+    const long long items = static_cast<long long>(d->H) * d->W;
+    const dim3 grid(plane_grid_x(items, cp, d->N, 2), cp, d->N);
+    bn_act_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(p);
+    if (int rc = launch_check("bn_act_bwd_reduce_kernel")) return rc;
+    bn_act_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(p);
+  }
   return launch_check("bn_act_bwd_apply_kernel");
 }
 

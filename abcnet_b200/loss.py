@@ -39,40 +39,60 @@ def _desc(logits, targets, type_w, sums, scale, dlogits):
     return d
 
 
+_IDX_CACHE = {}
+
+
+def _s_index(dev):
+    """Device-resident index / constant tensors (created once per device: no host -> device copy inside a CUDA-graph capture)."""
+    t = _IDX_CACHE.get(dev)
+    if t is None:
+        half = [1.0] * 8
+        half[5] = 0.5                                                      # train.py:133 (rho term: 0.5 * exp(-s) + s)
+        t = _IDX_CACHE[dev] = (torch.tensor(_S_INDEX, dtype=torch.long, device=dev),
+                               torch.tensor(half, dtype=torch.float64, device=dev))
+    return t
+
+
+def loss_forward_backward(s, type_w, targets, logits):
+    """Both passes without autograd: returns (total fp64 scalar, 8 weighted parts, dL/ds [10] fp64, 8 dL/dlogits fp32).
+    Everything stays on the device (no host synchronisation), so the call can be captured in a CUDA graph."""
+    _lib.require_device()
+    logits = [z.contiguous() for z in logits]
+    for z in logits:
+        if not (z.is_cuda and z.dtype == torch.float32):
+            raise ValueError("loss inputs must be fp32 CUDA tensors (no CPU fallback)")
+    # kernel target order: atom, type, charge, hs, bond, btype, rho, omega  (= the reference's argument order)
+    if targets[6].dtype != targets[7].dtype:
+        raise ValueError("rho / omega targets must share a dtype (fp32 or fp64, utils.py:91-92)")
+    for i, t in enumerate(targets):
+        want = (torch.float32, torch.float64) if i >= 6 else (torch.float32,)
+        if not (t.is_cuda and t.is_contiguous() and t.dtype in want):
+            raise ValueError(f"target {i}: contiguous CUDA tensor of dtype {want} required")
+    st = _lib.current_stream_ptr()
+    dev = logits[0].device
+    sums = torch.empty(16, dtype=torch.float64, device=dev)
+    check(lib.abc_loss_partials(C.byref(_desc(logits, targets, type_w, sums, None, None)), st), "abc_loss_partials")
+    num, den = sums[:8], sums[8:].clone()
+    den[7] = den[7] + 0.1                                                  # train.py:114
+    raw = num / den
+    idx, half = _s_index(dev)
+    sk = s.detach().double()[idx]
+    u = half * torch.exp(-sk) + sk
+    total = (raw * u).sum()
+    scale = (u / den).float().contiguous()
+    dlogits = [torch.empty_like(z) for z in logits]
+    check(lib.abc_loss_backward(C.byref(_desc(logits, targets, type_w, None, scale, dlogits)), st), "abc_loss_backward")
+    ds = torch.zeros(10, dtype=torch.float64, device=dev)
+    ds[idx] = raw * (1.0 - half * torch.exp(-sk))
+    return total, (raw * u).detach(), ds, dlogits
+
+
 class _HeatmapLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, s, type_w, targets, *logits):
-        _lib.require_device()
-        logits = [z.contiguous() for z in logits]
-        for z in logits:
-            if not (z.is_cuda and z.dtype == torch.float32):
-                raise ValueError("loss inputs must be fp32 CUDA tensors (no CPU fallback)")
-        # kernel target order: atom, type, charge, hs, bond, btype, rho, omega  (= the reference's argument order)
-        if targets[6].dtype != targets[7].dtype:
-            raise ValueError("rho / omega targets must share a dtype (fp32 or fp64, utils.py:91-92)")
-        for i, t in enumerate(targets):
-            want = (torch.float32, torch.float64) if i >= 6 else (torch.float32,)
-            if not (t.is_cuda and t.is_contiguous() and t.dtype in want):
-                raise ValueError(f"target {i}: contiguous CUDA tensor of dtype {want} required")
-        st = _lib.current_stream_ptr()
-        dev = logits[0].device
-        sums = torch.empty(16, dtype=torch.float64, device=dev)
-        check(lib.abc_loss_partials(C.byref(_desc(logits, targets, type_w, sums, None, None)), st), "abc_loss_partials")
-        num, den = sums[:8], sums[8:].clone()
-        den[7] = den[7] + 0.1                                                  # train.py:114
-        raw = num / den
-        sk = s.detach().double()[_S_INDEX]
-        half = torch.ones(8, dtype=torch.float64, device=dev)
-        half[5] = 0.5                                                          # train.py:133
-        u = half * torch.exp(-sk) + sk
-        total = (raw * u).sum()
-        scale = (u / den).float().contiguous()
-        dlogits = [torch.empty_like(z) for z in logits]
-        check(lib.abc_loss_backward(C.byref(_desc(logits, targets, type_w, None, scale, dlogits)), st), "abc_loss_backward")
-        ds = torch.zeros(10, dtype=torch.float64, device=dev)
-        ds[_S_INDEX] = raw * (1.0 - half * torch.exp(-sk))
+        total, parts, ds, dlogits = loss_forward_backward(s, type_w, targets, logits)
         ctx.save_for_backward(ds.to(s.dtype), *dlogits)
-        ctx.parts = (raw * u).detach()
+        ctx.parts = parts
         return total
 
     @staticmethod

@@ -23,6 +23,25 @@ TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 _seed_counter = itertools.count(0x5EED)
 
 
+timing = None   # set to a list to collect (label, start event, end event) around every conv / wgrad launch (tools only)
+
+
+class _timed:
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        if timing is not None:
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if timing is not None:
+            self.b.record()
+            timing.append((self.label, self.a, self.b))
+        return False
+
+
 def _st():
     return _lib.current_stream_ptr()
 
@@ -87,7 +106,8 @@ def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_sca
         d.out_H, d.out_W = H, W
     if pool is not None:
         d.pool_out, d.pool_planes, d.pool_plane_off = pool.data_ptr(), pool.shape[1], pool_plane_off
-    check(lib.abc_conv_igemm(C.byref(d), _st()), "abc_conv_igemm")
+    with _timed(f"conv {pk.cin}->{pk.cout} t{len(pk.taps)} @{H}x{W} nt{pk.n_tile}"):
+        check(lib.abc_conv_igemm(C.byref(d), _st()), "abc_conv_igemm")
 
 
 def wgrad(dz, dz_off, cout, a, a_off, cin, taps):
@@ -101,7 +121,8 @@ def wgrad(dz, dz_off, cout, a, a_off, cin, taps):
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
     d.dw = dw.data_ptr()
-    check(lib.abc_conv_wgrad(C.byref(d), _st()), "abc_conv_wgrad")
+    with _timed(f"wgrad {cin}->{cout} t{len(taps)} @{H}x{W}"):
+        check(lib.abc_conv_wgrad(C.byref(d), _st()), "abc_conv_wgrad")
     return dw
 
 
@@ -179,7 +200,8 @@ class TrainEngine:
             d.pool, d.pool_planes, d.pool_plane_off = pool.data_ptr(), pool.shape[1], 0
         d.N, d.H, d.W, d.C = N, H, W, Cc
         d.scale, d.shift = st[0].data_ptr(), st[1].data_ptr()
-        d.act, d.drop_p, d.seed = act, drop_p, seed
+        d.act, d.drop_p, d.seed = act, drop_p, 0
+        d.seed_dev = seed.data_ptr() if (seed is not None and drop_p > 0) else None
         check(lib.abc_bn_act(C.byref(d), _st()), "abc_bn_act")
         return st
 
@@ -196,7 +218,8 @@ class TrainEngine:
         d.dz, d.dz_planes, d.dz_plane_off = dz.data_ptr(), dz.shape[1], 0
         d.N, d.H, d.W, d.C = N, H, W, Cc
         d.scale, d.shift, d.mean, d.invstd = [t.data_ptr() for t in st]
-        d.act, d.drop_p, d.seed = act, drop_p, seed
+        d.act, d.drop_p, d.seed = act, drop_p, 0
+        d.seed_dev = seed.data_ptr() if (seed is not None and drop_p > 0) else None
         d.s1, d.s2 = s1.data_ptr(), s2.data_ptr()
         check(lib.abc_bn_act_backward(C.byref(d), _st()), "abc_bn_act_backward")
         return s1, s2
@@ -269,7 +292,12 @@ class TrainEngine:
         x = x.contiguous().view(torch.uint8) if u8 else x.contiguous().float()
         B, _, H, W = x.shape
         plan = self._plan(H, W)
-        sv = self.saved = dict(x=x, u8=u8, B=B, H=H, W=W, plan=plan, units={}, seed=next(_seed_counter) * 0x9E3779B97F4A7C15 % (1 << 63))
+        # dropout stream: a device-resident counter, advanced by a device op so that CUDA-graph replays draw new masks
+        seed_t = self.bufs.get("seed")
+        if seed_t is None:
+            seed_t = self.bufs["seed"] = torch.full((1,), next(_seed_counter), dtype=torch.int64, device=x.device)
+        seed_t.add_(0x5DEECE66D)
+        sv = self.saved = dict(x=x, u8=u8, B=B, H=H, W=W, plan=plan, units={}, seed=seed_t)
         for u in plan:
             h, w = u["hw"]
             if "up" in u:                                            # up-sampling conv: 4 sub-pixel phases, bias, no BN
@@ -300,7 +328,7 @@ class TrainEngine:
             pool = self._tensor(u["pool"], B, H, W) if u["pool"] else None
             bn = u["bn"]
             st = self._bn_forward("bn:" + u["name"], z, 0, cout, (bn.weight, bn.bias, bn.running_mean, bn.running_var), 1,
-                                  dst, u["dst_off"], pool, 0.0, 0)
+                                  dst, u["dst_off"], pool, 0.0, None)
             bn.num_batches_tracked += 1
             sv["units"][u["name"]] = dict(z=z, st=st)
         # heads: fused conv1 (N = 128 * heads) -> BN -> LeakyReLU -> Dropout -> per-head 1x1
@@ -400,7 +428,7 @@ class TrainEngine:
                 dA = self._tensor(u["dst"], B, H, W, (B, cout // 8, h, w, 8), grad=True)
             dP = self._tensor(u["pool"], B, H, W, grad=True) if u["pool"] else None
             dz = self.buf("g:z:" + u["name"], (B, cout // 8, h, w, 8))
-            s1, s2 = self._bn_backward("bn:" + u["name"], su["z"], cout, su["st"], 1, dA, u["dst_off"] if dA is not None else 0, dP, dz, 0.0, 0)
+            s1, s2 = self._bn_backward("bn:" + u["name"], su["z"], cout, su["st"], 1, dA, u["dst_off"] if dA is not None else 0, dP, dz, 0.0, None)
             sink(u["bn"].weight, s2.float())
             sink(u["bn"].bias, s1.float())
             sink(u["conv"].bias, torch.zeros(cout, device=dev))

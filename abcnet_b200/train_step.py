@@ -1,0 +1,136 @@
+"""One whole training iteration as a single replayable unit: forward (batch-statistics BatchNorm, dropout), the fused
+losses, the full backward, the bucketed gradient all-reduce and the optimiser step.
+
+Replaces the body of the reference's training loop, ``/root/reference/src/train.py:94-141`` (single process) and
+``/root/reference/src/multi_gpu_train2.py:139-196`` (one rank of the data-parallel job):
+
+    outs = model(imgs); ...eight losses...; optimizer.zero_grad(); loss.backward(); optimizer.step()
+
+The step is enqueued without any host synchronisation and -- by default -- captured once into a CUDA graph, so that the
+~1000 kernel launches of an iteration cost one ``cudaGraphLaunch`` on the host. ``model(x)`` + ``HeatmapLoss`` +
+``loss.backward()`` (autograd) remain available and produce the same numbers; this class is the fast path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .loss import ATOM_TYPE_WEIGHTS, loss_forward_backward
+
+
+class TrainStep:
+    """step = TrainStep(model, optimizer, class_weights=True, buckets=None, use_graph=True)
+    loss = step(imgs, targets)        # imgs [B,1,H,W] fp32/uint8 CUDA, targets = the 8 dense maps of utils.collate_fn
+
+    ``optimizer`` may be None (gradients are left in ``p.grad``). With ``use_graph`` the optimiser must be constructed
+    with ``capturable=True`` to be part of the graph; otherwise it is stepped eagerly after the replay.
+    ``buckets`` is an ``abcnet_b200.ddp.GradBuckets`` over ``model.parameters()`` for data-parallel runs."""
+
+    def __init__(self, model, optimizer=None, class_weights: bool = True, buckets=None, use_graph: bool = True):
+        self.model, self.opt, self.buckets, self.use_graph = model, optimizer, buckets, use_graph
+        dev = model.s.device
+        if dev.type != "cuda":
+            raise RuntimeError("abcnet_b200.TrainStep needs the model on a CUDA (sm_100) device; there is no CPU path")
+        _lib.require_device()
+        self.type_w = torch.tensor(ATOM_TYPE_WEIGHTS, dtype=torch.float32, device=dev) if class_weights else None
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        if buckets is None:
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+        self.graph = None
+        self._x = self._tg = None
+        self.loss = torch.zeros((), dtype=torch.float64, device=dev)
+        self.parts = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._opt_in_graph = optimizer is not None and bool(optimizer.defaults.get("capturable", False))
+
+    # ------------------------------------------------------------------ the enqueued work
+    def _sink(self, p, g):
+        if not p.requires_grad:
+            return
+        if self.buckets is not None:
+            p.grad.add_(g.to(p.grad.dtype).view_as(p.grad))
+            self.buckets.grad_ready(p)
+        else:
+            p.grad.copy_(g.view_as(p.grad))
+
+    def _enqueue(self, x, targets, with_opt):
+        m = self.model
+        eng = m._train_engine()
+        if self.buckets is not None:
+            self.buckets.zero()
+        outs = eng.forward(x)
+        total, parts, ds, dlogits = loss_forward_backward(m.s, self.type_w, list(targets), outs)
+        self.loss.copy_(total)
+        self.parts.copy_(parts)
+        self._sink(m.s, ds.to(m.s.dtype))
+        eng.backward(dlogits, self._sink)
+        if self.buckets is not None:
+            self.buckets.finish()
+        if with_opt and self.opt is not None:
+            self.opt.step()
+
+    # ------------------------------------------------------------------ public
+    @torch.no_grad()
+    def __call__(self, x, targets: Sequence[torch.Tensor]):
+        if not self.model.training:
+            raise RuntimeError("TrainStep: call model.train() first")
+        if not self.use_graph:
+            self._enqueue(x, targets, True)
+            return self.loss
+        if self.graph is None:
+            self._capture(x, targets)
+        else:
+            if x.shape != self._x.shape or x.dtype != self._x.dtype:
+                raise ValueError("TrainStep (graph mode): the batch shape / dtype is fixed at the first call")
+            if x.data_ptr() != self._x.data_ptr():
+                self._x.copy_(x, non_blocking=True)
+            for dst, src in zip(self._tg, targets):
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        if self.opt is not None and not self._opt_in_graph:
+            self.opt.step()
+        return self.loss
+
+    def _capture(self, x, targets):
+        # static input buffers; the first batch is also used for the warm-up iterations (parameters are restored after)
+        self._x = x.clone()
+        self._tg = [t.clone() for t in targets]
+        state = [p.detach().clone() for p in self.model.parameters()]
+        bufs = [b.detach().clone() for b in self.model.buffers()]
+        opt_in = self._opt_in_graph
+        opt_state = {}
+        if opt_in:                                         # optimiser state must exist before capture (lazy init is not replayable)
+            opt_state = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()} for p, st in self.opt.state.items()}
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up outside capture: lazy attribute / allocator work
+            for _ in range(2):
+                self._enqueue(self._x, self._tg, opt_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():                              # undo the BatchNorm running-statistics updates of the warm-up
+            for p, s in zip(self.model.parameters(), state):
+                p.copy_(s)
+            for b, s in zip(self.model.buffers(), bufs):
+                b.copy_(s)
+            if opt_in:                                     # ... and the optimiser's moments / step counters
+                for p, st in self.opt.state.items():
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            if p in opt_state:
+                                v.copy_(opt_state[p][k])
+                            else:
+                                v.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue(self._x, self._tg, self._opt_in_graph)
+
+
+def make_optimizer(model, lr: float = 2.5e-4, weight_decay: float = 1e-8, capturable: bool = True):
+    """The reference's optimiser (``train.py:55``: Adam, lr 2.5e-4, L2 1e-8), graph-capturable."""
+    return torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr, weight_decay=weight_decay,
+                            capturable=capturable, foreach=True)

@@ -202,6 +202,7 @@ typedef struct AbcBnActDesc {
   const float* scale; const float* shift;
   int act;                                         /* 0 none, 1 ReLU, 2 LeakyReLU(0.01) */
   float drop_p; uint64_t seed;                     /* counter-based dropout, p = 0 disables */
+  const uint64_t* seed_dev;                        /* optional device word added to seed at run time (CUDA-graph replays) */
 } AbcBnActDesc;
 ABC_API int abc_bn_act(const AbcBnActDesc* desc, void* stream);
 typedef struct AbcBnActBwdDesc {
@@ -213,6 +214,7 @@ typedef struct AbcBnActBwdDesc {
   const float* scale; const float* shift; const float* mean; const float* invstd;
   int act; float drop_p; uint64_t seed;
   double* s1; double* s2;                          /* [C] each */
+  const uint64_t* seed_dev;                        /* as in AbcBnActDesc */
 } AbcBnActBwdDesc;
 ABC_API int abc_bn_act_backward(const AbcBnActBwdDesc* desc, void* stream);
 /* fp32 NCHW -> bf16 P8 with zero-padded channels (dlogits -> tensor-core operand). */

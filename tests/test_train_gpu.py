@@ -165,3 +165,55 @@ def test_dropout_is_consistent_between_forward_and_backward():
     assert 0.70 < keep < 0.90, keep                      # ~80 % kept (LeakyReLU output is never exactly 0 otherwise)
     sum(o.sum() for o in outs).backward()
     assert all(torch.isfinite(p.grad).all() for n, p in m.named_parameters() if n != "s")
+
+
+def _targets(seed, B, h, w):
+    return [torch.from_numpy(t).cuda().contiguous() for t in synth.dense_targets(seed, B, h, w)]
+
+
+def test_train_step_matches_autograd_path_and_graph_replays():
+    """abcnet_b200.TrainStep (no autograd; eager and CUDA-graph replay) against model(x) + HeatmapLoss + loss.backward():
+    same loss, same gradients (fp32 atomics in the wgrad kernels -> 1e-4 relative), and after two optimiser steps the
+    same parameters. Dropout off so that the three runs see the same function."""
+    import abcnet_b200
+    B, H, W, seed = 2, 64, 64, 11
+    tg = None
+    results = {}
+    for mode in ("autograd", "eager", "graph"):
+        m, sd, x = _setup(seed, B, H, W)
+        xg = x.cuda()
+        tg = tg or _targets(seed, B, H // 4, W // 4)
+        if mode == "autograd":
+            opt = torch.optim.Adam(m.parameters(), lr=2.5e-4, weight_decay=1e-8)
+            crit = abcnet_b200.HeatmapLoss(class_weights=True)
+            losses = []
+            for it in range(2):
+                opt.zero_grad(set_to_none=True)
+                loss = crit(m(xg), tg, m.s)
+                loss.backward()
+                if it == 0:
+                    g0 = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+                opt.step()
+                losses.append(loss.item())
+        else:
+            opt = abcnet_b200.make_optimizer(m, capturable=mode == "graph")
+            step = abcnet_b200.TrainStep(m, opt, class_weights=True, use_graph=mode == "graph")
+            losses = []
+            for it in range(2):
+                losses.append(step(xg, tg).item())
+                if it == 0:
+                    torch.cuda.synchronize()
+                    g0 = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+        torch.cuda.synchronize()
+        results[mode] = (losses, g0, {n: p.detach().clone() for n, p in m.named_parameters()},
+                         {n: b.detach().clone() for n, b in m.named_buffers()})
+    la, ga, pa, ba = results["autograd"]
+    for mode in ("eager", "graph"):
+        l, g, p, b = results[mode]
+        assert abs(l[0] - la[0]) <= 1e-6 * abs(la[0]), (mode, l, la)
+        assert abs(l[1] - la[1]) <= 2e-3 * abs(la[1]), (mode, l, la)            # after one Adam step (sign-like updates)
+        for n in ga:
+            assert _rel(g[n], ga[n]) <= 1e-3 or ga[n].abs().max().item() == 0.0, (mode, n, _rel(g[n], ga[n]))
+        for n in ba:                                                               # running statistics: exactly two updates
+            assert _rel(b[n].float(), ba[n].float()) <= 1e-2, (mode, n)      # 2nd update sees a (noise-amplified) step-2 forward
+        assert int(b["inc1.double_conv.1.num_batches_tracked"]) == 2
