@@ -17,7 +17,7 @@ EXPORTS = (
     "abc_conv3x3_c1", "abc_conv3x3_c1_u8", "abc_conv_igemm", "abc_conv_wpack_bytes", "abc_decode_peaks",
     "abc_loss_partials", "abc_loss_backward",
     "abc_bn_stats", "abc_bn_finalize", "abc_bn_act", "abc_bn_act_backward", "abc_nchw_to_p8", "abc_channel_sum",
-    "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
+    "abc_nchw_to_p8_ex", "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
 )
 
 
@@ -129,6 +129,7 @@ def _load():
     lib.abc_bn_act.argtypes = [C.POINTER(AbcBnActDesc), vp]
     lib.abc_bn_act_backward.argtypes = [C.POINTER(AbcBnActBwdDesc), vp]
     lib.abc_nchw_to_p8.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    lib.abc_nchw_to_p8_ex.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     lib.abc_deinterleave2.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci, vp]
     lib.abc_conv_wgrad.argtypes = [C.POINTER(AbcWgradDesc), vp]
     lib.abc_conv3x3_c1_wgrad.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, vp, vp]

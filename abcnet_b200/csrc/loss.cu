@@ -93,7 +93,7 @@ __device__ __forceinline__ float ld_tgt(const void* base, size_t i, int f64) {
   return f64 ? static_cast<float>(static_cast<const double*>(base)[i]) : static_cast<const float*>(base)[i];
 }
 
-template <bool BWD>
+template <bool BWD, bool SUMS>
 __global__ void __launch_bounds__(kLossThreads) loss_kernel(const LossParams p) {
   const long long gid = static_cast<long long>(blockIdx.x) * kLossThreads + threadIdx.x;
   const long long total = static_cast<long long>(p.N) * p.HW;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const LossParams p) 
     const size_t hw = static_cast<size_t>(p.HW);
     float sc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sc[k] = BWD ? p.scale[k] : 0.f;
+    for (int k = 0; k < 8; ++k) sc[k] = BWD ? (p.scale ? p.scale[k] : 1.f) : 0.f;
     float d;
     {   // atom / bond centre maps
       const size_t o = static_cast<size_t>(n) * hw + pix;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const LossParams p) 
     acc[8 + ABC_L_RHO] = acc[8 + ABC_L_BTYPE];
     acc[8 + ABC_L_OMEGA] = omega_tsum;
   }
-  if (!BWD) {
+  if (SUMS) {
     __shared__ double red[16][kLossThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -176,7 +176,202 @@ __global__ void __launch_bounds__(kLossThreads) loss_kernel(const LossParams p) 
   }
 }
 
-static int fill(const AbcLossDesc* d, LossParams* p, bool bwd) {
+
+// ------------------------------------------------------------------------------------------------------------------
+// Specialised kernel for the v2 head list (14 atom types, 3 charges, 2 H-counts, 6 bond types; any n_omega).
+// * 256 threads = 64 consecutive pixels x 4 omega groups: the 60-bin loops of one pixel are split over 4 threads and every
+//   load / store is a 256-byte contiguous run per 64 threads;
+// * compile-time class counts -> the soft-max vectors live in registers (the generic kernel keeps them in local memory);
+// * every term except the two centre maps is multiplied by a target (or by a sum of targets) that is zero at ~99.9 % of the
+//   positions (utils.py:94-228 rasterises 3x3 neighbourhoods): where all targets of a group are zero both the loss term and
+//   its gradient are exactly zero whatever the logit, so the logits are not even read there. The pass is bound by reading
+//   the dense targets once and (backward) writing the dense gradient once.
+constexpr int kPx = 64;
+
+template <int C, bool BWD>
+__device__ __forceinline__ float focal_softmax_c(const float* __restrict__ z, const float* __restrict__ t, size_t cs,
+                                                 const float* __restrict__ cw, float* tsum, float scale, float* __restrict__ dz) {
+  float tv[C];
+  float ts = 0.f;
+  bool any = false;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    tv[c] = t[c * cs];
+    ts += tv[c];
+    any |= tv[c] != 0.f;
+  }
+  *tsum = ts;
+  if (!any) {
+    if (BWD) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) dz[c * cs] = 0.f;
+    }
+    return 0.f;
+  }
+  float zv[C];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    zv[c] = z[c * cs];
+    mx = fmaxf(mx, zv[c]);
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    zv[c] = expf(zv[c] - mx);
+    den += zv[c];
+  }
+  const float inv = 1.f / den;
+  float num = 0.f, gdot = 0.f;
+  float g[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float ps = zv[c] * inv;
+    const float p = clampp(ps);
+    const float w = cw ? cw[c] : 1.f;
+    const float lp = logf(p);
+    num += -w * tv[c] * (1.f - p) * (1.f - p) * lp;
+    if (BWD) {
+      const float pass = (ps >= kLo && ps <= kHi) ? 1.f : 0.f;
+      g[c] = -w * tv[c] * (-2.f * (1.f - p) * lp + (1.f - p) * (1.f - p) / p) * pass;
+      gdot += g[c] * ps;
+      zv[c] = ps;
+    }
+  }
+  if (BWD) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) dz[c * cs] = scale * zv[c] * (g[c] - gdot);
+  }
+  return num;
+}
+
+template <bool BWD, bool SUMS>
+__global__ void __launch_bounds__(256) loss_kernel_v2(const LossParams p) {
+  constexpr int CT = 14, CC = 3, CH = 2, NB = 6;
+  __shared__ float osum[4][kPx];
+  __shared__ double red[16][8];
+  const int px = threadIdx.x & (kPx - 1), wg = threadIdx.x >> 6;
+  const long long total = static_cast<long long>(p.N) * p.HW;
+  const size_t hw = static_cast<size_t>(p.HW);
+  const int w0 = (wg * p.n_omega) >> 2, w1 = ((wg + 1) * p.n_omega) >> 2;
+  float sc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sc[k] = BWD ? (p.scale ? p.scale[k] : 1.f) : 0.f;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  const long long ntiles = (total + kPx - 1) / kPx;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long gid = tile * kPx + px;
+    const bool live = gid < total;
+    int n = 0, pix = 0;
+    if (live) {
+      n = static_cast<int>(gid / p.HW);
+      pix = static_cast<int>(gid - static_cast<long long>(n) * p.HW);
+    }
+    const size_t ow = (static_cast<size_t>(n) * p.n_omega) * hw + pix;
+    // per-pixel sum of the omega targets (train.py:124): partial per omega group, combined through shared memory
+    float part = 0.f;
+    if (live)
+      for (int w = w0; w < w1; ++w) part += ld_tgt(p.t[7], ow + w * hw, p.tgt_f64);
+    osum[wg][px] = part;
+    __syncthreads();
+    const float omega_tsum = osum[0][px] + osum[1][px] + osum[2][px] + osum[3][px];
+    __syncthreads();
+    if (!live) continue;
+    float d;
+    if (wg == 0) {          // centre maps (dense terms)
+      const size_t o = static_cast<size_t>(n) * hw + pix;
+      const float ta = static_cast<const float*>(p.t[0])[o];
+      acc[ABC_L_ATOM] += focal_sigmoid<BWD>(p.z[0][o], ta, &d);
+      acc[8 + ABC_L_ATOM] += (ta == 1.f) ? 1.f : 0.f;
+      if (BWD) p.dz[0][o] = sc[ABC_L_ATOM] * d;
+      const float tb = static_cast<const float*>(p.t[4])[o];
+      acc[ABC_L_BOND] += focal_sigmoid<BWD>(p.z[4][o], tb, &d);
+      acc[8 + ABC_L_BOND] += (tb == 1.f) ? 1.f : 0.f;
+      if (BWD) p.dz[4][o] = sc[ABC_L_BOND] * d;
+      acc[8 + ABC_L_OMEGA] += omega_tsum;
+    } else if (wg == 1) {   // atom types
+      float ts;
+      const size_t o = (static_cast<size_t>(n) * CT) * hw + pix;
+      acc[ABC_L_TYPE] += focal_softmax_c<CT, BWD>(p.z[1] + o, static_cast<const float*>(p.t[1]) + o, hw, p.type_w, &ts,
+                                                  sc[ABC_L_TYPE], BWD ? p.dz[1] + o : nullptr);
+      acc[8 + ABC_L_TYPE] += ts;
+    } else if (wg == 2) {   // charges, H counts
+      float ts;
+      size_t o = (static_cast<size_t>(n) * CC) * hw + pix;
+      acc[ABC_L_CHARGE] += focal_softmax_c<CC, BWD>(p.z[2] + o, static_cast<const float*>(p.t[2]) + o, hw, nullptr, &ts,
+                                                    sc[ABC_L_CHARGE], BWD ? p.dz[2] + o : nullptr);
+      acc[8 + ABC_L_CHARGE] += ts;
+      o = (static_cast<size_t>(n) * CH) * hw + pix;
+      acc[ABC_L_HS] += focal_softmax_c<CH, BWD>(p.z[3] + o, static_cast<const float*>(p.t[3]) + o, hw, nullptr, &ts,
+                                                sc[ABC_L_HS], BWD ? p.dz[3] + o : nullptr);
+      acc[8 + ABC_L_HS] += ts;
+    }
+    const size_t obt = (static_cast<size_t>(n) * NB * p.n_omega) * hw + pix;
+    for (int w = w0; w < w1; ++w) {
+      float tsum;
+      acc[ABC_L_BTYPE] += focal_softmax_c<NB, BWD>(p.z[5] + obt + w * hw, static_cast<const float*>(p.t[5]) + obt + w * hw,
+                                                   hw * p.n_omega, nullptr, &tsum, sc[ABC_L_BTYPE],
+                                                   BWD ? p.dz[5] + obt + w * hw : nullptr);
+      acc[8 + ABC_L_BTYPE] += tsum;
+      if (tsum != 0.f) {
+        const float zr = p.z[6][ow + w * hw];
+        const float tr = ld_tgt(p.t[6], ow + w * hw, p.tgt_f64);
+        const float diff = fabsf(zr) - tr;
+        acc[ABC_L_RHO] += fabsf(diff) * tsum;
+        if (BWD) {
+          const float sd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+          const float sz = zr > 0.f ? 1.f : (zr < 0.f ? -1.f : 0.f);
+          p.dz[6][ow + w * hw] = sc[ABC_L_RHO] * sd * sz * tsum;
+        }
+      } else if (BWD) {
+        p.dz[6][ow + w * hw] = 0.f;
+      }
+      if (omega_tsum != 0.f) {
+        const float tw = ld_tgt(p.t[7], ow + w * hw, p.tgt_f64);
+        acc[ABC_L_OMEGA] += omega_tsum * focal_sigmoid<BWD>(p.z[7][ow + w * hw], tw, &d);
+        if (BWD) p.dz[7][ow + w * hw] = sc[ABC_L_OMEGA] * omega_tsum * d;
+      } else if (BWD) {
+        p.dz[7][ow + w * hw] = 0.f;
+      }
+    }
+  }
+  if (SUMS) {
+    acc[8 + ABC_L_RHO] = acc[8 + ABC_L_BTYPE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      double v = static_cast<double>(acc[i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[i][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+      if (v != 0.0) atomicAdd(p.sums + threadIdx.x, v);
+    }
+  }
+}
+
+template <bool BWD, bool SUMS>
+static int launch_loss(const LossParams& p, cudaStream_t st) {
+  const long long total = static_cast<long long>(p.N) * p.HW;
+  if (p.c_type == 14 && p.c_charge == 3 && p.c_hs == 2 && p.n_btype == 6 && p.n_omega >= 4) {
+    long long tiles = (total + kPx - 1) / kPx;
+    const long long cap = 148ll * 8 * 4;
+    const unsigned blocks = static_cast<unsigned>(tiles < cap ? tiles : cap);
+    loss_kernel_v2<BWD, SUMS><<<blocks, 256, 0, st>>>(p);
+    return launch_check("loss_kernel_v2");
+  }
+  const unsigned blocks = static_cast<unsigned>((total + kLossThreads - 1) / kLossThreads);
+  loss_kernel<BWD, SUMS><<<blocks, kLossThreads, 0, st>>>(p);
+  return launch_check("loss_kernel");
+}
+
+static int fill(const AbcLossDesc* d, LossParams* p, bool bwd, bool sums) {
   ABC_REQUIRE(d != nullptr, "abc_loss: null descriptor");
   for (int i = 0; i < 8; ++i) {
     ABC_REQUIRE(d->logits[i] && d->targets[i], "abc_loss: logits / targets %d null", i);
@@ -189,8 +384,8 @@ static int fill(const AbcLossDesc* d, LossParams* p, bool bwd) {
   ABC_REQUIRE(d->c_type <= kMaxC && d->c_charge <= kMaxC && d->c_hs <= kMaxC && d->n_btype <= kMaxC && d->c_type >= 1 &&
                   d->c_charge >= 1 && d->c_hs >= 1 && d->n_btype >= 1 && d->n_omega >= 1,
               "abc_loss: class counts must be in [1, %d]", kMaxC);
-  if (bwd) ABC_REQUIRE(d->scale != nullptr, "abc_loss_backward: scale is null");
-  else ABC_REQUIRE(d->sums != nullptr, "abc_loss_partials: sums is null");
+  if (sums) ABC_REQUIRE(d->sums != nullptr, "abc_loss: sums is null");
+  if (bwd && !sums) ABC_REQUIRE(d->scale != nullptr, "abc_loss_backward: scale is null");
   p->tgt_f64 = d->tgt_f64;
   p->N = d->N;
   p->HW = d->H * d->W;
@@ -207,21 +402,20 @@ extern "C" int abc_loss_partials(const AbcLossDesc* d, void* stream) {
   using namespace abc;
   if (int rc = device_check()) return rc;
   LossParams p{};
-  if (int rc = fill(d, &p, false)) return rc;
-  ABC_CUDA(cudaMemsetAsync(p.sums, 0, 16 * sizeof(double), static_cast<cudaStream_t>(stream)));
-  const long long total = static_cast<long long>(p.N) * p.HW;
-  const unsigned blocks = static_cast<unsigned>((total + kLossThreads - 1) / kLossThreads);
-  loss_kernel<false><<<blocks, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  return launch_check("loss_kernel<fwd>");
+  // fused mode: when every dlogits pointer is given, the same pass also writes the UNSCALED gradient (scale = 1, or
+  // desc->scale if non-null); the caller applies u_k / denom_k afterwards (abc_nchw_to_p8_ex does it while converting).
+  bool fused = d != nullptr;
+  for (int i = 0; fused && i < 8; ++i) fused = d->dlogits[i] != nullptr;
+  if (int rc = fill(d, &p, fused, true)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ABC_CUDA(cudaMemsetAsync(p.sums, 0, 16 * sizeof(double), st));
+  return fused ? launch_loss<true, true>(p, st) : launch_loss<false, true>(p, st);
 }
 
 extern "C" int abc_loss_backward(const AbcLossDesc* d, void* stream) {
   using namespace abc;
   if (int rc = device_check()) return rc;
   LossParams p{};
-  if (int rc = fill(d, &p, true)) return rc;
-  const long long total = static_cast<long long>(p.N) * p.HW;
-  const unsigned blocks = static_cast<unsigned>((total + kLossThreads - 1) / kLossThreads);
-  loss_kernel<true><<<blocks, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  return launch_check("loss_kernel<bwd>");
+  if (int rc = fill(d, &p, true, false)) return rc;
+  return launch_loss<true, false>(p, static_cast<cudaStream_t>(stream));
 }

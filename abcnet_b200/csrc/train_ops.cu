@@ -428,6 +428,48 @@ __global__ void __launch_bounds__(256) nchw_to_p8_kernel(const float* __restrict
   dst[t] = pack8(v);
 }
 
+// fp32 NCHW -> bf16 P8 with an optional device-side scale, zero-filled padding planes and per-channel sums of the scaled
+// values (the bias gradient of the 1x1 head convolutions): one pass over the loss gradient instead of three.
+__global__ void __launch_bounds__(256) nchw_to_p8_ex_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int C, int HW,
+                                                            int dst_planes, const float* __restrict__ scale,
+                                                            double* __restrict__ dbias) {
+  const int plane = blockIdx.y, n = blockIdx.z;
+  const float sc = scale ? *scale : 1.f;
+  const float* __restrict__ sb = src + (static_cast<size_t>(n) * C + plane * 8) * HW;
+  uint4* __restrict__ db = dst + (static_cast<size_t>(n) * dst_planes + plane) * HW;
+  const int nvalid = min(8, max(0, C - plane * 8));
+  float s[8], zero[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = zero[i] = 0.f;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < HW; e += gridDim.x * 256) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = i < nvalid ? sb[static_cast<size_t>(i) * HW + e] * sc : 0.f;
+      s[i] += v[i];
+    }
+    db[e] = pack8(v);
+  }
+  if (dbias != nullptr && nvalid > 0) {      // block-uniform condition
+    __shared__ double red[16][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = s[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[i][warp] = static_cast<double>(v);
+    }
+    __syncthreads();
+    if (threadIdx.x < nvalid) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+      atomicAdd(dbias + plane * 8 + threadIdx.x, v);
+    }
+  }
+}
+
 // dW[16][9], db-free: gradient of the first 1 -> 16 convolution (no dgrad: the image needs no gradient)
 template <typename T>
 __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const T* __restrict__ img, P8View dz, int N, int H, int W,
@@ -615,6 +657,19 @@ extern "C" int abc_nchw_to_p8(const float* src, void* dst, int N, int C, int H, 
   nchw_to_p8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<uint4*>(dst), N, C, H * W, planes);
   return launch_check("nchw_to_p8_kernel");
+}
+
+extern "C" int abc_nchw_to_p8_ex(const float* src, void* dst, int N, int C, int H, int W, int dst_planes, const float* scale,
+                                 double* dbias, void* stream) {
+  if (int rc = device_check()) return rc;
+  ABC_REQUIRE(src && dst && N > 0 && N <= 65535 && C > 0 && H > 0 && W > 0, "abc_nchw_to_p8_ex: bad arguments");
+  ABC_REQUIRE(dst_planes >= (C + 7) / 8 && dst_planes <= 65535, "abc_nchw_to_p8_ex: dst_planes=%d too small for C=%d", dst_planes, C);
+  ABC_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "abc_nchw_to_p8_ex: dst must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dbias) ABC_CUDA(cudaMemsetAsync(dbias, 0, C * sizeof(double), st));
+  const dim3 grid(plane_grid_x(static_cast<long long>(H) * W, dst_planes, N, 2), dst_planes, N);
+  nchw_to_p8_ex_kernel<<<grid, 256, 0, st>>>(src, static_cast<uint4*>(dst), C, H * W, dst_planes, scale, dbias);
+  return launch_check("nchw_to_p8_ex_kernel");
 }
 
 extern "C" int abc_channel_sum(const void* x, int N, int H, int W, int planes, int plane_off, int C, double* sum, double* sumsq_scratch,

@@ -32,6 +32,11 @@ struct WgradParams {
   int cout, cin, stages;
   uint32_t a_stage_bytes, dz_tile_bytes, in_tile_bytes, in_plane_bytes, in_row_bytes;
   uint32_t tap_off[9];
+  // tap-folded mode (cin <= 32): every tap's shifted 16 x 8 box of the input is loaded as its own smem block, so that the
+  // taps line up on the GEMM N axis (N = taps * cin) and ONE MMA per K step replaces `ntaps` N = cin MMAs whose cost is
+  // bounded below by the A-operand read, not by N.
+  int fold, fold_groups, fold_tap0[2], fold_ntaps[2];
+  int tap_dy[9], tap_dx[9];
   float* dw;               // [ntaps][cout][cin] fp32, accumulated with atomicAdd
 };
 
@@ -85,8 +90,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant_
         const uint32_t dst = stage0 + stage * p.a_stage_bytes;
         mbar_arrive_expect_tx(bar_full + 8 * stage, p.dz_tile_bytes + p.in_tile_bytes);
         tma_load_4d(dst, &tmap_dz, bar_full + 8 * stage, tx * 64, ty * 16, p.dz_plane_off + co_t * 16, n);
-        tma_load_4d(dst + 32768, &tmap_in, bar_full + 8 * stage, (tx * 8 - p.halo) * 8, ty * 16 - p.halo,
-                    p.a_plane_off + ci_t * (p.n_tile >> 3), n);
+        if (p.fold) {
+          const uint32_t blk = static_cast<uint32_t>(p.n_tile >> 3) * 2048u;
+          for (int t = 0; t < ntap; ++t)
+            tma_load_4d(dst + 32768 + t * blk, &tmap_in, bar_full + 8 * stage, (tx * 8 + p.tap_dx[tap0 + t]) * 8,
+                        ty * 16 + p.tap_dy[tap0 + t], p.a_plane_off + ci_t * (p.n_tile >> 3), n);
+        } else {
+          tma_load_4d(dst + 32768, &tmap_in, bar_full + 8 * stage, (tx * 8 - p.halo) * 8, ty * 16 - p.halo,
+                      p.a_plane_off + ci_t * (p.n_tile >> 3), n);
+        }
       }
       __syncwarp();
       if (++stage == p.stages) {
@@ -98,13 +110,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant_
     // A = dz^T (M = co): MN-major, LBO = next 8 pixels = next tile row (128 B), SBO = next 8 channels = plane pitch (2048 B)
     // B = a     (N = ci): MN-major, LBO = halo row pitch, SBO = halo plane pitch
     const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 1, 1);
+    const uint32_t idesc_f0 = umma_idesc_bf16(128, p.fold ? p.fold_ntaps[0] * p.n_tile : 16, 1, 1);
+    const uint32_t idesc_f1 = umma_idesc_bf16(128, (p.fold && p.fold_groups > 1) ? p.fold_ntaps[1] * p.n_tile : 16, 1, 1);
     const uint64_t a_hi64 = umma_desc_hi(128, 2048);
-    const uint64_t b_hi64 = umma_desc_hi(p.in_row_bytes, p.in_plane_bytes);
+    const uint64_t b_hi64 = p.fold ? umma_desc_hi(128, 2048) : umma_desc_hi(p.in_row_bytes, p.in_plane_bytes);
     const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), b_hi = static_cast<uint32_t>(b_hi64 >> 32);
     const uint32_t a_lo0 = static_cast<uint32_t>(a_hi64) | (stage0 >> 4);
     const uint32_t b_lo0 = static_cast<uint32_t>(b_hi64) | ((stage0 + 32768) >> 4);
     const uint32_t stage16 = p.a_stage_bytes >> 4;
-    const uint32_t a_kstep = (2 * 128) >> 4, b_kstep = (2 * p.in_row_bytes) >> 4;
+    const uint32_t a_kstep = (2 * 128) >> 4, b_kstep = p.fold ? a_kstep : (2 * p.in_row_bytes) >> 4;
+    const uint32_t fold_blk16 = (static_cast<uint32_t>(p.n_tile >> 3) * 2048u) >> 4;
     int stage = 0;
     uint32_t phase = 0, first = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -112,6 +127,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant_
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_base = a_lo0 + stage * stage16, b_base = b_lo0 + stage * stage16;
+        if (p.fold) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            umma_bf16_lohi(tmem_base, a_base + s * a_kstep, a_hi, b_base + s * b_kstep, b_hi, idesc_f0, s != 0 ? 1u : first);
+            if (p.fold_groups > 1)
+              umma_bf16_lohi(tmem_base + p.fold_tap0[1] * p.n_tile, a_base + s * a_kstep, a_hi,
+                             b_base + p.fold_tap0[1] * fold_blk16 + s * b_kstep, b_hi, idesc_f1, s != 0 ? 1u : first);
+          }
+        } else
         for (int t = 0; t < ntap; ++t) {
           const uint32_t b_tap = b_base + (p.tap_off[tap0 + t] >> 4);
 #pragma unroll
@@ -242,9 +266,24 @@ extern "C" int abc_conv_wgrad(const AbcWgradDesc* d, void* stream) {
   p.in_plane_bytes = rows * p.in_row_bytes;
   p.in_tile_bytes = (p.n_tile / 8) * p.in_plane_bytes;
   p.dz_tile_bytes = p.m_planes * 2048;
+  p.fold = (d->cin <= 32 && d->ntaps > 1 && p.tap_groups == 1) ? 1 : 0;
+  if (p.fold) {
+    p.in_tile_bytes = static_cast<uint32_t>(d->ntaps) * (p.n_tile / 8) * 2048u;
+    const int per = 256 / p.n_tile;                       // taps per MMA (N <= 256)
+    if (d->ntaps <= per) {
+      p.fold_groups = 1; p.fold_tap0[0] = 0; p.fold_ntaps[0] = d->ntaps;
+    } else {
+      ABC_REQUIRE(d->ntaps <= 2 * per, "abc_conv_wgrad: internal: fold groups");
+      p.fold_groups = 2; p.fold_tap0[0] = 0; p.fold_ntaps[0] = (d->ntaps + 1) / 2;
+      p.fold_tap0[1] = p.fold_ntaps[0]; p.fold_ntaps[1] = d->ntaps - p.fold_ntaps[0];
+    }
+  }
   p.a_stage_bytes = 32768 + ((p.in_tile_bytes + 1023u) & ~1023u);
-  for (int t = 0; t < d->ntaps; ++t)
+  for (int t = 0; t < d->ntaps; ++t) {
     p.tap_off[t] = static_cast<uint32_t>(((d->tap_dy[t] + halo) * cols + (d->tap_dx[t] + halo)) * 16);
+    p.tap_dy[t] = d->tap_dy[t];
+    p.tap_dx[t] = d->tap_dx[t];
+  }
   p.dw = d->dw;
   p.stages = static_cast<int>((232448 - kWgHeader) / p.a_stage_bytes);
   if (p.stages > kWgStages) p.stages = kWgStages;
@@ -253,7 +292,7 @@ extern "C" int abc_conv_wgrad(const AbcWgradDesc* d, void* stream) {
 
   CUtensorMap map_dz, map_in;
   if (int rc = make_map(&map_dz, d->dz, d->W, d->H, d->dz_planes, d->N, 8, 16, p.m_planes)) return rc;
-  if (int rc = make_map(&map_in, d->in, d->W, d->H, d->in_planes, d->N, cols, rows, p.n_tile / 8)) return rc;
+  if (int rc = make_map(&map_in, d->in, d->W, d->H, d->in_planes, d->N, p.fold ? 8 : cols, p.fold ? 16 : rows, p.n_tile / 8)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     ABC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));

@@ -49,13 +49,20 @@ def _s_index(dev):
         half = [1.0] * 8
         half[5] = 0.5                                                      # train.py:133 (rho term: 0.5 * exp(-s) + s)
         t = _IDX_CACHE[dev] = (torch.tensor(_S_INDEX, dtype=torch.long, device=dev),
-                               torch.tensor(half, dtype=torch.float64, device=dev))
+                               torch.tensor(half, dtype=torch.float64, device=dev),
+                               torch.tensor(_HEAD_TO_LOSS, dtype=torch.long, device=dev))
     return t
 
 
-def loss_forward_backward(s, type_w, targets, logits):
-    """Both passes without autograd: returns (total fp64 scalar, 8 weighted parts, dL/ds [10] fp64, 8 dL/dlogits fp32).
-    Everything stays on the device (no host synchronisation), so the call can be captured in a CUDA graph."""
+# head i of UNet.forward -> loss index of the kernels (AbcLossIndex): atom, type, charge, hs, bond, btype, rho, omega
+_HEAD_TO_LOSS = [0, 2, 3, 7, 1, 4, 5, 6]
+
+
+def loss_forward_backward(s, type_w, targets, logits, scaled=True):
+    """Losses + gradients without autograd. Returns (total fp64 scalar, 8 weighted parts, dL/ds [10] fp64, 8 dlogits fp32,
+    head_scale). ``scaled=True``: two passes, dlogits are dL/dlogits and head_scale is None. ``scaled=False``: ONE fused
+    pass, dlogits are unscaled and dL/dlogits[i] = head_scale[i] * dlogits[i] (fp32 device tensor [8]; the consumer --
+    TrainEngine.backward -- folds the factor into its fp32 -> bf16 conversion). No host synchronisation: capturable."""
     _lib.require_device()
     logits = [z.contiguous() for z in logits]
     for z in logits:
@@ -71,26 +78,31 @@ def loss_forward_backward(s, type_w, targets, logits):
     st = _lib.current_stream_ptr()
     dev = logits[0].device
     sums = torch.empty(16, dtype=torch.float64, device=dev)
-    check(lib.abc_loss_partials(C.byref(_desc(logits, targets, type_w, sums, None, None)), st), "abc_loss_partials")
+    dlogits = [torch.empty_like(z) for z in logits]
+    check(lib.abc_loss_partials(C.byref(_desc(logits, targets, type_w, sums, None, None if scaled else dlogits)), st),
+          "abc_loss_partials")
     num, den = sums[:8], sums[8:].clone()
     den[7] = den[7] + 0.1                                                  # train.py:114
     raw = num / den
-    idx, half = _s_index(dev)
+    idx, half, h2l = _s_index(dev)
     sk = s.detach().double()[idx]
     u = half * torch.exp(-sk) + sk
     total = (raw * u).sum()
     scale = (u / den).float().contiguous()
-    dlogits = [torch.empty_like(z) for z in logits]
-    check(lib.abc_loss_backward(C.byref(_desc(logits, targets, type_w, None, scale, dlogits)), st), "abc_loss_backward")
+    head_scale = None
+    if scaled:
+        check(lib.abc_loss_backward(C.byref(_desc(logits, targets, type_w, None, scale, dlogits)), st), "abc_loss_backward")
+    else:
+        head_scale = scale[h2l]
     ds = torch.zeros(10, dtype=torch.float64, device=dev)
     ds[idx] = raw * (1.0 - half * torch.exp(-sk))
-    return total, (raw * u).detach(), ds, dlogits
+    return total, (raw * u).detach(), ds, dlogits, head_scale
 
 
 class _HeatmapLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, s, type_w, targets, *logits):
-        total, parts, ds, dlogits = loss_forward_backward(s, type_w, targets, logits)
+        total, parts, ds, dlogits, _ = loss_forward_backward(s, type_w, targets, logits)
         ctx.save_for_backward(ds.to(s.dtype), *dlogits)
         ctx.parts = parts
         return total

@@ -362,9 +362,10 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ backward
     @torch.no_grad()
-    def backward(self, dlogits, sink):
-        """dlogits: 8 fp32 NCHW gradients. ``sink(param, grad_tensor)`` receives every parameter gradient as soon as it
-        is complete (reverse layer order) -- e.g. GradBuckets-aware accumulation."""
+    def backward(self, dlogits, sink, head_scale=None):
+        """dlogits: 8 fp32 NCHW gradients (times ``head_scale[i]``, an fp32 device tensor [8], when given).
+        ``sink(param, grad_tensor)`` receives every parameter gradient as soon as it is complete (reverse layer order)
+        -- e.g. GradBuckets-aware accumulation."""
         m, sv = self.m, self.saved
         B, H, W = sv["B"], sv["H"], sv["W"]
         H4, W4 = H // 4, W // 4
@@ -378,15 +379,16 @@ class TrainEngine:
                 g = torch.zeros((B, h_, H4, W4), dtype=torch.float32, device=dev)
             g = g.contiguous().float()
             c16 = (h_ + 15) // 16 * 16 if h_ <= 64 else (h_ + 63) // 64 * 64     # K of the data-gradient GEMM
-            dl = self.buf(f"g:logit{i}", (B, c16 // 8, H4, W4, 8), zero=True)
-            if c16 // 8 == (h_ + 7) // 8:
-                check(lib.abc_nchw_to_p8(g.data_ptr(), dl.data_ptr(), B, h_, H4, W4, _st()), "abc_nchw_to_p8")
-            else:
-                self._nchw_to_p8_padded(g, dl, B, h_, H4, W4)
+            dl = self.buf(f"g:logit{i}", (B, c16 // 8, H4, W4, 8))
+            db = self.buf(f"g:bias{i}", (h_,), torch.float64)
+            # one pass: (optional per-head loss scale) * dlogits -> bf16 P8 with zero K padding, + conv2 bias gradient
+            check(lib.abc_nchw_to_p8_ex(g.data_ptr(), dl.data_ptr(), B, h_, H4, W4, c16 // 8,
+                                        head_scale[i:i + 1].data_ptr() if head_scale is not None else None, db.data_ptr(), _st()),
+                  "abc_nchw_to_p8_ex")
             c8 = (h_ + 7) // 8 * 8
             dw2 = wgrad(dl, 0, c8, hd["hid"], 16 * i, 128, [(0, 0)])[0][:h_]
             sink(om.conv2.weight, dw2.reshape(h_, 128, 1, 1))
-            sink(om.conv2.bias, g.sum((0, 2, 3)))
+            sink(om.conv2.bias, db.float())
             w2 = om.conv2.weight.detach().float().reshape(h_, 128)
             w2p = torch.cat([w2, w2.new_zeros(c16 - h_, 128)], 0)            # K = padded logits channels
             conv(Packed(w2p.t().contiguous().unsqueeze(0), torch.zeros(128, device=dev), [(0, 0)], n_tile=128), dl, 0, dhid,
@@ -445,13 +447,6 @@ class TrainEngine:
             gsrc = self._tensor(u["src"], B, H, W, (B, cin // 8, h, w, 8), grad=True)
             mats = torch.stack([wt[:, :, dy + 1, dx + 1].t() for dy, dx in TAPS3]).contiguous()    # [9][ci][co]
             conv(Packed(mats, torch.zeros(cin, device=dev), [(-dy, -dx) for dy, dx in TAPS3]), dz, 0, gsrc, out_plane_off=u["src_off"])
-
-    def _nchw_to_p8_padded(self, g, dl, B, h_, H4, W4):
-        """Odd plane count: convert into a compact temporary, then copy into the (zero-initialised) padded buffer."""
-        tmp = self.buf(f"g:tmp{h_}", (B, (h_ + 7) // 8, H4, W4, 8))
-        check(lib.abc_nchw_to_p8(g.data_ptr(), tmp.data_ptr(), B, h_, H4, W4, _st()), "abc_nchw_to_p8")
-        dl[:, :tmp.shape[1]].copy_(tmp)
-
 
 class _UNetTrainFn(torch.autograd.Function):
     @staticmethod

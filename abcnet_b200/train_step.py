@@ -62,11 +62,11 @@ class TrainStep:
         if self.buckets is not None:
             self.buckets.zero()
         outs = eng.forward(x)
-        total, parts, ds, dlogits = loss_forward_backward(m.s, self.type_w, list(targets), outs)
+        total, parts, ds, dlogits, head_scale = loss_forward_backward(m.s, self.type_w, list(targets), outs, scaled=False)
         self.loss.copy_(total)
         self.parts.copy_(parts)
         self._sink(m.s, ds.to(m.s.dtype))
-        eng.backward(dlogits, self._sink)
+        eng.backward(dlogits, self._sink, head_scale=head_scale)
         if self.buckets is not None:
             self.buckets.finish()
         if with_opt and self.opt is not None:

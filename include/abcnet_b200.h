@@ -158,7 +158,9 @@ ABC_API int abc_decode_peaks(const AbcDecodeDesc* desc, void* stream);
 /* ---------------------------------------------------------------------------------------------------
  * Fused training losses, forward + backward in one pass. Replaces the ~60 ATen kernels (+ autograd) of
  * src/train.py:95-137 (= src/multi_gpu_train2.py:140-192 with class_weights = 0).
- * Pass 1 (abc_loss_partials) accumulates the 8 numerators and 8 denominators in fp64;
+ * Pass 1 (abc_loss_partials) accumulates the 8 numerators and 8 denominators in fp64; when all eight dlogits pointers
+ * are given it also writes the UNSCALED gradient in the same pass ("fused mode": the per-loss factor u_k / denom_k is
+ * applied by the consumer, abc_nchw_to_p8_ex), which saves the second pass over the dense targets;
  * pass 2 (abc_loss_backward) writes dL/dlogits for the 8 maps given the per-loss scale factors
  * u_k / denom_k computed by the host wrapper from `s` (train.py:127-135).
  * Logits and dlogits: fp32 NCHW as returned by UNet.forward. Targets: fp32 dense maps in the reference's
@@ -219,6 +221,11 @@ typedef struct AbcBnActBwdDesc {
 ABC_API int abc_bn_act_backward(const AbcBnActBwdDesc* desc, void* stream);
 /* fp32 NCHW -> bf16 P8 with zero-padded channels (dlogits -> tensor-core operand). */
 ABC_API int abc_nchw_to_p8(const float* src, void* dst, int N, int C, int H, int W, void* stream);
+/* Same in one pass with: a device-side scalar scale (NULL = 1), dst_planes >= ceil(C/8) planes written (padding planes
+ * zero: the K padding of the data-gradient GEMM) and, if dbias != NULL, dbias[c] = sum over (n, y, x) of the scaled values
+ * (fp64; the bias gradient of the 1x1 head convolutions, src/unet.py:70). */
+ABC_API int abc_nchw_to_p8_ex(const float* src, void* dst, int N, int C, int H, int W, int dst_planes, const float* scale,
+                              double* dbias, void* stream);
 /* per-channel sum of a P8 tensor (bias gradients of convolutions that are not followed by BatchNorm). */
 ABC_API int abc_channel_sum(const void* x, int N, int H, int W, int planes, int plane_off, int C, double* sum, double* scratch, void* stream);
 /* P8 [N][planes][2H][2W][8] -> [N][4*C/8][H][W][8], phase (py, px) stacked on the plane axis (backward of the

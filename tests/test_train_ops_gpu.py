@@ -167,3 +167,35 @@ def test_upsampling_conv_backward(crop_first):
     torch.cuda.synchronize()
     assert_close(from_p8(dx).cpu(), xx.grad.float(), 2 ** -6, 2e-3 * xx.grad.abs().max().item(), "upconv dgrad")
     assert_close(dw.cpu(), ww.grad.float(), 1e-3, 1e-3 * ww.grad.abs().max().item(), "upconv wgrad")
+
+
+def test_fused_loss_mode_and_scaled_p8_conversion():
+    """abc_loss_partials in fused mode (sums + unscaled gradient in one pass) times head_scale equals the two-pass
+    gradient bit for bit up to one fp32 rounding, and abc_nchw_to_p8_ex applies that scale, zero-pads the K planes and
+    yields the conv2 bias gradient (sum over batch and pixels)."""
+    from abcnet_b200.loss import ATOM_TYPE_WEIGHTS, loss_forward_backward
+    from oracle import synth
+    L = _lib()
+    dev = "cuda"
+    tg = [torch.from_numpy(t).to(dev).contiguous() for t in synth.dense_targets(7, 2, 32, 32)]
+    logits = [torch.from_numpy(o).to(dev) for o in synth.random_logits(7, 2, 32, 32)]
+    s = rnd(9, (10,), -0.3, 0.3).to(dev)
+    tw = torch.tensor(ATOM_TYPE_WEIGHTS, device=dev)
+    t1, p1, ds1, d1, hs1 = loss_forward_backward(s, tw, tg, logits, scaled=True)
+    t2, p2, ds2, d2, hs2 = loss_forward_backward(s, tw, tg, logits, scaled=False)
+    assert hs1 is None and hs2.shape == (8,)
+    assert t1.item() == t2.item() and torch.equal(ds1, ds2)
+    for i in range(8):
+        assert_close((d2[i] * hs2[i]).cpu(), d1[i].cpu(), 1e-6, 1e-12, f"dlogits {i}")
+    for i, g in enumerate(d2):
+        N, Cc, H, W = g.shape
+        planes = (Cc + 15) // 16 * 2
+        out = torch.full((N, planes, H, W, 8), float("nan"), dtype=torch.bfloat16, device=dev)
+        db = torch.empty(Cc, dtype=torch.float64, device=dev)
+        L.check(L.lib.abc_nchw_to_p8_ex(g.data_ptr(), out.data_ptr(), N, Cc, H, W, planes, hs2[i:i + 1].data_ptr(), db.data_ptr(), _st()))
+        torch.cuda.synchronize()
+        ref = (g * hs2[i]).cpu()
+        got = from_p8(out).cpu()
+        assert torch.equal(got[:, :Cc], bf16_round(ref)), i
+        assert (got[:, Cc:] == 0).all()
+        assert_close(db.cpu().float(), ref.double().sum((0, 2, 3)).float(), 1e-5, 1e-9, f"dbias {i}")
