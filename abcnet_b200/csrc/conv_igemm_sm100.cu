@@ -14,12 +14,12 @@
 //   GEMM N = n_tile output channels (runtime, multiple of 16, <= 256)
 //   GEMM K = 16 channels per MMA (two planes, LBO = plane pitch), KC = min(cin, 64) channels per pipeline stage
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over M tiles, blockIdx.y = N tile):
+// Warp roles (384 threads, 1 CTA / SM, persistent over M tiles, blockIdx.y = N tile):
 //   warp 0 : TMA producer for activation halo tiles (A ring)
 //   warp 3 : bulk-copy producer for packed weight blocks (B ring, or resident when the layer's weights fit in smem)
 //   warp 1 : MMA issuer (one thread), accumulators double-buffered in TMEM
 //   warp 2 : TMEM allocation / release
-//   warps 4-7 : epilogue (tcgen05.ld -> bias + activation -> bf16 P8 / fp32 NCHW stores, optional fused max-pool)
+//   warps 4-11 : epilogue (tcgen05.ld -> bias + activation -> bf16 P8 / fp32 NCHW stores, optional fused max-pool)
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -29,16 +29,17 @@
 
 namespace abc {
 
-constexpr int kMaxNA = 4;
+constexpr int kMaxNA = 8;
+constexpr int kMaxAcc = 8;           // accumulator stages in TMEM: 512 / (mt * n_tile) columns each, 2..8
 constexpr int kMaxNB = 16;
 constexpr uint32_t kHeaderBytes = 2048;
 constexpr uint32_t kSmemBudget = 232448;   // 227 KB opt-in limit per CTA
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;          // warps 0-3: producers / MMA / TMEM, warps 4-11: epilogue
 constexpr int kTmemCols = 512;
 
 struct ConvKParams {
   int N, H, W, tiles_x, tiles_y, groups_x, num_groups;   // a group = mt horizontally adjacent 16x8 tiles
-  int in_plane_off, kp, nkc, ntaps, halo, n_tile, resident_b, na, nb, mt;
+  int in_plane_off, kp, nkc, ntaps, halo, n_tile, resident_b, na, nb, mt, nacc, acc_cols;
   int chunks_per_seg, blocks_per_ntile;      // K segments: chunk kc uses taps [seg_tap0[s], seg_tap0[s] + seg_ntaps[s]), s = kc / chunks_per_seg
   int seg_tap0[4], seg_ntaps[4];
   uint32_t a_stage_bytes, a_tile_bytes, a_plane_bytes, a_row_bytes, b_block_bytes;
@@ -72,7 +73,10 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   return r;
 }
 
-template <int KSTEPS>   // K-steps of 16 channels per pipeline stage = kp / 2 (1, 2, 3 or 4)
+// KSTEPS: K-steps of 16 channels per pipeline stage = kp / 2 (1, 2, 3 or 4). RESIDENT: the layer's weights of one n-tile
+// stay in shared memory (no B ring). Both are compile-time so that the MMA-issuing warp -- for the 16/32-channel layers
+// THE pacing resource: 9 small MMAs per 128-pixel tile -- runs a branch-free, fully unrolled tap loop.
+template <int KSTEPS, bool RESIDENT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -85,9 +89,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   const uint32_t bar_a_empty = sbase + 8 * kMaxNA;          // [kMaxNA]
   const uint32_t bar_b_full = sbase + 8 * (2 * kMaxNA);     // [kMaxNB]
   const uint32_t bar_b_empty = bar_b_full + 8 * kMaxNB;     // [kMaxNB]
-  const uint32_t bar_acc_full = bar_b_empty + 8 * kMaxNB;   // [2]
-  const uint32_t bar_acc_empty = bar_acc_full + 16;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
+  const uint32_t bar_acc_full = bar_b_empty + 8 * kMaxNB;   // [kMaxAcc]
+  const uint32_t bar_acc_empty = bar_acc_full + 8 * kMaxAcc;   // [kMaxAcc]
+  static_assert(8 * (2 * kMaxNA + 2 * kMaxNB + 2 * kMaxAcc) <= 768, "barrier slots overflow the header");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 768);
   float* bias_s = reinterpret_cast<float*>(smem + 1024);    // [256]
 
   if (threadIdx.x == 0) {
@@ -99,9 +104,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       mbar_init(bar_b_full + 8 * i, 1);
       mbar_init(bar_b_empty + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 4);
+      mbar_init(bar_acc_empty + 8 * i, 8);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmap);
@@ -146,7 +151,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (packed weight blocks)
     const uint8_t* wsrc = p.wpack + static_cast<size_t>(blockIdx.y) * blocks_per_ntile * p.b_block_bytes;
-    if (p.resident_b) {
+    if (RESIDENT) {
       if (blockIdx.x < p.num_groups && elect_one()) {
         mbar_arrive_expect_tx(bar_b_full, static_cast<uint32_t>(blocks_per_ntile) * p.b_block_bytes);
         for (int blk = 0; blk < blocks_per_ntile; ++blk)
@@ -186,14 +191,77 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const uint32_t a_tile16 = p.a_tile_bytes >> 4, a_stage16 = p.a_stage_bytes >> 4, b_block16 = p.b_block_bytes >> 4;
     int a_stage = 0, b_stage = 0, acc = 0;
     uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
-    if (p.resident_b && blockIdx.x < p.num_groups) {
+    if (RESIDENT && blockIdx.x < p.num_groups) {
       mbar_wait(bar_b_full, 0);
       tc_fence_after();
     }
+    if (p.chunks_per_seg == p.nkc) {
+      // ---- fast path (one K segment = every layer of the forward pass and every 3x3 data gradient)
+      uint32_t tap16[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap16[t] = p.tap_off[t] >> 4;
+      const int ntaps = p.ntaps, nkc = p.nkc, mt = p.mt, n_tile = p.n_tile, na = p.na, nb = p.nb, nacc = p.nacc;
+      const uint32_t acc_cols = p.acc_cols;
+      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+        mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * acc_cols;
+        uint32_t b_res = b_lo0;                               // resident weights: blocks in (chunk, tap) order
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(bar_a_full + 8 * a_stage, a_phase);
+          tc_fence_after();
+          const uint32_t a_base = a_lo0 + a_stage * a_stage16;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if (t < ntaps) {                                  // warp-uniform
+              uint32_t b_base;
+              if (RESIDENT) {
+                b_base = b_res;
+                b_res += b_block16;
+              } else {
+                mbar_wait(bar_b_full + 8 * b_stage, b_phase);
+                tc_fence_after();
+                b_base = b_lo0 + b_stage * b_block16;
+              }
+              const uint32_t a_tap = a_base + tap16[t];
+              const uint32_t acc0 = (kc | t) != 0 ? 1u : 0u;
+              if (elect_one()) {
+                uint32_t d_col = tmem_d, a_t = a_tap;
+                for (int i = 0; i < mt; ++i, d_col += n_tile, a_t += a_tile16) {
+#pragma unroll
+                  for (int j = 0; j < KSTEPS; ++j)
+                    umma_bf16_lohi(d_col, a_t + j * a_kstep, a_hi, b_base + j * b_kstep, b_hi, idesc, j != 0 ? 1u : acc0);
+                }
+                if (!RESIDENT) umma_commit(bar_b_empty + 8 * b_stage);
+              }
+              __syncwarp();
+              if (!RESIDENT) {
+                if (++b_stage == nb) {
+                  b_stage = 0;
+                  b_phase ^= 1;
+                }
+              }
+            }
+          }
+          if (elect_one()) umma_commit(bar_a_empty + 8 * a_stage);
+          __syncwarp();
+          if (++a_stage == na) {
+            a_stage = 0;
+            a_phase ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit(bar_acc_full + 8 * acc);
+        __syncwarp();
+        if (++acc == nacc) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    } else
     for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
       mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * 256;
+      const uint32_t tmem_d = tmem_base + acc * p.acc_cols;
       int blk = 0;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait(bar_a_full + 8 * a_stage, a_phase);
@@ -203,7 +271,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
         const int t_begin = p.seg_tap0[seg], t_end = t_begin + p.seg_ntaps[seg];
         for (int t = t_begin; t < t_end; ++t, ++blk) {
           uint32_t b_base;
-          if (p.resident_b) {
+          if (RESIDENT) {
             b_base = b_lo0 + blk * b_block16;
           } else {
             mbar_wait(bar_b_full + 8 * b_stage, b_phase);
@@ -220,10 +288,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
                 umma_bf16_lohi(tmem_d + i * p.n_tile, a_tap + i * a_tile16 + j * a_kstep, a_hi, b_base + j * b_kstep, b_hi,
                                idesc, j != 0 ? 1u : acc0);
             }
-            if (!p.resident_b) umma_commit(bar_b_empty + 8 * b_stage);
+            if (!RESIDENT) umma_commit(bar_b_empty + 8 * b_stage);
           }
           __syncwarp();
-          if (!p.resident_b) {
+          if (!RESIDENT) {
             if (++b_stage == p.nb) {
               b_stage = 0;
               b_phase ^= 1;
@@ -239,17 +307,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       }
       if (elect_one()) umma_commit(bar_acc_full + 8 * acc);
       __syncwarp();
-      if (++acc == 2) {
+      if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int q = warp - 4;                 // TMEM lane quarter == warp_id % 4
+    // ------------------------------------------------------------------ epilogue (8 warps: two per TMEM lane quarter)
+    // The accumulators of one group are mt * n_tile contiguous TMEM columns. They are drained in 16-column units, two
+    // units per 32-column load; the two warps of a lane quarter take alternate loads and each keeps the next load in
+    // flight while it converts / stores the current one (for the 16-channel layers the epilogue, not the MMA, paces
+    // the kernel: 9 small MMAs per 128-pixel tile against ~150 instructions per thread and tile here).
+    const int q = warp & 3;                 // TMEM lane quarter == warp_id % 4
+    const int eh = (warp - 4) >> 2;         // which of the two interleaved chunk streams
     const int m = q * 32 + lane;            // GEMM row = pixel within the 16 x 8 tile
     const int r = m >> 3, c = m & 7;
     const int n0 = blockIdx.y * p.n_tile;
+    const int units = (p.mt * p.n_tile) >> 4;
+    const int nchunks = (units + 1) >> 1;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
@@ -259,80 +334,98 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       const int tx0 = (rem - ty * p.groups_x) * p.mt;
       const int y = ty * 16 + r;
       const int oy = y * p.out_sy + p.out_oy;
+      const uint32_t tbase = tmem_base + acc * p.acc_cols + (static_cast<uint32_t>(q * 32) << 16);
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
-      for (int ti = 0; ti < p.mt; ++ti) {
-        const int tx = tx0 + ti;
-        if (tx >= p.tiles_x) break;                       // warp-uniform
-        const int x = tx * 8 + c;
-        const bool valid = (y < p.H) && (x < p.W);
-        const int ox = x * p.out_sx + p.out_ox;
-        const uint32_t taddr = tmem_base + acc * 256 + ti * p.n_tile + (static_cast<uint32_t>(q * 32) << 16);
-        for (int colb = 0; colb < p.n_tile; colb += 32) {
-          // two 16-column TMEM loads in flight before the wait
-          uint32_t raw[2][16];
-          const bool two = (colb + 16) < p.n_tile;
-          tmem_ld16(taddr + colb, raw[0]);
-          if (two) tmem_ld16(taddr + colb + 16, raw[1]);
-          tmem_ld_wait();
+
+      auto load = [&](uint32_t (&raw)[2][16], int ch) {
+        tmem_ld16(tbase + ch * 32, raw[0]);
+        if (2 * ch + 1 < units) tmem_ld16(tbase + ch * 32 + 16, raw[1]);
+      };
+      auto process = [&](uint32_t (&raw)[2][16], int ch) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half == 1 && !two) break;
-            const int col0 = colb + 16 * half;
-            float v[16];
+        for (int half = 0; half < 2; ++half) {
+          const int u = 2 * ch + half;
+          if (u >= units) break;                            // warp-uniform
+          const int col = u << 4;
+          const int ti = col / p.n_tile;
+          const int col0 = col - ti * p.n_tile;
+          const int tx = tx0 + ti;
+          if (tx >= p.tiles_x) continue;                    // warp-uniform
+          const int x = tx * 8 + c;
+          const bool valid = (y < p.H) && (x < p.W);
+          const int ox = x * p.out_sx + p.out_ox;
+          float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[half][i]) + bias_s[col0 + i], p.act);
-            if (p.out_mode == 0) {
-              const int plane = (n0 + col0) >> 3;
-              if (p.out != nullptr && valid && (n0 + col0) < p.cout) {
-                uint4* o = reinterpret_cast<uint4*>(p.out);
-                const size_t px = (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * p.out_H + oy;
-                o[px * p.out_W + ox] = pack8_bf16(v);
-                if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(p.out_H)) * p.out_W + ox] = pack8_bf16(v + 8);
-              }
-              if (p.pool_out != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  float t = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-                  v[i] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
-                }
-                if (valid && !(c & 1) && !(r & 1) && (n0 + col0) < p.cout) {
-                  const int ph = p.H >> 1, pw = p.W >> 1;
-                  uint4* o = reinterpret_cast<uint4*>(p.pool_out);
-                  const size_t px = (static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * ph + (y >> 1);
-                  o[px * pw + (x >> 1)] = pack8_bf16(v);
-                  if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = pack8_bf16(v + 8);
-                }
-              }
-            } else if (p.out_mode == 2) {
-              // fp32 planar-8 logits [N][planes][H][W][8]: 32 contiguous bytes per thread and plane
-              if (valid && (n0 + col0) < p.cout) {
-                float4* o = reinterpret_cast<float4*>(p.out);
-                const size_t px = ((static_cast<size_t>(n) * p.out_planes + p.out_plane_off + ((n0 + col0) >> 3)) * p.out_H + oy) *
-                                      p.out_W + ox;
-                o[px * 2] = make_float4(v[0], v[1], v[2], v[3]);
-                o[px * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
-                if ((n0 + col0 + 8) < p.cout) {
-                  const size_t px2 = px + static_cast<size_t>(p.out_H) * p.out_W;
-                  o[px2 * 2] = make_float4(v[8], v[9], v[10], v[11]);
-                  o[px2 * 2 + 1] = make_float4(v[12], v[13], v[14], v[15]);
-                }
-              }
-            } else if (valid) {
-              float* o = reinterpret_cast<float*>(p.out);
+          for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[half][i]) + bias_s[col0 + i], p.act);
+          if (p.out_mode == 0) {
+            const int plane = (n0 + col0) >> 3;
+            if (p.out != nullptr && valid && (n0 + col0) < p.cout) {
+              uint4* o = reinterpret_cast<uint4*>(p.out);
+              const size_t px = (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * p.out_H + oy;
+              o[px * p.out_W + ox] = pack8_bf16(v);
+              if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(p.out_H)) * p.out_W + ox] = pack8_bf16(v + 8);
+            }
+            if (p.pool_out != nullptr) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int co = n0 + col0 + i;
-                if (co < p.cout) o[((static_cast<size_t>(n) * p.cout + co) * p.out_H + oy) * p.out_W + ox] = v[i];
+                float t = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                v[i] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
+              }
+              if (valid && !(c & 1) && !(r & 1) && (n0 + col0) < p.cout) {
+                const int ph = p.H >> 1, pw = p.W >> 1;
+                uint4* o = reinterpret_cast<uint4*>(p.pool_out);
+                const size_t px = (static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * ph + (y >> 1);
+                o[px * pw + (x >> 1)] = pack8_bf16(v);
+                if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = pack8_bf16(v + 8);
               }
             }
+          } else if (p.out_mode == 2) {
+            // fp32 planar-8 logits [N][planes][H][W][8]: 32 contiguous bytes per thread and plane
+            if (valid && (n0 + col0) < p.cout) {
+              float4* o = reinterpret_cast<float4*>(p.out);
+              const size_t px = ((static_cast<size_t>(n) * p.out_planes + p.out_plane_off + ((n0 + col0) >> 3)) * p.out_H + oy) *
+                                    p.out_W + ox;
+              o[px * 2] = make_float4(v[0], v[1], v[2], v[3]);
+              o[px * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+              if ((n0 + col0 + 8) < p.cout) {
+                const size_t px2 = px + static_cast<size_t>(p.out_H) * p.out_W;
+                o[px2 * 2] = make_float4(v[8], v[9], v[10], v[11]);
+                o[px2 * 2 + 1] = make_float4(v[12], v[13], v[14], v[15]);
+              }
+            }
+          } else if (valid) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int co = n0 + col0 + i;
+              if (co < p.cout) o[((static_cast<size_t>(n) * p.cout + co) * p.out_H + oy) * p.out_W + ox] = v[i];
+            }
           }
+        }
+      };
+
+      uint32_t raw_a[2][16], raw_b[2][16];
+      int ch = eh;
+      if (ch < nchunks) {
+        load(raw_a, ch);
+        while (true) {
+          tmem_ld_wait();
+          if (ch + 2 < nchunks) load(raw_b, ch + 2);
+          process(raw_a, ch);
+          ch += 2;
+          if (ch >= nchunks) break;
+          tmem_ld_wait();
+          if (ch + 2 < nchunks) load(raw_a, ch + 2);
+          process(raw_b, ch);
+          ch += 2;
+          if (ch >= nchunks) break;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
-      if (++acc == 2) {
+      if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -483,6 +576,10 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
     }
   }
   ABC_REQUIRE(p.mt >= 1, "abc_conv_igemm: cin=%d n_tile=%d does not fit in shared memory", d->cin, d->n_tile);
+  p.acc_cols = p.mt * d->n_tile;
+  p.nacc = kTmemCols / p.acc_cols;
+  if (p.nacc > kMaxAcc) p.nacc = kMaxAcc;
+  if (const char* e = getenv("ABCNET_NACC")) { int v = atoi(e); if (v >= 2 && v < p.nacc) p.nacc = v; }
   p.groups_x = (p.tiles_x + p.mt - 1) / p.mt;
   const int64_t groups = static_cast<int64_t>(d->N) * p.groups_x * p.tiles_y;
   ABC_REQUIRE(groups < (1ll << 31), "abc_conv_igemm: too many tiles");
@@ -520,11 +617,15 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   }
 
   typedef void (*KernelFn)(const CUtensorMap, const ConvKParams);
-  KernelFn kernels[5] = {nullptr, conv_igemm_kernel<1>, conv_igemm_kernel<2>, conv_igemm_kernel<3>, conv_igemm_kernel<4>};
+  KernelFn kernels[2][5] = {{nullptr, conv_igemm_kernel<1, false>, conv_igemm_kernel<2, false>, conv_igemm_kernel<3, false>,
+                             conv_igemm_kernel<4, false>},
+                            {nullptr, conv_igemm_kernel<1, true>, conv_igemm_kernel<2, true>, conv_igemm_kernel<3, true>,
+                             conv_igemm_kernel<4, true>}};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int k = 1; k <= 4; ++k)
-      ABC_CUDA(cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    for (int r = 0; r < 2; ++r)
+      for (int k = 1; k <= 4; ++k)
+        ABC_CUDA(cudaFuncSetAttribute(kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   const int ksteps = p.kp / 2;
@@ -536,6 +637,6 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   if (gx < 1) gx = 1;
   if (gx > p.num_groups) gx = p.num_groups;
   dim3 grid(gx, n_tiles, 1);
-  kernels[ksteps]<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
+  kernels[p.resident_b ? 1 : 0][ksteps]<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
   return launch_check("conv_igemm_kernel");
 }

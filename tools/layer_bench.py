@@ -16,7 +16,7 @@ from abcnet_b200.unet import _Packed  # noqa: E402
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
 
-def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, mt=None, iters=5, act=1):
+def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, mt=None, iters=5, act=1, nacc=None):
     dev = torch.device("cuda")
     g = torch.Generator(device="cuda").manual_seed(0)
     src = (torch.rand((B, cin // 8, H, W, 8), device=dev, generator=g) - 0.5).to(torch.bfloat16)
@@ -47,6 +47,10 @@ def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, 
         os.environ["ABCNET_MT"] = str(mt)
     else:
         os.environ.pop("ABCNET_MT", None)
+    if nacc is not None:
+        os.environ["ABCNET_NACC"] = str(nacc)
+    else:
+        os.environ.pop("ABCNET_NACC", None)
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
         _lib.check(_lib.lib.abc_conv_igemm(C.byref(d), st))
@@ -60,7 +64,7 @@ def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, 
     ms = a.elapsed_time(b) / iters
     flops = 2.0 * B * H * W * cout * cin * len(taps)
     byts = src.numel() * 2 + out_bytes
-    print(f"{name:28s} B={B:3d} {cin:4d}->{cout:4d} @{H}x{W} n_tile={n_tile:3d} mt={mt}  {ms:8.3f} ms  "
+    print(f"{name:28s} B={B:3d} {cin:4d}->{cout:4d} @{H}x{W} n_tile={n_tile:3d} mt={mt} nacc={nacc}  {ms:8.3f} ms  "
           f"{flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s", flush=True)
     return ms
 
@@ -75,6 +79,23 @@ if __name__ == "__main__":
             bench("32->32@256", 64, 32, 32, 256, 256, 32, mt=mt)
         for mt in (1, 2, 4):
             bench("64->64@128", 256, 64, 64, 128, 128, 64, mt=mt)
+    if which == "one16":                      # single configuration for ncu captures: layer_bench.py one16 [mt]
+        bench("16->16@512", 64, 16, 16, 512, 512, 16, mt=int(sys.argv[2]) if len(sys.argv) > 2 else None, iters=1)
+    if which == "one128":
+        bench("128->128@128", 256, 128, 128, 128, 128, 128, iters=1)
+    if which in ("sweep",):
+        for mt in (2, 4, 8):
+            for nacc in (2, 4, 8):
+                bench("16->16@512", 64, 16, 16, 512, 512, 16, mt=mt, nacc=nacc)
+        for mt in (2, 4, 8):
+            for nacc in (2, 4, 8):
+                bench("32->32@256", 64, 32, 32, 256, 256, 32, mt=mt, nacc=nacc)
+        for mt in (1, 2, 4):
+            for nacc in (2, 4, 8):
+                bench("64->64@128", 256, 64, 64, 128, 128, 64, mt=mt, nacc=nacc)
+        for mt in (1, 2):
+            for nacc in (2, 4):
+                bench("128->128@128", 256, 128, 128, 128, 128, 128, mt=mt, nacc=nacc)
     if which in ("all", "mid"):
         for nt, mt in ((128, 1), (128, 2), (64, 1), (64, 2)):
             bench("128->128@128", 256, 128, 128, 128, 128, nt, mt=mt)
