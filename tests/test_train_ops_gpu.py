@@ -184,9 +184,11 @@ def test_fused_loss_mode_and_scaled_p8_conversion():
     t1, p1, ds1, d1, hs1 = loss_forward_backward(s, tw, tg, logits, scaled=True)
     t2, p2, ds2, d2, hs2 = loss_forward_backward(s, tw, tg, logits, scaled=False)
     assert hs1 is None and hs2.shape == (8,)
-    assert t1.item() == t2.item() and torch.equal(ds1, ds2)
+    # fp64 atomics: the accumulation order differs from launch to launch -> equal to ~1e-15 relative, not bitwise
+    assert abs(t1.item() - t2.item()) <= 1e-12 * abs(t1.item())
+    assert_close(ds2.cpu(), ds1.cpu(), 1e-12, 1e-15, "ds")
     for i in range(8):
-        assert_close((d2[i] * hs2[i]).cpu(), d1[i].cpu(), 1e-6, 1e-12, f"dlogits {i}")
+        assert_close((d2[i] * hs2[i]).cpu(), d1[i].cpu(), 2e-6, 1e-12, f"dlogits {i}")
     for i, g in enumerate(d2):
         N, Cc, H, W = g.shape
         planes = (Cc + 15) // 16 * 2
