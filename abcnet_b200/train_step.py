@@ -41,6 +41,7 @@ class TrainStep:
                 if p.grad is None:
                     p.grad = torch.zeros_like(p)
         self.graph = None
+        self.launches_per_step = 0
         self._x = self._tg = None
         self.loss = torch.zeros((), dtype=torch.float64, device=dev)
         self.parts = torch.zeros(8, dtype=torch.float64, device=dev)
@@ -126,8 +127,10 @@ class TrainStep:
                             else:
                                 v.zero_()
         self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self._enqueue(self._x, self._tg, self._opt_in_graph)
+        self.launches_per_step = _lib.launch_count() - l0      # kernels of this library inside one replay
 
 
 def make_optimizer(model, lr: float = 2.5e-4, weight_decay: float = 1e-8, capturable: bool = True):

@@ -160,6 +160,60 @@ def run_reference(args, rank, world):
     print(json.dumps(out))
 
 
+# ----------------------------------------------------------------------------------------- GPU arm: training step
+TRAIN_FLOPS_PER_IMAGE = 281.9e9    # fprop + dgrad + wgrad
+
+
+def run_train(args, rank, world, dev):
+    """BASELINE.json configs[3] / [4]: one training iteration = forward (batch-statistics BN, dropout 0.2) + the 8 fused
+    losses + full backward + bucketed NCCL gradient all-reduce (world > 1, overlapped with backward) + Adam, at the
+    reference's batch size (train.py:44: 64 per GPU), replayed as one CUDA graph. Inputs resident in HBM."""
+    import torch.distributed as dist
+
+    import abcnet_b200
+    from abcnet_b200.ddp import GradBuckets
+    from oracle import synth
+    B = args.train_batch
+    model = abcnet_b200.UNet(1, HEADS).to(dev)
+    model.load_state_dict(make_weights())
+    model.train()
+    buckets = GradBuckets(list(model.parameters())) if world > 1 else None
+    opt = abcnet_b200.make_optimizer(model, capturable=True)
+    step = abcnet_b200.TrainStep(model, opt, class_weights=True, buckets=buckets, use_graph=True)
+    x = make_images(2000 + rank, 8).repeat((B + 7) // 8, 1, 1, 1)[:B].contiguous().to(dev)
+    tg = [torch.from_numpy(t).repeat(*([(B + 7) // 8] + [1] * (t.ndim - 1)))[:B].contiguous().to(dev)
+          for t in synth.dense_targets(rank, 8, 128, 128)]
+    from abcnet_b200 import _lib
+    for _ in range(max(args.warmup, 3)):
+        loss = step(x, tg)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x, tg)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    v = world * B * args.steps / (ms * 1e-3)
+    return {"metric": "images_per_sec_train_step", "value": v, "unit": UNIT, "ms_per_step": ms / args.steps,
+            "batch_per_gpu": B, "scaling": "weak", "dtype": "bf16 activations / fp32 master weights, accumulators and gradients",
+            "workload": "forward (train-mode BN, dropout) + 8 losses + backward + gradient all-reduce + Adam, 1x512x512 images, "
+                        "dense targets resident in HBM (BASELINE configs[3]/[4])",
+            "whole_step_tflops": TRAIN_FLOPS_PER_IMAGE * v / 1e12, "loss": float(loss.item()),
+            "replay": "one CUDA graph per iteration (kernels counted at capture: %d)" % step.launches_per_step,
+            "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
@@ -269,6 +323,12 @@ def run_ours(args, rank, world, local_rank):
         ms, ms_e2e = t.tolist()
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    train = None
+    if not args.no_train:
+        model._bufs.clear()
+        out_bufs = xbuf = x = None
+        torch.cuda.empty_cache()
+        train = run_train(args, rank, world, dev)
     if rank != 0:
         return
     pk, pk_src = peaks()
@@ -303,7 +363,7 @@ def run_ours(args, rank, world, local_rank):
            "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms_e2e / args.steps},
-           "gpu_launches": int(launches), "clocks": clocks}
+           "gpu_launches": int(launches), "clocks": clocks, "train": train}
     print(json.dumps(out))
 
 
@@ -317,6 +377,8 @@ def main():
     ap.add_argument("--atom-cap", type=int, default=1024)
     ap.add_argument("--bond-cap", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (the 'train' object)")
+    ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step (train.py:44)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
