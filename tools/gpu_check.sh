@@ -1,0 +1,17 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench line, ncu launch list of the bench command, ncu full capture of the dominant kernel.
+# Usage (from the repo root): gpurun --timeout 1500 -- 'bash tools/gpu_check.sh <tag>'
+TAG=${1:-run}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/${TAG}_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
+tail -3 gpurun_out/${TAG}_pytest.log
+timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+echo "bench exit $?"; tail -c 3000 gpurun_out/${TAG}_bench.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/${TAG}_ncu_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 37 -c 1 -f -o gpurun_out/${TAG}_heads_conv1 \
+    python tools/prof_forward.py 64 > gpurun_out/${TAG}_ncu_full.log 2>&1
+echo done
