@@ -73,6 +73,23 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   return r;
 }
 
+__device__ __forceinline__ uint32_t pool_max_bf16x2(uint32_t a) {
+  uint32_t b = __shfl_xor_sync(0xffffffffu, a, 1);
+  __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  a = *reinterpret_cast<uint32_t*>(&m);
+  b = __shfl_xor_sync(0xffffffffu, a, 8);
+  m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&m);
+}
+
+__device__ __forceinline__ uint4 pool_max_bf16x8(uint4 q) {
+  q.x = pool_max_bf16x2(q.x);
+  q.y = pool_max_bf16x2(q.y);
+  q.z = pool_max_bf16x2(q.z);
+  q.w = pool_max_bf16x2(q.w);
+  return q;
+}
+
 // KSTEPS: K-steps of 16 channels per pipeline stage = kp / 2 (1, 2, 3 or 4). RESIDENT: the layer's weights of one n-tile
 // stay in shared memory (no B ring). Both are compile-time so that the MMA-issuing warp -- for the 16/32-channel layers
 // THE pacing resource: 9 small MMAs per 128-pixel tile -- runs a branch-free, fully unrolled tap loop.
@@ -360,24 +377,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
           for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[half][i]) + bias_s[col0 + i], p.act);
           if (p.out_mode == 0) {
             const int plane = (n0 + col0) >> 3;
+            uint4 q0 = pack8_bf16(v), q1 = pack8_bf16(v + 8);
             if (p.out != nullptr && valid && (n0 + col0) < p.cout) {
               uint4* o = reinterpret_cast<uint4*>(p.out);
               const size_t px = (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * p.out_H + oy;
-              o[px * p.out_W + ox] = pack8_bf16(v);
-              if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(p.out_H)) * p.out_W + ox] = pack8_bf16(v + 8);
+              o[px * p.out_W + ox] = q0;
+              if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(p.out_H)) * p.out_W + ox] = q1;
             }
             if (p.pool_out != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float t = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-                v[i] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 8));
-              }
+              // 2x2 max-pool on the packed bf16 pairs (rounding is monotonic: max of rounded == rounded max), lane <-> pixel:
+              // xor 1 = x neighbour, xor 8 = y neighbour. 16 shuffles per 16 channels instead of 32.
+              q0 = pool_max_bf16x8(q0);
+              q1 = pool_max_bf16x8(q1);
               if (valid && !(c & 1) && !(r & 1) && (n0 + col0) < p.cout) {
                 const int ph = p.H >> 1, pw = p.W >> 1;
                 uint4* o = reinterpret_cast<uint4*>(p.pool_out);
                 const size_t px = (static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * ph + (y >> 1);
-                o[px * pw + (x >> 1)] = pack8_bf16(v);
-                if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = pack8_bf16(v + 8);
+                o[px * pw + (x >> 1)] = q0;
+                if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = q1;
               }
             }
           } else if (p.out_mode == 2) {
