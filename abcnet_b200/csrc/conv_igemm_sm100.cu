@@ -43,7 +43,8 @@ struct ConvKParams {
   int chunks_per_seg, blocks_per_ntile;      // K segments: chunk kc uses taps [seg_tap0[s], seg_tap0[s] + seg_ntaps[s]), s = kc / chunks_per_seg
   int seg_tap0[4], seg_ntaps[4];
   uint32_t a_stage_bytes, a_tile_bytes, a_plane_bytes, a_row_bytes, b_block_bytes;
-  uint32_t tap_off[9];
+  uint32_t tap_off[18];
+  int fold;                                  // row folding J (1, 2, 4): GEMM column = (16-channel block, row j, channel)
   uint32_t smem_a_off, smem_b_off;
   const uint8_t* wpack;
   const float* bias;
@@ -80,6 +81,25 @@ __device__ __forceinline__ uint32_t pool_max_bf16x2(uint32_t a) {
   b = __shfl_xor_sync(0xffffffffu, a, 8);
   m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&m);
+}
+
+__device__ __forceinline__ uint32_t hmax_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&m);
+}
+
+__device__ __forceinline__ uint4 hmax_bf16x8(uint4 a, uint4 b) {
+  return make_uint4(hmax_bf16x2(a.x, b.x), hmax_bf16x2(a.y, b.y), hmax_bf16x2(a.z, b.z), hmax_bf16x2(a.w, b.w));
+}
+
+// max with the horizontally adjacent pixel (lane ^ 1)
+__device__ __forceinline__ uint4 pool_hmax_x(uint4 q) {
+  uint4 o;
+  o.x = __shfl_xor_sync(0xffffffffu, q.x, 1);
+  o.y = __shfl_xor_sync(0xffffffffu, q.y, 1);
+  o.z = __shfl_xor_sync(0xffffffffu, q.z, 1);
+  o.w = __shfl_xor_sync(0xffffffffu, q.w, 1);
+  return hmax_bf16x8(q, o);
 }
 
 __device__ __forceinline__ uint4 pool_max_bf16x8(uint4 q) {
@@ -130,6 +150,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   }
   if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
   for (int i = threadIdx.x; i < p.n_tile; i += kThreads) bias_s[i] = p.bias[blockIdx.y * p.n_tile + i];
+  uint32_t* utab = reinterpret_cast<uint32_t*>(smem + 800);   // [<= 32] per-unit constants of the epilogue
+  if (threadIdx.x < ((p.mt * p.n_tile) >> 4)) {
+    const int col = threadIdx.x << 4;
+    const int ti = col / p.n_tile;
+    const int ul = (col - ti * p.n_tile) >> 4;               // 16-column unit within the tile = bias unit
+    const int b16 = ul / p.fold;
+    utab[threadIdx.x] = static_cast<uint32_t>(ti) | (ul << 8) | (b16 << 16) | ((ul - b16 * p.fold) << 24);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -149,7 +177,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       const int rem = g - n * groups_per_img;
       const int ty = rem / p.groups_x;
       const int tx0 = (rem - ty * p.groups_x) * p.mt;
-      const int c1 = ty * 16 - p.halo;
+      const int c1 = ty * 16 * p.fold - p.halo;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait(bar_a_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
@@ -199,7 +227,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
     // descriptors as (lo, hi) halves: hi is constant, lo = (smem address >> 4) advances by plain 32-bit adds
-    const uint64_t a_hi64 = umma_desc_hi(p.a_plane_bytes, p.a_row_bytes);   // LBO = plane pitch, SBO = tile-row pitch
+    const uint64_t a_hi64 = umma_desc_hi(p.a_plane_bytes, p.a_row_bytes * p.fold);   // LBO = plane pitch, SBO = pitch of J tile rows
     const uint64_t b_hi64 = umma_desc_hi(p.n_tile * 16, 128);              // LBO = plane pitch, SBO = 8 rows * 16 B
     const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), b_hi = static_cast<uint32_t>(b_hi64 >> 32);
     const uint32_t a_lo0 = static_cast<uint32_t>(a_hi64) | (a_region >> 4);
@@ -214,9 +242,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     }
     if (p.chunks_per_seg == p.nkc) {
       // ---- fast path (one K segment = every layer of the forward pass and every 3x3 data gradient)
-      uint32_t tap16[9];
+      uint32_t tap16[18];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) tap16[t] = p.tap_off[t] >> 4;
+      for (int t = 0; t < 18; ++t) tap16[t] = p.tap_off[t] >> 4;
       const int ntaps = p.ntaps, nkc = p.nkc, mt = p.mt, n_tile = p.n_tile, na = p.na, nb = p.nb, nacc = p.nacc;
       const uint32_t acc_cols = p.acc_cols;
       for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
@@ -229,7 +257,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
           tc_fence_after();
           const uint32_t a_base = a_lo0 + a_stage * a_stage16;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
+          for (int t = 0; t < 18; ++t) {
             if (t < ntaps) {                                  // warp-uniform
               uint32_t b_base;
               if (RESIDENT) {
@@ -333,8 +361,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     // ------------------------------------------------------------------ epilogue (8 warps: two per TMEM lane quarter)
     // The accumulators of one group are mt * n_tile contiguous TMEM columns. They are drained in 16-column units, two
     // units per 32-column load; the two warps of a lane quarter take alternate loads and each keeps the next load in
-    // flight while it converts / stores the current one (for the 16-channel layers the epilogue, not the MMA, paces
-    // the kernel: 9 small MMAs per 128-pixel tile against ~150 instructions per thread and tile here).
+    // flight while it converts / stores the current one. For the 16 / 32-channel layers and the 1x1 heads this loop, not
+    // the MMA, paces the kernel (ncu source view), so per-unit integer work is table-driven: utab[u] holds what depends on
+    // the unit index only, everything that depends on the group is hoisted out of the unit loop.
     const int q = warp & 3;                 // TMEM lane quarter == warp_id % 4
     const int eh = (warp - 4) >> 2;         // which of the two interleaved chunk streams
     const int m = q * 32 + lane;            // GEMM row = pixel within the 16 x 8 tile
@@ -342,6 +371,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const int n0 = blockIdx.y * p.n_tile;
     const int units = (p.mt * p.n_tile) >> 4;
     const int nchunks = (units + 1) >> 1;
+    const float slope = p.act == 1 ? 0.f : (p.act == 2 ? 0.01f : 1.f);     // act(v) = max(v, slope * v)
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
+    const size_t out_plane_px = static_cast<size_t>(p.out_H) * p.out_W;
+    const int ph = p.H >> 1, pw = p.W >> 1;
+    const size_t pool_plane_px = static_cast<size_t>(ph) * pw;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
@@ -349,8 +383,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       const int rem = g - n * groups_per_img;
       const int ty = rem / p.groups_x;
       const int tx0 = (rem - ty * p.groups_x) * p.mt;
-      const int y = ty * 16 + r;
-      const int oy = y * p.out_sy + p.out_oy;
+      const int ybase = (ty * 16 + r) * p.fold;            // row of this thread's pixel (fold: of its first pixel)
+      const int xbase = tx0 * 8 + c;
+      // pixel offset of (ybase, xbase) in one output plane, and the plane index of channel n0 of image n
+      const size_t out_px0 = static_cast<size_t>(ybase * p.out_sy + p.out_oy) * p.out_W + (xbase * p.out_sx + p.out_ox);
+      const size_t out_pl0 = static_cast<size_t>(n) * p.out_planes + p.out_plane_off + (n0 >> 3);
+      const size_t pool_px0 = static_cast<size_t>(ybase >> 1) * pw + (xbase >> 1);
+      const size_t pool_pl0 = static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + (n0 >> 3);
       const uint32_t tbase = tmem_base + acc * p.acc_cols + (static_cast<uint32_t>(q * 32) << 16);
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
@@ -360,64 +399,83 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
         if (2 * ch + 1 < units) tmem_ld16(tbase + ch * 32 + 16, raw[1]);
       };
       auto process = [&](uint32_t (&raw)[2][16], int ch) {
+        uint4 keep0 = make_uint4(0, 0, 0, 0), keep1 = keep0;    // fold + pool: the even row's packed values
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int u = 2 * ch + half;
           if (u >= units) break;                            // warp-uniform
-          const int col = u << 4;
-          const int ti = col / p.n_tile;
-          const int col0 = col - ti * p.n_tile;
-          const int tx = tx0 + ti;
-          if (tx >= p.tiles_x) continue;                    // warp-uniform
-          const int x = tx * 8 + c;
-          const bool valid = (y < p.H) && (x < p.W);
-          const int ox = x * p.out_sx + p.out_ox;
+          // utab[u] = (tile ti | bias unit << 8 | 16-channel block b << 16 | folded row j << 24); without folding j == 0
+          const uint32_t info = utab[u];
+          const int ti = info & 0xff, bu = (info >> 8) & 0xff, b16 = (info >> 16) & 0xff, j = info >> 24;
+          if (tx0 + ti >= p.tiles_x) continue;              // warp-uniform
+          const int ch0 = n0 + (b16 << 4);
+          const int y = ybase + j;
+          const int x = xbase + ti * 8;
+          const bool valid = (y < p.H) && (x < p.W) && (ch0 < p.cout);
+          const bool two = (ch0 + 8) < p.cout;
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(raw[half][i]) + bias_s[col0 + i], p.act);
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = bias4[bu * 4 + i];
+            float t0 = __uint_as_float(raw[half][4 * i + 0]) + bb.x, t1 = __uint_as_float(raw[half][4 * i + 1]) + bb.y;
+            float t2 = __uint_as_float(raw[half][4 * i + 2]) + bb.z, t3 = __uint_as_float(raw[half][4 * i + 3]) + bb.w;
+            v[4 * i + 0] = fmaxf(t0, t0 * slope);
+            v[4 * i + 1] = fmaxf(t1, t1 * slope);
+            v[4 * i + 2] = fmaxf(t2, t2 * slope);
+            v[4 * i + 3] = fmaxf(t3, t3 * slope);
+          }
           if (p.out_mode == 0) {
-            const int plane = (n0 + col0) >> 3;
             uint4 q0 = pack8_bf16(v), q1 = pack8_bf16(v + 8);
-            if (p.out != nullptr && valid && (n0 + col0) < p.cout) {
-              uint4* o = reinterpret_cast<uint4*>(p.out);
-              const size_t px = (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + plane) * p.out_H + oy;
-              o[px * p.out_W + ox] = q0;
-              if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(p.out_H)) * p.out_W + ox] = q1;
+            if (p.out != nullptr && valid) {
+              uint4* o = reinterpret_cast<uint4*>(p.out) + (out_pl0 + 2 * b16) * out_plane_px + out_px0 +
+                         static_cast<size_t>(j * p.out_sy) * p.out_W + ti * 8 * p.out_sx;
+              o[0] = q0;
+              if (two) o[out_plane_px] = q1;
             }
             if (p.pool_out != nullptr) {
-              // 2x2 max-pool on the packed bf16 pairs (rounding is monotonic: max of rounded == rounded max), lane <-> pixel:
-              // xor 1 = x neighbour, xor 8 = y neighbour. 16 shuffles per 16 channels instead of 32.
-              q0 = pool_max_bf16x8(q0);
-              q1 = pool_max_bf16x8(q1);
-              if (valid && !(c & 1) && !(r & 1) && (n0 + col0) < p.cout) {
-                const int ph = p.H >> 1, pw = p.W >> 1;
-                uint4* o = reinterpret_cast<uint4*>(p.pool_out);
-                const size_t px = (static_cast<size_t>(n) * p.pool_planes + p.pool_plane_off + plane) * ph + (y >> 1);
-                o[px * pw + (x >> 1)] = q0;
-                if ((n0 + col0 + 8) < p.cout) o[(px + static_cast<size_t>(ph)) * pw + (x >> 1)] = q1;
+              // 2x2 max-pool on the packed bf16 pairs (rounding is monotonic: max of rounded == rounded max).
+              bool write;
+              if (p.fold == 1) {
+                // lane <-> pixel: xor 1 = x neighbour, xor 8 = y neighbour
+                q0 = pool_max_bf16x8(q0);
+                q1 = pool_max_bf16x8(q1);
+                write = !(c & 1) && !(r & 1);
+              } else {
+                // folded rows: the vertical neighbour (j ^ 1) is the other half of this chunk, in the same thread
+                if (half == 0) {
+                  keep0 = q0;
+                  keep1 = q1;
+                  continue;
+                }
+                q0 = pool_hmax_x(hmax_bf16x8(q0, keep0));
+                q1 = pool_hmax_x(hmax_bf16x8(q1, keep1));
+                write = !(c & 1);
+              }
+              if (valid && write) {
+                uint4* o = reinterpret_cast<uint4*>(p.pool_out) + (pool_pl0 + 2 * b16) * pool_plane_px + pool_px0 +
+                           static_cast<size_t>(j >> 1) * pw + ti * 4;
+                o[0] = q0;
+                if (two) o[pool_plane_px] = q1;
               }
             }
           } else if (p.out_mode == 2) {
             // fp32 planar-8 logits [N][planes][H][W][8]: 32 contiguous bytes per thread and plane
-            if (valid && (n0 + col0) < p.cout) {
-              float4* o = reinterpret_cast<float4*>(p.out);
-              const size_t px = ((static_cast<size_t>(n) * p.out_planes + p.out_plane_off + ((n0 + col0) >> 3)) * p.out_H + oy) *
-                                    p.out_W + ox;
-              o[px * 2] = make_float4(v[0], v[1], v[2], v[3]);
-              o[px * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
-              if ((n0 + col0 + 8) < p.cout) {
-                const size_t px2 = px + static_cast<size_t>(p.out_H) * p.out_W;
-                o[px2 * 2] = make_float4(v[8], v[9], v[10], v[11]);
-                o[px2 * 2 + 1] = make_float4(v[12], v[13], v[14], v[15]);
+            if (valid) {
+              float4* o = reinterpret_cast<float4*>(p.out) + 2 * ((out_pl0 + 2 * b16) * out_plane_px + out_px0 + ti * 8 * p.out_sx);
+              o[0] = make_float4(v[0], v[1], v[2], v[3]);
+              o[1] = make_float4(v[4], v[5], v[6], v[7]);
+              if (two) {
+                o += 2 * out_plane_px;
+                o[0] = make_float4(v[8], v[9], v[10], v[11]);
+                o[1] = make_float4(v[12], v[13], v[14], v[15]);
               }
             }
           } else if (valid) {
-            float* o = reinterpret_cast<float*>(p.out);
+            float* o = reinterpret_cast<float*>(p.out) + (static_cast<size_t>(n) * p.cout + ch0) * out_plane_px + out_px0 +
+                       ti * 8 * p.out_sx;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int co = n0 + col0 + i;
-              if (co < p.cout) o[((static_cast<size_t>(n) * p.cout + co) * p.out_H + oy) * p.out_W + ox] = v[i];
-            }
+            for (int i = 0; i < 16; ++i)
+              if (ch0 + i < p.cout) o[i * out_plane_px] = v[i];
           }
         }
       };
@@ -483,7 +541,7 @@ static int conv_kc(int cin) { return cin < 64 ? cin : 64; }
 }  // namespace abc
 
 extern "C" int64_t abc_conv_wpack_bytes(int cin, int cout, int ntaps, int n_tile) {
-  if (cin <= 0 || cin % 16 || n_tile < 16 || n_tile > 256 || n_tile % 16 || ntaps < 1 || ntaps > 9 || cout < 1) return -1;
+  if (cin <= 0 || cin % 16 || n_tile < 16 || n_tile > 256 || n_tile % 16 || ntaps < 1 || ntaps > 18 || cout < 1) return -1;
   const int n_tiles = (cout + n_tile - 1) / n_tile;
   return static_cast<int64_t>(n_tiles) * n_tile * cin * ntaps * 2;
 }
@@ -504,6 +562,15 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   ABC_REQUIRE(d->out_mode >= 0 && d->out_mode <= 2, "abc_conv_igemm: out_mode=%d", d->out_mode);
   ABC_REQUIRE((reinterpret_cast<uintptr_t>(d->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->wpack) & 15) == 0,
               "abc_conv_igemm: input / weights must be 16-byte aligned");
+  const int fold = d->row_fold > 1 ? d->row_fold : 1;
+  if (fold > 1) {
+    // Row folding (16 / 32-channel layers): J vertically adjacent output pixels share one GEMM row, GEMM N = J * cout.
+    ABC_REQUIRE(fold == 2 || fold == 4, "abc_conv_igemm: row_fold=%d must be 1, 2 or 4", fold);
+    ABC_REQUIRE(d->ntaps == 9 && d->k_segments <= 1, "abc_conv_igemm: row_fold needs the plain 3x3 tap set");
+    ABC_REQUIRE(d->cout % 16 == 0 && d->n_tile == fold * d->cout, "abc_conv_igemm: row_fold needs n_tile == row_fold * cout (cout %% 16 == 0)");
+    ABC_REQUIRE(d->out_mode == 0 && d->out_sy == 1 && d->out_sx == 1 && d->out_oy == 0 && d->out_ox == 0,
+                "abc_conv_igemm: row_fold supports plain P8 outputs only");
+  }
   int halo = 0;
   for (int t = 0; t < d->ntaps; ++t) {
     ABC_REQUIRE(d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1,
@@ -532,21 +599,27 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   ConvKParams p{};
   p.N = d->N; p.H = d->H; p.W = d->W;
   p.tiles_x = (d->W + 7) / 8;
-  p.tiles_y = (d->H + 15) / 16;
+  p.fold = fold;
+  p.tiles_y = (d->H + 16 * fold - 1) / (16 * fold);
   p.in_plane_off = d->in_plane_off;
   const int kc = conv_kc(d->cin);
   p.kp = kc / 8;
   p.nkc = d->cin / kc;
-  p.ntaps = d->ntaps;
+  p.ntaps = fold > 1 ? 3 * (fold + 2) : d->ntaps;
   p.halo = halo;
   p.n_tile = d->n_tile;
-  const int rows = 16 + 2 * halo, cols = 8 + 2 * halo;
+  const int rows = 16 * fold + 2 * halo, cols = 8 + 2 * halo;
   p.a_row_bytes = cols * 16;
   p.a_plane_bytes = rows * p.a_row_bytes;
   p.a_tile_bytes = p.kp * p.a_plane_bytes;
   p.b_block_bytes = static_cast<uint32_t>(d->n_tile) * kc * 2;
-  for (int t = 0; t < d->ntaps; ++t)
-    p.tap_off[t] = static_cast<uint32_t>(((d->tap_dy[t] + halo) * cols + (d->tap_dx[t] + halo)) * 16);
+  if (fold > 1) {
+    // folded taps in (row offset 0..J+1, column offset 0..2) order = the block order of the folded weight pack
+    for (int t = 0; t < p.ntaps; ++t) p.tap_off[t] = static_cast<uint32_t>(((t / 3) * cols + (t % 3)) * 16);
+  } else {
+    for (int t = 0; t < d->ntaps; ++t)
+      p.tap_off[t] = static_cast<uint32_t>(((d->tap_dy[t] + halo) * cols + (d->tap_dx[t] + halo)) * 16);
+  }
   ABC_REQUIRE((p.a_tile_bytes & 127u) == 0, "abc_conv_igemm: internal: A tile not a 128-byte multiple");
   const int nseg = d->k_segments > 1 ? d->k_segments : 1;
   ABC_REQUIRE(nseg <= 4 && p.nkc % nseg == 0, "abc_conv_igemm: k_segments=%d must divide the %d K chunks (<= 4)", nseg, p.nkc);
@@ -554,8 +627,8 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.blocks_per_ntile = 0;
   for (int sgi = 0; sgi < nseg; ++sgi) {
     p.seg_tap0[sgi] = nseg > 1 ? d->seg_tap0[sgi] : 0;
-    p.seg_ntaps[sgi] = nseg > 1 ? d->seg_ntaps[sgi] : d->ntaps;
-    ABC_REQUIRE(p.seg_tap0[sgi] >= 0 && p.seg_ntaps[sgi] >= 1 && p.seg_tap0[sgi] + p.seg_ntaps[sgi] <= d->ntaps,
+    p.seg_ntaps[sgi] = nseg > 1 ? d->seg_ntaps[sgi] : p.ntaps;
+    ABC_REQUIRE(p.seg_tap0[sgi] >= 0 && p.seg_ntaps[sgi] >= 1 && p.seg_tap0[sgi] + p.seg_ntaps[sgi] <= p.ntaps,
                 "abc_conv_igemm: segment %d tap range", sgi);
     p.blocks_per_ntile += p.chunks_per_seg * p.seg_ntaps[sgi];
   }

@@ -18,6 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import AbcBnActBwdDesc, AbcBnActDesc, AbcConvDesc, AbcWgradDesc, check, lib
+from .unet import fold_rows, row_fold_for
 
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 _seed_counter = itertools.count(0x5EED)
@@ -56,9 +57,13 @@ def _n_tile(cout):
 class Packed:
     """Packed bf16 weight blocks in the kernel's consumption order (see include/abcnet_b200.h)."""
 
-    def __init__(self, w_taps, bias, taps, n_tile=None, segments=None):
+    def __init__(self, w_taps, bias, taps, n_tile=None, segments=None, fold=1):
         # w_taps: [ntaps, cout, K] fp32; without segments every tap sees all K channels. With segments =
         # [(tap0, ntaps), ...] the K axis of tap t covers only its segment's channels (K = channels per segment).
+        self.fold, real_cout = fold, w_taps.shape[1]
+        if fold > 1:                                                   # row folding (AbcConvDesc.row_fold): Toeplitz along y
+            w_taps, bias = fold_rows(w_taps, bias, taps, fold)
+            n_tile = fold * real_cout
         ntaps, cout, K = w_taps.shape
         n_tile = n_tile or _n_tile(cout)
         n_tiles = (cout + n_tile - 1) // n_tile
@@ -79,7 +84,7 @@ class Packed:
             self.cin = K * len(segments)
         self.w = blocks.contiguous().to(torch.bfloat16)
         self.bias = bias.contiguous().float()
-        self.taps, self.n_tile, self.cout, self.segments = taps, n_tile, cout, segments
+        self.taps, self.n_tile, self.cout, self.segments = taps, n_tile, real_cout, segments
 
 
 def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_scale=(1, 0, 1, 0), pool=None, pool_plane_off=0):
@@ -95,6 +100,7 @@ def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_sca
         d.k_segments = len(pk.segments)
         for i, (t0, nt) in enumerate(pk.segments):
             d.seg_tap0[i], d.seg_ntaps[i] = t0, nt
+    d.row_fold = pk.fold
     d.act, d.out_mode = act, out_mode
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = out_scale
     if dst is not None:
@@ -323,7 +329,7 @@ class TrainEngine:
             else:
                 src = self._tensor(u["src"], B, H, W, (B, u["cin"] // 8, h, w, 8))
                 mats = torch.stack([wt[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
-                conv(Packed(mats, bias, TAPS3), src, u["src_off"], z)
+                conv(Packed(mats, bias, TAPS3, fold=row_fold_for(u["cin"], cout)), src, u["src_off"], z)
             dst = self._tensor(u["dst"], B, H, W, (B, cout // 8, h, w, 8)) if u["keep"] or u["dst"][0] == "cat" else None
             pool = self._tensor(u["pool"], B, H, W) if u["pool"] else None
             bn = u["bn"]
@@ -446,7 +452,8 @@ class TrainEngine:
             sink(u["conv"].weight, dwt.permute(1, 2, 0).reshape(cout, cin, 3, 3))
             gsrc = self._tensor(u["src"], B, H, W, (B, cin // 8, h, w, 8), grad=True)
             mats = torch.stack([wt[:, :, dy + 1, dx + 1].t() for dy, dx in TAPS3]).contiguous()    # [9][ci][co]
-            conv(Packed(mats, torch.zeros(cin, device=dev), [(-dy, -dx) for dy, dx in TAPS3]), dz, 0, gsrc, out_plane_off=u["src_off"])
+            conv(Packed(mats, torch.zeros(cin, device=dev), [(-dy, -dx) for dy, dx in TAPS3], fold=row_fold_for(cout, cin)), dz, 0, gsrc,
+                 out_plane_off=u["src_off"])
 
 class _UNetTrainFn(torch.autograd.Function):
     @staticmethod

@@ -63,11 +63,46 @@ def _head(cin, cout):
     return holder
 
 
+def row_fold_for(cin, cout):
+    """Row-folding factor of a 3x3 layer (include/abcnet_b200.h, AbcConvDesc.row_fold): the 16 / 32-channel layers are
+    bound by the shared-memory operand fetch of their small-N MMAs; folding J rows into the GEMM N axis (N = J * cout = 64)
+    cuts the MMA count per pixel by 3J / (J + 2)."""
+    if os.environ.get("ABCNET_NO_FOLD"):
+        return 1
+    if cout == 16 and cin <= 32:
+        return 4
+    if cout == 32 and cin <= 32:
+        return 2
+    return 1
+
+
+def fold_rows(w_taps, bias, taps, J):
+    """Toeplitz expansion along y of a 3x3 kernel: w_taps [9, cout, cin] for ``taps`` (dy, dx) -> folded
+    [3 * (J + 2), J * cout, cin] in (row offset r, column offset c) order, column n = (b * J + j) * 16 + i for output
+    channel 16 b + i of folded row j; tap (r, c) contributes W[(dy = r - 1 - j, dx = c - 1)]. Returns (w, bias)."""
+    ntaps, cout, cin = w_taps.shape
+    assert ntaps == 9 and cout % 16 == 0 and sorted(taps) == sorted((dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1))
+    by_off = {t: w_taps[i] for i, t in enumerate(taps)}
+    out = w_taps.new_zeros(3 * (J + 2), cout // 16, J, 16, cin)
+    for r in range(J + 2):
+        for c in range(3):
+            for j in range(J):
+                dy = r - 1 - j
+                if -1 <= dy <= 1:
+                    out[r * 3 + c, :, j] = by_off[(dy, c - 1)].view(cout // 16, 16, cin)
+    b = bias.view(cout // 16, 1, 16).expand(cout // 16, J, 16).reshape(-1)
+    return out.view(3 * (J + 2), J * cout, cin), b
+
+
 class _Packed:
     """Device-resident, kernel-ready form of one convolution: packed bf16 weights + fp32 bias + tap list."""
 
-    def __init__(self, w_taps, bias, taps, n_tile, cout):
+    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1):
         # w_taps: fp32 [ntaps, cout, cin] (already BN-folded); taps: list of (dy, dx)
+        self.fold = fold
+        if fold > 1:
+            w_taps, bias = fold_rows(w_taps, bias, taps, fold)
+            n_tile = fold * cout
         ntaps, co, cin = w_taps.shape
         kc = min(cin, 64)
         n_tiles = (cout + n_tile - 1) // n_tile
@@ -77,7 +112,7 @@ class _Packed:
             bias = torch.cat([bias, bias.new_zeros(pad)])
         w = w_taps.view(ntaps, n_tiles, n_tile, cin // kc, kc // 8, 8).permute(1, 3, 0, 4, 2, 5)
         self.w = w.contiguous().to(torch.bfloat16)
-        assert self.w.numel() * 2 == lib.abc_conv_wpack_bytes(cin, cout, ntaps, n_tile)
+        assert self.w.numel() * 2 == lib.abc_conv_wpack_bytes(cin, co, ntaps, n_tile)
         self.bias = bias.contiguous().float()
         self.taps, self.n_tile, self.cout, self.cin = taps, n_tile, cout, cin
 
@@ -195,7 +230,8 @@ class UNet(nn.Module):
             w, b = _fold(conv.weight, conv.bias, bn)
             cout, cin = w.shape[:2]
             wt = torch.stack([w[:, :, ky, kx] for (_, _, ky, kx) in _TAPS3])
-            P[name] = _Packed(wt, b, [(dy, dx) for (dy, dx, _, _) in _TAPS3], _default_n_tile(cin, cout), cout)
+            P[name] = _Packed(wt, b, [(dy, dx) for (dy, dx, _, _) in _TAPS3], _default_n_tile(cin, cout), cout,
+                              fold=row_fold_for(cin, cout))
 
         # first conv (1 -> 16): direct kernel, fp32 folded weights [16][9]
         c0, b0 = self.inc1.double_conv[0], self.inc1.double_conv[1]
@@ -265,6 +301,7 @@ class UNet(nn.Module):
         d.cout, d.n_tile, d.ntaps = pk.cout, pk.n_tile, len(pk.taps)
         for i, (dy, dx) in enumerate(pk.taps):
             d.tap_dy[i], d.tap_dx[i] = dy, dx
+        d.row_fold = pk.fold
         d.act, d.out_mode = act, out_mode
         sy, oy, sx, ox = out_scale
         d.out_sy, d.out_oy, d.out_sx, d.out_ox = sy, oy, sx, ox

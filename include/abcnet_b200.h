@@ -101,6 +101,15 @@ typedef struct AbcConvDesc {
   int k_segments;
   int seg_tap0[4];
   int seg_ntaps[4];
+  /* Optional row folding for the 16 / 32-channel layers (0 / 1 = off; 2 or 4): the tensor pipe of an N <= 32 MMA is
+   * bound by the shared-memory read of its 128 x 16 activation operand, so J vertically adjacent output pixels are made
+   * ONE GEMM row with N = J * cout columns (a Toeplitz expansion of the 3x3 kernel along y): 3 * (J + 2) MMAs per
+   * 128 * J pixels instead of 9 * J. Needs the plain 3x3 tap set (ntaps = 9), out_mode 0 without output scaling,
+   * n_tile == J * cout, and a folded weight pack: per K chunk the blocks of the 3 * (J + 2) folded taps
+   * t' = 3 * r + c (input row offset r - 1 from the first of the J rows, column offset c - 1); block row
+   * n = (b * J + j) * 16 + i holds W[co = 16 b + i][ci][ky = r - j][kx = c] (zero unless 0 <= r - j <= 2);
+   * bias[n] = bias of channel 16 b + i. */
+  int row_fold;
 } AbcConvDesc;
 
 ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);

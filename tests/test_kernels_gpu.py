@@ -42,14 +42,15 @@ def bf16_round(x):
 
 
 def run_conv(x, w_taps, bias, taps, n_tile, act=0, out_mode=0, pool=False, out_planes_extra=0, out_plane_off=0,
-             in_plane_off=0, in_planes_extra=0, out_scale=(1, 0, 1, 0), out_hw=None, want_full=True):
+             in_plane_off=0, in_planes_extra=0, out_scale=(1, 0, 1, 0), out_hw=None, want_full=True, fold=1):
     """x: NCHW fp32 (bf16-representable). w_taps: [ntaps, cout, cin]. Returns (out NCHW fp32 or None, pooled or None)."""
     L = _lib()
     from abcnet_b200.unet import _Packed
     dev = torch.device("cuda")
     N, cin, H, W = x.shape
     cout = w_taps.shape[1]
-    pk = _Packed(w_taps.to(dev), bias.to(dev), taps, n_tile, cout)
+    pk = _Packed(w_taps.to(dev), bias.to(dev), taps, n_tile, cout, fold=fold)
+    n_tile = pk.n_tile
     xin = x
     if in_planes_extra or in_plane_off:
         full = torch.full((N, cin + 8 * in_planes_extra, H, W), 7.0)
@@ -63,7 +64,7 @@ def run_conv(x, w_taps, bias, taps, n_tile, act=0, out_mode=0, pool=False, out_p
     d.cout, d.n_tile, d.ntaps = cout, n_tile, len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
-    d.act, d.out_mode = act, out_mode
+    d.act, d.out_mode, d.row_fold = act, out_mode, fold
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = out_scale
     oH, oW = out_hw or (H, W)
     out = pooled = None
@@ -171,6 +172,31 @@ def test_igemm_pool_and_concat_slot():
     assert_close(pooled, F.max_pool2d(bf16_round(ref), 2), 2 ** -7, 2e-3, "fused pool")
     # pooled-only launch (no full-resolution output)
     _, pooled2 = run_conv(x, wt, b, TAPS3, 64, act=1, pool=True, want_full=False)
+    assert torch.equal(pooled2, pooled)
+
+
+@pytest.mark.parametrize("cin,cout,fold,N,H,W", [
+    (16, 16, 4, 2, 128, 64),           # inc1.3 / inc2.x: four rows folded into N = 64
+    (16, 16, 4, 1, 40, 24),            # partial tiles in both directions (tile = 64 x 8 pixels)
+    (16, 32, 2, 2, 64, 32),            # down1.0
+    (32, 32, 2, 1, 96, 40),            # down1.3
+    (32, 16, 4, 1, 64, 16),            # data gradient of down1.0
+])
+def test_igemm_row_folded_conv3x3(cin, cout, fold, N, H, W):
+    """Row-folded variant (AbcConvDesc.row_fold) == the plain implicit GEMM, bit for bit (same products, same fp32
+    accumulation order per output: taps in (ky, kx) order), full-resolution and fused max-pool outputs, concat slot."""
+    x = bf16_round(rnd(cin + H, (N, cin, H, W)))
+    w = bf16_round(rnd(cout + W, (cout, cin, 3, 3)) * (2.0 / (cin * 9) ** 0.5))
+    b = rnd(5, (cout,))
+    wt = torch.stack([w[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
+    plain, plain_pool = run_conv(x, wt, b, TAPS3, cout, act=1, pool=True, out_planes_extra=3, out_plane_off=1)
+    got, pooled = run_conv(x, wt, b, TAPS3, cout, act=1, pool=True, out_planes_extra=3, out_plane_off=1, fold=fold)
+    ref = ref_conv3(x, w, b, 1)
+    assert_close(got[:, 8:8 + cout], ref, 2 ** -7, 2e-3, f"folded conv3x3 {cin}->{cout} J={fold}")
+    assert (got[:, :8] == -5.0).all() and (got[:, 8 + cout:] == -5.0).all()
+    assert_close(pooled, F.max_pool2d(bf16_round(ref), 2), 2 ** -7, 2e-3, "folded fused pool")
+    assert torch.equal(got, plain) and torch.equal(pooled, plain_pool)
+    _, pooled2 = run_conv(x, wt, b, TAPS3, cout, act=1, pool=True, want_full=False, fold=fold)
     assert torch.equal(pooled2, pooled)
 
 

@@ -16,12 +16,13 @@ from abcnet_b200.unet import _Packed  # noqa: E402
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
 
-def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, mt=None, iters=5, act=1, nacc=None):
+def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, mt=None, iters=5, act=1, nacc=None, fold=1, want_full=True):
     dev = torch.device("cuda")
     g = torch.Generator(device="cuda").manual_seed(0)
     src = (torch.rand((B, cin // 8, H, W, 8), device=dev, generator=g) - 0.5).to(torch.bfloat16)
     w = (torch.rand((len(taps), cout, cin), device=dev, generator=g) - 0.5) * 0.05
-    pk = _Packed(w, torch.zeros(cout, device=dev), taps, n_tile, cout)
+    pk = _Packed(w, torch.zeros(cout, device=dev), taps, n_tile, cout, fold=fold)
+    n_tile = pk.n_tile
     d = _lib.AbcConvDesc()
     d.in_, d.N, d.H, d.W = src.data_ptr(), B, H, W
     d.in_planes, d.in_plane_off, d.cin = cin // 8, 0, cin
@@ -29,7 +30,7 @@ def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, 
     d.cout, d.n_tile, d.ntaps = cout, n_tile, len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
-    d.act, d.out_mode = act, out_mode
+    d.act, d.out_mode, d.row_fold = act, out_mode, fold
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = 1, 0, 1, 0
     d.out_H, d.out_W = H, W
     if out_mode in (0, 2):
@@ -39,10 +40,13 @@ def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, 
     else:
         out = torch.empty((B, cout, H, W), dtype=torch.float32, device=dev)
         out_bytes = out.numel() * 4
-    d.out = out.data_ptr()
+    d.out = out.data_ptr() if want_full else None
+    if not want_full:
+        out_bytes = 0
     if pool:
         po = torch.empty((B, cout // 8, H // 2, W // 2, 8), dtype=torch.bfloat16, device=dev)
         d.pool_out, d.pool_planes = po.data_ptr(), po.shape[1]
+        out_bytes += po.numel() * 2
     if mt is not None:
         os.environ["ABCNET_MT"] = str(mt)
     else:
@@ -64,7 +68,7 @@ def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, 
     ms = a.elapsed_time(b) / iters
     flops = 2.0 * B * H * W * cout * cin * len(taps)
     byts = src.numel() * 2 + out_bytes
-    print(f"{name:28s} B={B:3d} {cin:4d}->{cout:4d} @{H}x{W} n_tile={n_tile:3d} mt={mt} nacc={nacc}  {ms:8.3f} ms  "
+    print(f"{name:28s} B={B:3d} {cin:4d}->{cout:4d} @{H}x{W} n_tile={n_tile:3d} mt={mt} nacc={nacc} fold={fold}  {ms:8.3f} ms  "
           f"{flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s", flush=True)
     return ms
 
@@ -79,6 +83,19 @@ if __name__ == "__main__":
             bench("32->32@256", 64, 32, 32, 256, 256, 32, mt=mt)
         for mt in (1, 2, 4):
             bench("64->64@128", 256, 64, 64, 128, 128, 64, mt=mt)
+    if which == "fold":                       # A/B of the row-folded variant (same box, same clocks)
+        for fold in (1, 4, 1, 4):
+            bench("16->16@512", 64, 16, 16, 512, 512, 16, fold=fold, iters=10)
+        for fold in (1, 4):
+            for mt in (1, 2):
+                bench("16->16@512", 64, 16, 16, 512, 512, 16, fold=fold, mt=mt, iters=10)
+        for fold in (1, 4):
+            bench("16->16@512 pool only", 64, 16, 16, 512, 512, 16, pool=True, want_full=False, fold=fold, iters=10)
+        for fold in (1, 2):
+            bench("16->32@256", 64, 16, 32, 256, 256, 32, fold=fold, iters=10)
+            bench("32->32@256 pool only", 64, 32, 32, 256, 256, 32, pool=True, want_full=False, fold=fold, iters=10)
+    if which == "one16f":
+        bench("16->16@512", 64, 16, 16, 512, 512, 16, fold=4, iters=1)
     if which == "one16":                      # single configuration for ncu captures: layer_bench.py one16 [mt]
         bench("16->16@512", 64, 16, 16, 512, 512, 16, mt=int(sys.argv[2]) if len(sys.argv) > 2 else None, iters=1)
     if which == "one128":
