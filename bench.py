@@ -36,6 +36,9 @@ METRIC = "images_per_sec_unet_fwd_decode"
 UNIT = "images/s"
 FLOPS_PER_IMAGE = 93.98e9          # SURVEY.md section 6 (forward, v2 heads, 512x512)
 HEADS_CONV1_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 1024 * 1152      # fused 8-head 3x3 conv: M=16384, N=1024, K=1152
+# dram__bytes_read.sum + dram__bytes_write.sum of that launch at batch 256, from the committed `ncu --set full` capture
+# profiles/r01_heads_conv1_b256_v7.summary.txt (3.02 GB read + 8.54 GB written; algorithmic: 1.07 GB trunk in + 8.59 GB hidden out)
+HEADS_CONV1_DRAM_BYTES_B256 = 3.024684e9 + 8.543432e9
 
 
 def peaks():
@@ -345,7 +348,9 @@ def run_ours(args, rank, world, local_rank):
         peak = pk["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "conv_igemm_kernel[heads.conv1 128->1024 3x3 @128x128]", "achieved": ach,
                 "peak": peak, "peak_source": pk_src + " (sustained bf16)", "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "ms_per_launch": dom_ms, "flops_per_launch": HEADS_CONV1_FLOPS_PER_IMAGE * B}
+                "traffic": HEADS_CONV1_DRAM_BYTES_B256 if B == 256 else None,
+                "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01_heads_conv1_b256_v7.summary.txt)",
+                "ms_per_launch": dom_ms, "flops_per_launch": HEADS_CONV1_FLOPS_PER_IMAGE * B}
     total_tflops = FLOPS_PER_IMAGE * B * args.steps / (ms * 1e-3) / 1e12
     cpu = None
     if not args.no_cpu:
@@ -370,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
