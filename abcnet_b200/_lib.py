@@ -18,6 +18,7 @@ EXPORTS = (
     "abc_loss_partials", "abc_loss_backward",
     "abc_bn_stats", "abc_bn_finalize", "abc_bn_act", "abc_bn_act_backward", "abc_nchw_to_p8", "abc_channel_sum",
     "abc_nchw_to_p8_ex", "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
+    "abc_heads_fused", "abc_heads_fused_pack_sizes",
 )
 
 
@@ -56,6 +57,15 @@ class AbcDecodeDesc(C.Structure):
         ("atoms", C.c_void_p), ("atom_cap", C.c_int),
         ("bonds", C.c_void_p), ("bond_cap", C.c_int),
         ("counts", C.c_void_p), ("p8f_mask", C.c_int),
+    ]
+
+
+class AbcHeadsFusedDesc(C.Structure):
+    _fields_ = [
+        ("in_", C.c_void_p), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("in_planes", C.c_int), ("in_plane_off", C.c_int),
+        ("w1pack", C.c_void_p), ("bias1", C.c_void_p), ("n_heads", C.c_int), ("cout", C.c_int * 16),
+        ("w2pack", C.c_void_p), ("w2pack_bytes", C.c_int64), ("bias2", C.c_void_p), ("bias2_len", C.c_int),
+        ("out", C.c_void_p * 16), ("out_mode", C.c_int * 16), ("out_planes", C.c_int * 16), ("item_slot", C.c_int * 6),
     ]
 
 
@@ -135,6 +145,8 @@ def _load():
     lib.abc_conv_wgrad.argtypes = [C.POINTER(AbcWgradDesc), vp]
     lib.abc_conv3x3_c1_wgrad.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, vp, vp]
     lib.abc_conv3x3_c1_raw.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.abc_heads_fused.argtypes = [C.POINTER(AbcHeadsFusedDesc), vp]
+    lib.abc_heads_fused_pack_sizes.argtypes = [ci, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     return lib
 
 

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import AbcConvDesc, check, lib
+from ._lib import AbcConvDesc, AbcHeadsFusedDesc, check, lib
 
 BN_EPS = 1e-5
 _TAPS3 = [(ky - 1, kx - 1, ky, kx) for ky in range(3) for kx in range(3)]          # (dy, dx, ky, kx)
@@ -267,14 +267,48 @@ class UNet(nn.Module):
         wt = torch.stack([w[:, :, ky, kx] for (_, _, ky, kx) in _TAPS3])
         nt = int(os.environ.get("ABCNET_NTILE_HEADS", "256"))       # N = 256 tiles: measured 1.4x faster than N = 128
         P["heads.conv1"] = _Packed(wt, torch.cat(bs), [(dy, dx) for (dy, dx, _, _) in _TAPS3], nt, w.shape[0])
+        self._packed_heads_ntile = nt
         for i, om in enumerate(self.out_modules):
             w2 = om.conv2.weight.detach().float().reshape(om.conv2.weight.shape[0], -1)
             h = w2.shape[0]
             n_tile = 16 if h <= 16 else (64 if h <= 64 else 128)
             P[f"heads.{i}.conv2"] = _Packed(w2.unsqueeze(0).contiguous(), om.conv2.bias.detach().float(), [(0, 0)], n_tile, h)
+        P["heads.fused"] = self._pack_fused_heads(dev)
         self._packed = P
         self._packed_key = self._param_key()
         return self
+
+    def _pack_fused_heads(self, dev):
+        """conv2 weights / biases in the (head, chunk) order of abc_heads_fused (include/abcnet_b200.h); None when the head list
+        is outside the fused kernel's limits (then conv1 and the per-head conv2 run as separate launches)."""
+        heads = self.heads
+        if len(heads) > 16 or os.environ.get("ABCNET_FUSED_HEADS", "1") == "0" or self._packed_heads_ntile != 256:
+            return None
+        for i in range(0, len(heads), 2):
+            pair = heads[i:i + 2]
+            chunks = sum((h + 127) // 128 for h in pair)
+            cols = sum(sum(((min(h - c0, 128) + 15) // 16) * 16 for c0 in range(0, h, 128)) for h in pair)
+            if chunks > 6 or cols > 512:
+                return None
+        blocks, biases = [], []
+        for om, h in zip(self.out_modules, heads):
+            w2 = om.conv2.weight.detach().float().reshape(h, -1)
+            b2 = om.conv2.bias.detach().float()
+            for c0 in range(0, h, 128):
+                cnt = min(h - c0, 128)
+                nc = (cnt + 15) // 16 * 16
+                wb = w2.new_zeros(nc, 128)
+                wb[:cnt] = w2[c0:c0 + cnt]
+                blocks.append(wb.view(nc, 16, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16).reshape(-1))
+                bb = b2.new_zeros(nc)
+                bb[:cnt] = b2[c0:c0 + cnt]
+                biases.append(bb)
+        w2pack = torch.cat(blocks).contiguous()
+        bias2 = torch.cat(biases).contiguous()
+        nb, nl = C.c_int64(0), C.c_int(0)
+        check(lib.abc_heads_fused_pack_sizes(len(heads), (C.c_int * len(heads))(*heads), C.byref(nb), C.byref(nl)), "abc_heads_fused_pack_sizes")
+        assert w2pack.numel() * 2 == nb.value and bias2.numel() == nl.value
+        return w2pack, bias2
 
     def _phase_taps(self, parity):
         """(kernel index, input offset) pairs of one output parity of ConvTranspose2d(k=3, s=2) + crop."""
@@ -336,7 +370,17 @@ class UNet(nn.Module):
 
     @torch.no_grad()
     def trunk_and_hidden(self, x):
-        """Runs everything up to the fused head conv1; returns (trunk P8, hidden P8) for tests / fused decode."""
+        """Runs everything up to the 8-head conv1 as a separate launch; returns (trunk P8, hidden P8)."""
+        k2 = self.trunk(x)
+        B, _, H4, W4, _ = k2.shape
+        hid = self._buf("hid", (B, 16 * len(self.heads), H4, W4, 8))
+        with self._timed("heads.conv1"):
+            self._conv(self._packed["heads.conv1"], k2, 0, hid, act=2, stream=_lib.current_stream_ptr())   # BN fold + LeakyReLU(0.01)
+        return k2, hid
+
+    @torch.no_grad()
+    def trunk(self, x):
+        """Encoder + decoder up to dconv2 (unet.py:101-115): the 128-channel stride-4 trunk, P8 bf16."""
         if not x.is_cuda:
             raise RuntimeError("abcnet_b200.UNet.forward needs a CUDA tensor (no CPU fallback)")
         _lib.require_device()
@@ -421,26 +465,51 @@ class UNet(nn.Module):
         cv("dconv1.3", k1, 0, k2)
         cv("dconv2.0", k2, 0, k1)
         cv("dconv2.3", k1, 0, k2)                                           # trunk
-        hid = self._buf("hid", (B, 16 * len(self.heads), H // 4, W // 4, 8))
-        cv("heads.conv1", k2, 0, hid, act=2)                                # BN fold + LeakyReLU(0.01); Dropout is identity in eval
-        return k2, hid
+        return k2
 
     @torch.no_grad()
-    def infer(self, x, outs=None, layout="nchw"):
+    def infer(self, x, outs=None, layout="nchw", fused=None):
         """Eval forward. layout="nchw": the reference's list of fp32 NCHW tensors. layout="p8f": a ``HeadMaps`` list in
         which heads with more than one channel are fp32 planar-8 [B, ceil(h/8), H/4, W/4, 8] (padding slots undefined);
-        this is the format the fused inference + decode path uses (``PeakDecoder`` accepts both)."""
-        _, hid = self.trunk_and_hidden(x)
-        B, _, H4, W4, _ = hid.shape
-        st = _lib.current_stream_ptr()
-        p8f = layout == "p8f"
+        this is the format the fused inference + decode path uses (``PeakDecoder`` accepts both).
+        fused (default: on when the head list fits abc_heads_fused): conv1 + LeakyReLU + conv2 of all heads in one kernel;
+        fused=False runs conv1 and the per-head conv2 as separate launches (hidden maps materialised in HBM)."""
         if layout not in ("nchw", "p8f"):
             raise ValueError("layout must be 'nchw' or 'p8f'")
+        p8f = layout == "p8f"
+        k2 = self.trunk(x)
+        B, _, H4, W4, _ = k2.shape
+        st = _lib.current_stream_ptr()
         if outs is None:
             outs = HeadMaps(self.heads)
             for h in self.heads:
                 shape = (B, (h + 7) // 8, H4, W4, 8) if (p8f and h > 1) else (B, h, H4, W4)
-                outs.append(torch.empty(shape, dtype=torch.float32, device=hid.device))
+                outs.append(torch.empty(shape, dtype=torch.float32, device=k2.device))
+        fpack = self._packed.get("heads.fused")
+        if fused is None:
+            fused = fpack is not None
+        if fused:
+            if fpack is None:
+                raise ValueError("this head list does not fit abc_heads_fused (see include/abcnet_b200.h); use fused=False")
+            w2pack, bias2 = fpack
+            pk1 = self._packed["heads.conv1"]
+            d = AbcHeadsFusedDesc()
+            d.in_, d.N, d.H, d.W, d.in_planes, d.in_plane_off = k2.data_ptr(), B, H4, W4, k2.shape[1], 0
+            d.w1pack, d.bias1, d.n_heads = pk1.w.data_ptr(), pk1.bias.data_ptr(), len(self.heads)
+            d.w2pack, d.w2pack_bytes, d.bias2, d.bias2_len = w2pack.data_ptr(), w2pack.numel() * 2, bias2.data_ptr(), bias2.numel()
+            slots = [int(v) for v in os.environ.get("ABCNET_HF_SLOTS", "").split(",") if v.strip()]
+            for i in range(6):
+                d.item_slot[i] = slots[i] if i < len(slots) else -1
+            for i, h in enumerate(self.heads):
+                d.cout[i], d.out[i] = h, outs[i].data_ptr()
+                d.out_mode[i] = 2 if outs[i].dim() == 5 else 1
+                d.out_planes[i] = outs[i].shape[1] if outs[i].dim() == 5 else 0
+            with self._timed("heads.fused"):
+                check(lib.abc_heads_fused(C.byref(d), st), "abc_heads_fused")
+            return outs
+        hid = self._buf("hid", (B, 16 * len(self.heads), H4, W4, 8))
+        with self._timed("heads.conv1"):
+            self._conv(self._packed["heads.conv1"], k2, 0, hid, act=2, stream=st)   # BN fold + LeakyReLU(0.01); Dropout is identity in eval
         with self._timed("heads.conv2"):
             for i, h in enumerate(self.heads):
                 self._conv(self._packed[f"heads.{i}.conv2"], hid, 16 * i, outs[i], act=0,

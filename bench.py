@@ -39,6 +39,8 @@ HEADS_CONV1_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 1024 * 1152      # fused 8-head 
 # dram__bytes_read.sum + dram__bytes_write.sum of that launch at batch 256, from the committed `ncu --set full` capture
 # profiles/r01_heads_conv1_b256_v7.summary.txt (3.02 GB read + 8.54 GB written; algorithmic: 1.07 GB trunk in + 8.59 GB hidden out)
 HEADS_CONV1_DRAM_BYTES_B256 = 3.024684e9 + 8.543432e9
+HEADS_CONV2_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 128 * 501        # the eight 1x1 convs, algorithmic (unpadded) channels
+HEADS_FUSED_DRAM_BYTES_B256 = None                                # filled from the ncu capture of heads_fused_kernel
 
 
 def peaks():
@@ -340,17 +342,22 @@ def run_ours(args, rank, world, local_rank):
     for name, a, b in timing:
         agg.setdefault(name, []).append(a.elapsed_time(b))
     layers = {k: float(np.mean(v)) for k, v in agg.items()}
-    dom = "heads.conv1"
+    fused = "heads.fused" in layers
+    dom = "heads.fused" if fused else "heads.conv1"
     dom_ms = layers.get(dom)
     roof = None
     if dom_ms:
-        ach = HEADS_CONV1_FLOPS_PER_IMAGE * B / (dom_ms * 1e-3) / 1e12
+        flops = (HEADS_CONV1_FLOPS_PER_IMAGE + (HEADS_CONV2_FLOPS_PER_IMAGE if fused else 0.0)) * B
+        ach = flops / (dom_ms * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel[heads.conv1 128->1024 3x3 @128x128]", "achieved": ach,
+        traffic = (HEADS_FUSED_DRAM_BYTES_B256 if fused else HEADS_CONV1_DRAM_BYTES_B256) if B == 256 else None
+        roof = {"bound": "tensor",
+                "kernel": "heads_fused_kernel[8 x (128->128 3x3 + LeakyReLU + 128->h 1x1) @128x128]" if fused
+                else "conv_igemm_kernel[heads.conv1 128->1024 3x3 @128x128]", "achieved": ach,
                 "peak": peak, "peak_source": pk_src + " (sustained bf16)", "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": HEADS_CONV1_DRAM_BYTES_B256 if B == 256 else None,
-                "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01_heads_conv1_b256_v7.summary.txt)",
-                "ms_per_launch": dom_ms, "flops_per_launch": HEADS_CONV1_FLOPS_PER_IMAGE * B}
+                "traffic": traffic,
+                "traffic_unit": "bytes per launch (ncu dram read + write of the committed --set full capture under profiles/)",
+                "ms_per_launch": dom_ms, "flops_per_launch": flops}
     total_tflops = FLOPS_PER_IMAGE * B * args.steps / (ms * 1e-3) / 1e12
     cpu = None
     if not args.no_cpu:

@@ -117,6 +117,40 @@ ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);
 ABC_API int64_t abc_conv_wpack_bytes(int cin, int cout, int ntaps, int n_tile);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Fused output heads (inference): for every head conv3x3(128 -> 128) + BatchNorm (folded) + LeakyReLU(0.01) +
+ * conv1x1(128 -> cout[h]) in one kernel -- OutConv, src/unet.py:63-74, applied to the shared trunk at :116-118. The hidden
+ * 128-channel maps stay in shared memory / TMEM (csrc/heads_fused_sm100.cu). Two heads share one CTA column.
+ *   w1pack / bias1 : conv1 of all heads concatenated on the output-channel axis, packed as for abc_conv_igemm with
+ *                    n_tile = 256 and the 3x3 taps in (ky, kx) order (zero-padded to a multiple of 256 channels)
+ *   w2pack / bias2 : conv2 in (head, chunk) order, chunk c = output channels [128 c, 128 (c + 1)) of the head with
+ *                    nc = count rounded up to 16: bf16 [16 (K planes)][nc][8] (zero rows past the count), bias fp32 [nc];
+ *                    total sizes from abc_heads_fused_pack_sizes
+ *   out[h]         : fp32 logits, out_mode[h] = 1: NCHW [N][cout][H][W]; 2: planar-8 [N][out_planes][H][W][8]
+ *   item_slot[i]   : tuning knob, -1 = default: the i-th conv2 chunk of a CTA column is issued after this (K chunk, tap)
+ *                    step (0..17) of the next tile's conv1
+ * Limits: n_heads <= 16, at most 6 chunks and 512 padded conv2 channels per pair of heads.
+ */
+typedef struct AbcHeadsFusedDesc {
+  const void* in;          /* trunk: P8 bf16 [N][in_planes][H][W][8], 128 channels from plane in_plane_off */
+  int N, H, W;
+  int in_planes, in_plane_off;
+  const void* w1pack;
+  const float* bias1;
+  int n_heads;
+  int cout[16];
+  const void* w2pack;
+  int64_t w2pack_bytes;
+  const float* bias2;
+  int bias2_len;
+  void* out[16];
+  int out_mode[16];
+  int out_planes[16];
+  int item_slot[6];
+} AbcHeadsFusedDesc;
+ABC_API int abc_heads_fused(const AbcHeadsFusedDesc* desc, void* stream);
+ABC_API int abc_heads_fused_pack_sizes(int n_heads, const int* cout, int64_t* w2pack_bytes, int* bias2_len);
+
+/* ---------------------------------------------------------------------------------------------------
  * Heat-map decoding: threshold + 3x3 NMS on the atom / bond centre maps, ordered peak compaction, per-peak
  * class / offset gather. Replaces src/img2smiles.py:62-80 (dense NMS / omega NMS), :115-124 (dense argmax
  * maps) and the gather part of :134-182 (one .cpu().item() sync per scalar in the reference).

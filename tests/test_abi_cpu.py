@@ -25,13 +25,30 @@ def test_header_symbols_are_exported():
     assert _lib.lib.abc_version() >= 100
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """Every ctypes mirror in abcnet_b200/_lib.py has the size and field offsets the C compiler gives the struct declared in
+    include/abcnet_b200.h (gcc compiles a probe that prints sizeof / offsetof)."""
+    import subprocess
     from abcnet_b200 import _lib
     assert C.sizeof(_lib.AbcAtomRec) == 8 and C.sizeof(_lib.AbcBondRec) == 12
-    # AbcConvDesc: 8-byte pointers interleaved with ints exactly as declared (checked against the compiler by the
-    # GPU tests; here: field order / count sanity)
-    names = [f[0] for f in _lib.AbcConvDesc._fields_]
-    assert names[:7] == ["in_", "N", "H", "W", "in_planes", "in_plane_off", "cin"] and names[-1] == "seg_ntaps"
+    structs = [n for n in dir(_lib) if n.startswith("Abc") and isinstance(getattr(_lib, n), type) and issubclass(getattr(_lib, n), C.Structure)]
+    assert {"AbcConvDesc", "AbcDecodeDesc", "AbcLossDesc", "AbcHeadsFusedDesc", "AbcWgradDesc", "AbcBnActDesc", "AbcBnActBwdDesc"} <= set(structs)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "abcnet_b200.h"', 'int main(void) {']
+    for sname in structs:
+        lines.append(f'  printf("{sname} %zu\\n", sizeof({sname}));')
+        for fname, *_ in getattr(_lib, sname)._fields_:
+            lines.append(f'  printf("{sname}.{fname} %zu\\n", offsetof({sname}, {fname.rstrip("_")}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for sname in structs:
+        cls = getattr(_lib, sname)
+        assert int(got[sname]) == C.sizeof(cls), f"sizeof({sname}): C {got[sname]} vs ctypes {C.sizeof(cls)}"
+        for fname, *_ in cls._fields_:
+            assert int(got[f"{sname}.{fname}"]) == getattr(cls, fname).offset, f"offsetof({sname}, {fname})"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")

@@ -58,7 +58,7 @@ def test_unet_layer_by_layer_vs_oracle():
     acts = {}
     with torch.no_grad():
         unet_ref.forward(x, sd, acts=acts)
-    m(x.cuda())
+    m.infer(x.cuda(), fused=False)          # separate conv1 / conv2 launches: the hidden maps are materialised
     torch.cuda.synchronize()
     pairs = [("k2", "dconv2.double_conv.3"), ("cat3", None), ("h2", "down5.maxpool_conv.1.double_conv.3")]
     got = m.activation("k2").cpu()
@@ -234,3 +234,30 @@ def test_planar_logits_layout_is_equivalent():
     assert sum(len(a) for a, _, _ in r1) > 10
     for (a1, b1, n1), (a2, b2, n2) in zip(r1, r2):
         assert n1 == n2 and np.array_equal(a1, a2) and np.array_equal(b1, b2)
+
+
+@pytest.mark.parametrize("heads,B,H,W", [(HEADS, 3, 64, 96), (HEADS, 2, 32, 32), ([1, 21, 5, 1, 4, 2], 2, 64, 64), ([1, 14, 3], 1, 96, 32),
+                                         (HEADS, 2, 512, 512)])
+def test_fused_heads_match_separate_launches(heads, B, H, W):
+    """abc_heads_fused (conv1 + LeakyReLU + conv2 in one kernel, hidden maps kept on chip) against the separate
+    conv_igemm launches: same bf16 hidden values, same fp32 accumulation order over K -> identical logits; both output
+    layouts; partial tiles; even / odd head counts (the head list is a constructor argument, unet.py:96-98)."""
+    import abcnet_b200
+    sd = unet_ref.make_state_dict(seed=9, heads=tuple(heads), variant="W1")
+    m = abcnet_b200.UNet(1, list(heads)).cuda().eval()
+    m.load_state_dict(sd)
+    x = torch.from_numpy(synth.binary_images(9, B, H, W, 0.08)).cuda()
+    sep = [o.clone() for o in m.infer(x, fused=False)]
+    fus = m.infer(x, fused=True)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(sep, fus)):
+        assert a.shape == b.shape
+        d = (a - b).abs().max().item()
+        assert d <= 1e-5 * max(1.0, a.abs().max().item()), f"head {i}: fused vs separate differ by {d}"
+    p8 = m.infer(x, layout="p8f", fused=True)
+    for a, b in zip(sep, p8.to_nchw()):
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, a.abs().max().item())
+    if tuple(heads) == tuple(HEADS) and H <= 96:
+        with torch.no_grad():
+            ref = unet_ref.forward(x.cpu(), sd)
+        _check_logits(fus, ref, "fused heads vs oracle")
