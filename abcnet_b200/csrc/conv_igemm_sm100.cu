@@ -637,6 +637,10 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   // mt = tiles per pipeline stage: amortises the per-stage barrier round trips and puts more bytes in flight per SM.
   // Bounded by TMEM (two accumulator stages of mt * n_tile <= 256 columns each) and by shared memory.
   int mt_max = 256 / d->n_tile;
+  // n_tile = 256: with one tile per stage every CTA streams the layer's full weight set per 128 pixels (64 B/clk/SM at
+  // the MMA rate, above the ~43 B/clk/SM the L2 delivers); two tiles per weight block halve that at the price of a
+  // single accumulator stage (512 TMEM columns): the epilogue no longer overlaps the next group's MMAs.
+  if (d->n_tile == 256 && getenv("ABCNET_MT256")) mt_max = atoi(getenv("ABCNET_MT256")) >= 2 ? 2 : 1;
   if (mt_max > 8) mt_max = 8;
   if (mt_max > p.tiles_x) mt_max = p.tiles_x;
   if (const char* e = getenv("ABCNET_MT")) { int v = atoi(e); if (v >= 1 && v < mt_max) mt_max = v; }

@@ -282,7 +282,7 @@ class UNet(nn.Module):
         """conv2 weights / biases in the (head, chunk) order of abc_heads_fused (include/abcnet_b200.h); None when the head list
         is outside the fused kernel's limits (then conv1 and the per-head conv2 run as separate launches)."""
         heads = self.heads
-        if len(heads) > 16 or os.environ.get("ABCNET_FUSED_HEADS", "1") == "0" or self._packed_heads_ntile != 256:
+        if len(heads) > 16 or self._packed_heads_ntile != 256:
             return None
         for i in range(0, len(heads), 2):
             pair = heads[i:i + 2]
@@ -472,8 +472,8 @@ class UNet(nn.Module):
         """Eval forward. layout="nchw": the reference's list of fp32 NCHW tensors. layout="p8f": a ``HeadMaps`` list in
         which heads with more than one channel are fp32 planar-8 [B, ceil(h/8), H/4, W/4, 8] (padding slots undefined);
         this is the format the fused inference + decode path uses (``PeakDecoder`` accepts both).
-        fused (default: on when the head list fits abc_heads_fused): conv1 + LeakyReLU + conv2 of all heads in one kernel;
-        fused=False runs conv1 and the per-head conv2 as separate launches (hidden maps materialised in HBM)."""
+        fused=True (or ABCNET_FUSED_HEADS=1): conv1 + LeakyReLU + conv2 of all heads in one kernel (abc_heads_fused);
+        default: conv1 and the per-head conv2 as separate launches (hidden maps materialised in HBM)."""
         if layout not in ("nchw", "p8f"):
             raise ValueError("layout must be 'nchw' or 'p8f'")
         p8f = layout == "p8f"
@@ -487,7 +487,10 @@ class UNet(nn.Module):
                 outs.append(torch.empty(shape, dtype=torch.float32, device=k2.device))
         fpack = self._packed.get("heads.fused")
         if fused is None:
-            fused = fpack is not None
+            # measured on B200 (profiles/r01_bench_v8_fused_heads.json): 12.1 ms fused against 6.9 + 3.4 ms for the separate
+            # launches -- with two 32 KB hidden operands in shared memory the weight ring shrinks to 3 blocks and the
+            # L2 -> SM weight stream (64 B/clk/SM at the MMA rate) starves the tensor pipe. Opt-in until that is fixed.
+            fused = fpack is not None and os.environ.get("ABCNET_FUSED_HEADS", "0") == "1"
         if fused:
             if fpack is None:
                 raise ValueError("this head list does not fit abc_heads_fused (see include/abcnet_b200.h); use fused=False")

@@ -10,11 +10,11 @@ tail -3 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit $?"; tail -c 3000 gpurun_out/${TAG}_bench.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
-# launch list of the bench command: only this library's kernels (-k regex:abc), skipping the calibration forward (39) and
-# the three warm-up steps (3 x 40) so that the two timed steps are what is listed
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:conv|decode|heads" -s 156 -c 80 --csv --log-file gpurun_out/${TAG}_launches.csv \
+# launch list of the bench command: only this library's kernels (-k regex:abc), skipping the calibration forward (47) and
+# the three warm-up steps (3 x 48) so that the two timed steps are what is listed
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:conv|decode|heads" -s 191 -c 96 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:heads_fused -c 1 -f -o gpurun_out/${TAG}_heads_fused \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 37 -c 1 -f -o gpurun_out/${TAG}_heads_conv1 \
     python tools/prof_forward.py 256 > gpurun_out/${TAG}_ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -c 3 -f -o gpurun_out/${TAG}_shallow \
     python tools/prof_forward.py 64 > gpurun_out/${TAG}_ncu_shallow.log 2>&1

@@ -94,6 +94,14 @@ if __name__ == "__main__":
         for fold in (1, 2):
             bench("16->32@256", 64, 16, 32, 256, 256, 32, fold=fold, iters=10)
             bench("32->32@256 pool only", 64, 32, 32, 256, 256, 32, pool=True, want_full=False, fold=fold, iters=10)
+    if which == "heads":
+        for mt256 in (None, "2", None, "2"):
+            if mt256:
+                os.environ["ABCNET_MT256"] = mt256
+            else:
+                os.environ.pop("ABCNET_MT256", None)
+            bench(f"heads 128->1024@128 MT256={mt256}", 256, 128, 1024, 128, 128, 256, act=2, iters=5)
+        os.environ.pop("ABCNET_MT256", None)
     if which == "one16f":
         bench("16->16@512", 64, 16, 16, 512, 512, 16, fold=4, iters=1)
     if which == "one16":                      # single configuration for ncu captures: layer_bench.py one16 [mt]
