@@ -44,6 +44,7 @@ struct ConvKParams {
   int seg_tap0[4], seg_ntaps[4];
   uint32_t a_stage_bytes, a_tile_bytes, a_plane_bytes, a_row_bytes, b_block_bytes;
   uint32_t tap_off[18];
+  int dbg;                                   // experiments only (ABCNET_PAIR_DBG)
   int fold;                                  // row folding J (1, 2, 4): GEMM column = (16-channel block, row j, channel)
   uint32_t smem_a_off, smem_b_off;
   const uint8_t* wpack;
@@ -113,13 +114,19 @@ __device__ __forceinline__ uint4 pool_max_bf16x8(uint4 q) {
 // KSTEPS: K-steps of 16 channels per pipeline stage = kp / 2 (1, 2, 3 or 4). RESIDENT: the layer's weights of one n-tile
 // stay in shared memory (no B ring). Both are compile-time so that the MMA-issuing warp -- for the 16/32-channel layers
 // THE pacing resource: 9 small MMAs per 128-pixel tile -- runs a branch-free, fully unrolled tap loop.
-template <int KSTEPS, bool RESIDENT>
+// CG2: CTA-pair mode (cta_group::2, launched as (2,1,1) clusters): the two CTAs of a pair take two consecutive groups,
+// each loads its own activation tiles and HALF of every weight block (n_tile / 2 rows), the leader's MMA warp issues
+// M = 256 instructions for both, and each CTA's epilogue drains its own 128 TMEM lanes. See ptx_sm100.cuh.
+template <int KSTEPS, bool RESIDENT, bool CG2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p) {
+  static_assert(!(CG2 && RESIDENT), "the CTA-pair variant streams its weights");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = static_cast<int>(warp_id_uniform());   // provably warp-uniform
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   // barrier slots (8 bytes each)
   const uint32_t bar_a_full = sbase;                        // [kMaxNA]
@@ -133,22 +140,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   float* bias_s = reinterpret_cast<float*>(smem + 1024);    // [256]
 
   if (threadIdx.x == 0) {
+    // pair mode: the leader's "full" barriers also collect one relayed arrival from the peer CTA (its data has landed),
+    // and its "accumulator empty" barriers the epilogue warps of both CTAs
+    const uint32_t full_count = (CG2 && leader && !(p.dbg & 1)) ? 2 : 1;
     for (int i = 0; i < kMaxNA; ++i) {
-      mbar_init(bar_a_full + 8 * i, 1);
+      mbar_init(bar_a_full + 8 * i, full_count);
       mbar_init(bar_a_empty + 8 * i, 1);
     }
     for (int i = 0; i < kMaxNB; ++i) {
-      mbar_init(bar_b_full + 8 * i, 1);
+      mbar_init(bar_b_full + 8 * i, full_count);
       mbar_init(bar_b_empty + 8 * i, 1);
     }
     for (int i = 0; i < kMaxAcc; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 8);
+      mbar_init(bar_acc_empty + 8 * i, CG2 ? 16 : 8);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmap);
   }
-  if (warp == 2) tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
+  if (CG2) cluster_sync_all();              // both CTAs' barriers exist before the pair-wide TMEM allocation / any remote arrival
+  if (warp == 2) {
+    if (CG2) tmem_alloc_pair<kTmemCols>(smem_u32(tmem_slot));
+    else tmem_alloc<kTmemCols>(smem_u32(tmem_slot));
+  }
   for (int i = threadIdx.x; i < p.n_tile; i += kThreads) bias_s[i] = p.bias[blockIdx.y * p.n_tile + i];
   uint32_t* utab = reinterpret_cast<uint32_t*>(smem + 800);   // [<= 32] per-unit constants of the epilogue
   if (threadIdx.x < ((p.mt * p.n_tile) >> 4)) {
@@ -159,9 +173,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     utab[threadIdx.x] = static_cast<uint32_t>(ti) | (ul << 8) | (b16 << 16) | ((ul - b16 * p.fold) << 24);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // groups: a CTA takes g_first, g_first + gridDim.x, ...; in pair mode both CTAs iterate over the leader's sequence and
+  // the peer takes the following group (clamped to the last one when the count is odd: computed, not stored)
+  const int g_first = CG2 ? static_cast<int>(blockIdx.x & ~1u) : static_cast<int>(blockIdx.x);
 
   const int groups_per_img = p.groups_x * p.tiles_y;
   const uint32_t a_region = sbase + p.smem_a_off;
@@ -172,7 +190,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     // ------------------------------------------------------------------ A producer (TMA halo tiles)
     int stage = 0;
     uint32_t phase = 0;
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+    for (int gp = g_first; gp < p.num_groups; gp += gridDim.x) {
+      const int g = CG2 ? min(gp + static_cast<int>(cta_rank), p.num_groups - 1) : gp;
       const int n = g / groups_per_img;
       const int rem = g - n * groups_per_img;
       const int ty = rem / p.groups_x;
@@ -195,7 +214,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ B producer (packed weight blocks)
-    const uint8_t* wsrc = p.wpack + static_cast<size_t>(blockIdx.y) * blocks_per_ntile * p.b_block_bytes;
+    // pair mode: p.b_block_bytes is this CTA's half block; the pack holds [block][half] (see abc_conv_igemm)
+    const size_t b_src_stride = CG2 ? 2 * static_cast<size_t>(p.b_block_bytes) : p.b_block_bytes;
+    const uint8_t* wsrc = p.wpack + static_cast<size_t>(blockIdx.y) * blocks_per_ntile * b_src_stride +
+                          (CG2 ? cta_rank * p.b_block_bytes : 0u);
     if (RESIDENT) {
       if (blockIdx.x < p.num_groups && elect_one()) {
         mbar_arrive_expect_tx(bar_b_full, static_cast<uint32_t>(blocks_per_ntile) * p.b_block_bytes);
@@ -207,12 +229,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     } else {
       int stage = 0;
       uint32_t phase = 0;
-      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      for (int g = g_first; g < p.num_groups; g += gridDim.x) {
         for (int blk = 0; blk < blocks_per_ntile; ++blk) {
           mbar_wait(bar_b_empty + 8 * stage, phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(bar_b_full + 8 * stage, p.b_block_bytes);
-            bulk_load_1d(b_region + stage * p.b_block_bytes, wsrc + static_cast<size_t>(blk) * p.b_block_bytes,
+            bulk_load_1d(b_region + stage * p.b_block_bytes, wsrc + static_cast<size_t>(blk) * b_src_stride,
                          p.b_block_bytes, bar_b_full + 8 * stage);
           }
           __syncwarp();
@@ -223,16 +245,53 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
         }
       }
     }
+  } else if (warp == 1 && CG2 && !leader) {
+    // ------------------------------------------------------------------ peer CTA: relay "my operands have landed" to the
+    // leader's full barriers (same stage sequence as the leader's MMA loop; one arrival per stage use)
+    int a_stage = 0, b_stage = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    for (int g = g_first; g < p.num_groups; g += gridDim.x) {
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        mbar_wait(bar_a_full + 8 * a_stage, a_phase);
+        if (!(p.dbg & 1) && elect_one()) mbar_arrive_cluster(mapa_cluster(bar_a_full + 8 * a_stage, 0));
+        __syncwarp();
+        if (++a_stage == p.na) {
+          a_stage = 0;
+          a_phase ^= 1;
+        }
+        for (int t = 0; t < p.ntaps; ++t) {
+          mbar_wait(bar_b_full + 8 * b_stage, b_phase);
+          if (!(p.dbg & 1) && elect_one()) mbar_arrive_cluster(mapa_cluster(bar_b_full + 8 * b_stage, 0));
+          __syncwarp();
+          if (++b_stage == p.nb) {
+            b_stage = 0;
+            b_phase ^= 1;
+          }
+        }
+      }
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(CG2 ? 256 : 128, p.n_tile, 0, 0);
+    const int b_rows = CG2 ? p.n_tile >> 1 : p.n_tile;          // weight rows held by this CTA
+    auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t a_hi_, uint32_t b_lo, uint32_t b_hi_, uint32_t acc_) {
+      if (CG2) umma_bf16_lohi_pair(d, a_lo, a_hi_, b_lo, b_hi_, idesc, acc_);
+      else umma_bf16_lohi(d, a_lo, a_hi_, b_lo, b_hi_, idesc, acc_);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (CG2) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     // descriptors as (lo, hi) halves: hi is constant, lo = (smem address >> 4) advances by plain 32-bit adds
     const uint64_t a_hi64 = umma_desc_hi(p.a_plane_bytes, p.a_row_bytes * p.fold);   // LBO = plane pitch, SBO = pitch of J tile rows
-    const uint64_t b_hi64 = umma_desc_hi(p.n_tile * 16, 128);              // LBO = plane pitch, SBO = 8 rows * 16 B
+    // weights: planar (SWIZZLE_NONE) blocks [kc/8][rows][8]; in pair mode 128-byte-swizzled rows of 64 channels -- the half
+    // of B that the peer SM fetches from this CTA's shared memory moves in 128-byte rows instead of 16-byte pieces
+    // (measured: 344 clk per N = 256 MMA with planar blocks, i.e. ~12 B/clk across the pair)
+    const uint64_t b_hi64 = CG2 ? umma_desc_hi_sw128() : umma_desc_hi(b_rows * 16, 128);   // LBO = plane pitch, SBO = 8 rows * 16 B
     const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), b_hi = static_cast<uint32_t>(b_hi64 >> 32);
     const uint32_t a_lo0 = static_cast<uint32_t>(a_hi64) | (a_region >> 4);
     const uint32_t b_lo0 = static_cast<uint32_t>(b_hi64) | (b_region >> 4);
-    const uint32_t a_kstep = (2 * p.a_plane_bytes) >> 4, b_kstep = (2 * p.n_tile * 16) >> 4;
+    const uint32_t a_kstep = (2 * p.a_plane_bytes) >> 4, b_kstep = CG2 ? 2u : (2 * b_rows * 16) >> 4;
     const uint32_t a_tile16 = p.a_tile_bytes >> 4, a_stage16 = p.a_stage_bytes >> 4, b_block16 = p.b_block_bytes >> 4;
     int a_stage = 0, b_stage = 0, acc = 0;
     uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
@@ -247,7 +306,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       for (int t = 0; t < 18; ++t) tap16[t] = p.tap_off[t] >> 4;
       const int ntaps = p.ntaps, nkc = p.nkc, mt = p.mt, n_tile = p.n_tile, na = p.na, nb = p.nb, nacc = p.nacc;
       const uint32_t acc_cols = p.acc_cols;
-      for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+      for (int g = g_first; g < p.num_groups; g += gridDim.x) {
         mbar_wait(bar_acc_empty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_cols;
@@ -275,9 +334,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
                 for (int i = 0; i < mt; ++i, d_col += n_tile, a_t += a_tile16) {
 #pragma unroll
                   for (int j = 0; j < KSTEPS; ++j)
-                    umma_bf16_lohi(d_col, a_t + j * a_kstep, a_hi, b_base + j * b_kstep, b_hi, idesc, j != 0 ? 1u : acc0);
+                    mma(d_col, a_t + j * a_kstep, a_hi, b_base + j * b_kstep, b_hi, j != 0 ? 1u : acc0);
                 }
-                if (!RESIDENT) umma_commit(bar_b_empty + 8 * b_stage);
+                if (!RESIDENT) commit(bar_b_empty + 8 * b_stage);
               }
               __syncwarp();
               if (!RESIDENT) {
@@ -288,14 +347,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
               }
             }
           }
-          if (elect_one()) umma_commit(bar_a_empty + 8 * a_stage);
+          if (elect_one()) commit(bar_a_empty + 8 * a_stage);
           __syncwarp();
           if (++a_stage == na) {
             a_stage = 0;
             a_phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(bar_acc_full + 8 * acc);
+        if (elect_one()) commit(bar_acc_full + 8 * acc);
         __syncwarp();
         if (++acc == nacc) {
           acc = 0;
@@ -378,7 +437,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const size_t pool_plane_px = static_cast<size_t>(ph) * pw;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int g = blockIdx.x; g < p.num_groups; g += gridDim.x) {
+    const uint32_t acc_empty_base = CG2 ? mapa_cluster(bar_acc_empty, 0) : bar_acc_empty;   // the leader's barriers
+    for (int gp = g_first; gp < p.num_groups; gp += gridDim.x) {
+      const int g = CG2 ? min(gp + static_cast<int>(cta_rank), p.num_groups - 1) : gp;
+      const bool g_valid = !CG2 || (gp + static_cast<int>(cta_rank) < p.num_groups);   // odd group count: the peer's last group is a dummy
       const int n = g / groups_per_img;
       const int rem = g - n * groups_per_img;
       const int ty = rem / p.groups_x;
@@ -411,7 +473,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
           const int ch0 = n0 + (b16 << 4);
           const int y = ybase + j;
           const int x = xbase + ti * 8;
-          const bool valid = (y < p.H) && (x < p.W) && (ch0 < p.cout);
+          const bool valid = (y < p.H) && (x < p.W) && (ch0 < p.cout) && g_valid;
           const bool two = (ch0 + 8) < p.cout;
           float v[16];
 #pragma unroll
@@ -499,7 +561,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+      if (lane == 0) {
+        if (CG2) mbar_arrive_cluster(acc_empty_base + 8 * acc);
+        else mbar_arrive(bar_acc_empty + 8 * acc);
+      }
       if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1;
@@ -508,10 +573,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all();          // the peer may still be reading its accumulators / this CTA's barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if (CG2) tmem_dealloc_pair<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -600,6 +667,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.N = d->N; p.H = d->H; p.W = d->W;
   p.tiles_x = (d->W + 7) / 8;
   p.fold = fold;
+  p.dbg = getenv("ABCNET_PAIR_DBG") ? atoi(getenv("ABCNET_PAIR_DBG")) : 0;
   p.tiles_y = (d->H + 16 * fold - 1) / (16 * fold);
   p.in_plane_off = d->in_plane_off;
   const int kc = conv_kc(d->cin);
@@ -632,7 +700,14 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
                 "abc_conv_igemm: segment %d tap range", sgi);
     p.blocks_per_ntile += p.chunks_per_seg * p.seg_ntaps[sgi];
   }
-  const uint32_t total_b = static_cast<uint32_t>(p.blocks_per_ntile) * p.b_block_bytes;
+  // CTA-pair mode (AbcConvDesc.cta_pair): only for layers whose weights are streamed (Cin >= 128) -- decided below
+  const bool want_pair = d->cta_pair != 0;
+  if (want_pair) {
+    ABC_REQUIRE(fold == 1 && nseg == 1 && kc == 64 && d->n_tile % 32 == 0,
+                "abc_conv_igemm: cta_pair needs cin %% 64 == 0, n_tile %% 32 == 0, no row folding / K segments");
+    p.b_block_bytes /= 2;                                  // this CTA's half of every weight block
+  }
+  const uint32_t total_b = want_pair ? (1u << 30) : static_cast<uint32_t>(p.blocks_per_ntile) * p.b_block_bytes;
   p.smem_a_off = kHeaderBytes;
   // mt = tiles per pipeline stage: amortises the per-stage barrier round trips and puts more bytes in flight per SM.
   // Bounded by TMEM (two accumulator stages of mt * n_tile <= 256 columns each) and by shared memory.
@@ -664,6 +739,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
       if (kHeaderBytes + 3 * a_stage + 6 * p.b_block_bytes <= kSmemBudget) p.na = 3;
       p.a_stage_bytes = a_stage;
       p.smem_b_off = kHeaderBytes + p.na * a_stage;
+      if (want_pair) p.smem_b_off = (p.smem_b_off + 1023u) & ~1023u;   // swizzled blocks start on 1024-byte boundaries
       int nb = static_cast<int>((kSmemBudget - p.smem_b_off) / p.b_block_bytes);
       p.nb = nb > kMaxNB ? kMaxNB : nb;
       smem_bytes = p.smem_b_off + p.nb * p.b_block_bytes;
@@ -711,15 +787,17 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   }
 
   typedef void (*KernelFn)(const CUtensorMap, const ConvKParams);
-  KernelFn kernels[2][5] = {{nullptr, conv_igemm_kernel<1, false>, conv_igemm_kernel<2, false>, conv_igemm_kernel<3, false>,
-                             conv_igemm_kernel<4, false>},
-                            {nullptr, conv_igemm_kernel<1, true>, conv_igemm_kernel<2, true>, conv_igemm_kernel<3, true>,
-                             conv_igemm_kernel<4, true>}};
+  KernelFn kernels[2][5] = {{nullptr, conv_igemm_kernel<1, false, false>, conv_igemm_kernel<2, false, false>,
+                             conv_igemm_kernel<3, false, false>, conv_igemm_kernel<4, false, false>},
+                            {nullptr, conv_igemm_kernel<1, true, false>, conv_igemm_kernel<2, true, false>,
+                             conv_igemm_kernel<3, true, false>, conv_igemm_kernel<4, true, false>}};
+  KernelFn pair_kernel = conv_igemm_kernel<4, false, true>;
   static bool attr_set = false;
   if (!attr_set) {
     for (int r = 0; r < 2; ++r)
       for (int k = 1; k <= 4; ++k)
         ABC_CUDA(cudaFuncSetAttribute(kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    ABC_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   const int ksteps = p.kp / 2;
@@ -729,6 +807,28 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   if (sms <= 0) sms = 148;
   int gx = sms / n_tiles;
   if (gx < 1) gx = 1;
+  if (want_pair) {
+    // (2,1,1) clusters: the two CTAs of a pair sit on one TPC and share every tcgen05.mma (M = 256)
+    ABC_REQUIRE(!p.resident_b && ksteps == 4, "abc_conv_igemm: internal: cta_pair with resident weights");
+    const int need = (p.num_groups + 1) & ~1;
+    gx &= ~1;
+    if (gx > need) gx = need;
+    if (gx < 2) gx = 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, n_tiles, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = static_cast<cudaStream_t>(stream_);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ABC_CUDA(cudaLaunchKernelEx(&cfg, pair_kernel, tmap, p));
+    return launch_check("conv_igemm_kernel<pair>");
+  }
   if (gx > p.num_groups) gx = p.num_groups;
   dim3 grid(gx, n_tiles, 1);
   kernels[p.resident_b ? 1 : 0][ksteps]<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);

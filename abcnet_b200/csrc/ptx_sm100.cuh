@@ -134,6 +134,56 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
+// ----------------------------------------------------------------------------- CTA pair (cta_group::2)
+// Two CTAs of a (2,1,1) cluster sit on the two SMs of one TPC and execute ONE tcgen05.mma with M = 256: each CTA holds
+// its own 128 rows of A and of the accumulator, and HALF of the B operand (N / 2 rows); the instruction is issued by one
+// thread of the even ("leader") CTA. Halves the per-SM shared-memory operand traffic and the L2 -> SM weight stream.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst) {   // one whole warp in EACH CTA of the pair
+  const uint32_t ncols = kCols;
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  const uint32_t ncols = kCols;
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_lohi_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                    uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs of the pair when all previously issued tcgen05 ops have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave") canonical layouts:
 //   K-major  : core matrix = 8 rows (M/N) x 16 bytes (8 bf16 along K), 128 contiguous bytes;
 //              LBO = byte distance between core matrices adjacent in K,
@@ -147,6 +197,12 @@ __device__ __forceinline__ uint64_t umma_desc_hi(uint32_t lbo_bytes, uint32_t sb
 }
 __device__ __forceinline__ uint64_t umma_desc(uint64_t hi, uint32_t smem_addr) {
   return hi | static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+}
+// K-major operand in the 128-byte swizzle layout: one row = 64 bf16 (128 B), 8-row groups of 1024 B (SBO), the 16-byte
+// chunk c of row r stored at chunk position c ^ (r % 8); the block must start on a 1024-byte boundary. A K step of 16
+// elements advances the start address by 32 bytes. layout type (bits 61..63) = 2.
+__device__ __forceinline__ uint64_t umma_desc_hi_sw128() {
+  return (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // Instruction descriptor for kind::f16, BF16 x BF16 -> FP32.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {

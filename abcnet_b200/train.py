@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import AbcBnActBwdDesc, AbcBnActDesc, AbcConvDesc, AbcWgradDesc, check, lib
-from .unet import fold_rows, row_fold_for
+from .unet import fold_rows, pair_pack, row_fold_for, use_cta_pair
 
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 _seed_counter = itertools.count(0x5EED)
@@ -73,7 +73,11 @@ class Packed:
             bias = torch.cat([bias, bias.new_zeros(pad)])
         kc = min(K, 64)
         w = w_taps.view(ntaps, n_tiles, n_tile, K // kc, kc // 8, 8)
-        if segments is None:
+        self.pair = segments is None and fold == 1 and use_cta_pair(K, ntaps, n_tile)
+        if self.pair:                                                  # CTA-pair mode: blocks as two halves of n_tile / 2 rows
+            blocks = pair_pack(w_taps, n_tiles, n_tile)
+            self.cin = K
+        elif segments is None:
             blocks = w.permute(1, 3, 0, 4, 2, 5)                      # [nt][chunk][tap][kp][n_tile][8]
             self.cin = K
         else:
@@ -100,7 +104,7 @@ def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_sca
         d.k_segments = len(pk.segments)
         for i, (t0, nt) in enumerate(pk.segments):
             d.seg_tap0[i], d.seg_ntaps[i] = t0, nt
-    d.row_fold = pk.fold
+    d.row_fold, d.cta_pair = pk.fold, int(pk.pair)
     d.act, d.out_mode = act, out_mode
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = out_scale
     if dst is not None:

@@ -76,6 +76,31 @@ def row_fold_for(cin, cout):
     return 1
 
 
+def use_cta_pair(cin, ntaps, n_tile):
+    """CTA-pair (cta_group::2) mode for the layers whose weights of one n-tile do not fit in shared memory and are streamed
+    (Cin >= 128 3x3 layers, the 8-head conv1, the large up-sampling phases): see AbcConvDesc.cta_pair.
+    Opt-in (ABCNET_PAIR=1). Measured on B200 (tools/layer_bench.py pair / pairdbg): bit-identical results, but the peer CTA
+    reports "operands landed" to the leader through a relayed mbarrier arrival per weight block, which costs ~1300 clk per
+    block and makes the mode 1.4 - 1.8x slower; with that relay removed (timing experiment only) the pair mode merely ties
+    the single-CTA kernel (7.7 vs 7.3 ms for the 8-head conv1, 1.01 vs 1.05 ms for 128 -> 128 @128x128): these layers sit
+    at ~95 % / ~85 % of the cuBLAS bf16 rate the 1 kW power cap sustains, not on a shared-memory or L2 limit."""
+    if os.environ.get("ABCNET_PAIR", "0") != "1":
+        return False
+    return cin % 64 == 0 and n_tile % 32 == 0 and cin * ntaps * n_tile * 2 > 160 * 1024
+
+
+def pair_pack(w_taps, n_tiles, n_tile):
+    """Weight blocks of the CTA-pair mode: [n_tiles][cin/64][ntaps][2 halves][n_tile/2 rows][64 channels], each row 128-byte
+    swizzled (16-byte chunk c of row r at chunk position c ^ (r % 8)); w_taps: [ntaps, n_tiles * n_tile, cin] fp32."""
+    ntaps, _, cin = w_taps.shape
+    w = w_taps.view(ntaps, n_tiles, 2, n_tile // 16, 8, cin // 64, 8, 8)          # [t][nt][half][row group][r8][chunk][c][e]
+    r8 = torch.arange(8, device=w_taps.device).view(8, 1)
+    pos = torch.arange(8, device=w_taps.device).view(1, 8)
+    src = (pos ^ r8).view(1, 1, 1, 1, 8, 1, 8, 1).expand(ntaps, n_tiles, 2, n_tile // 16, 8, cin // 64, 8, 8)
+    w = torch.gather(w, 6, src)                                                     # out[..., r8, :, pos, :] = in[..., r8, :, pos ^ r8, :]
+    return w.permute(1, 5, 0, 2, 3, 4, 6, 7)                                        # [nt][chunk][t][half][row group][r8][pos][e]
+
+
 def fold_rows(w_taps, bias, taps, J):
     """Toeplitz expansion along y of a 3x3 kernel: w_taps [9, cout, cin] for ``taps`` (dy, dx) -> folded
     [3 * (J + 2), J * cout, cin] in (row offset r, column offset c) order, column n = (b * J + j) * 16 + i for output
@@ -97,8 +122,9 @@ def fold_rows(w_taps, bias, taps, J):
 class _Packed:
     """Device-resident, kernel-ready form of one convolution: packed bf16 weights + fp32 bias + tap list."""
 
-    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1):
+    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1, pair=None):
         # w_taps: fp32 [ntaps, cout, cin] (already BN-folded); taps: list of (dy, dx)
+        # pair: CTA-pair mode (AbcConvDesc.cta_pair); None = decide from the layer size (weights too large to stay resident)
         self.fold = fold
         if fold > 1:
             w_taps, bias = fold_rows(w_taps, bias, taps, fold)
@@ -110,7 +136,13 @@ class _Packed:
         if pad:
             w_taps = torch.cat([w_taps, w_taps.new_zeros(ntaps, pad, cin)], 1)
             bias = torch.cat([bias, bias.new_zeros(pad)])
-        w = w_taps.view(ntaps, n_tiles, n_tile, cin // kc, kc // 8, 8).permute(1, 3, 0, 4, 2, 5)
+        if pair is None:
+            pair = use_cta_pair(cin, ntaps, n_tile) and fold == 1
+        self.pair = bool(pair)
+        if self.pair:      # every (n-tile, chunk, tap) block as two halves of n_tile / 2 rows: one per CTA of the pair
+            w = pair_pack(w_taps, n_tiles, n_tile)
+        else:
+            w = w_taps.view(ntaps, n_tiles, n_tile, cin // kc, kc // 8, 8).permute(1, 3, 0, 4, 2, 5)
         self.w = w.contiguous().to(torch.bfloat16)
         assert self.w.numel() * 2 == lib.abc_conv_wpack_bytes(cin, co, ntaps, n_tile)
         self.bias = bias.contiguous().float()
@@ -267,6 +299,8 @@ class UNet(nn.Module):
         wt = torch.stack([w[:, :, ky, kx] for (_, _, ky, kx) in _TAPS3])
         nt = int(os.environ.get("ABCNET_NTILE_HEADS", "256"))       # N = 256 tiles: measured 1.4x faster than N = 128
         P["heads.conv1"] = _Packed(wt, torch.cat(bs), [(dy, dx) for (dy, dx, _, _) in _TAPS3], nt, w.shape[0])
+        P["heads.conv1.plain"] = P["heads.conv1"] if not P["heads.conv1"].pair else None   # abc_heads_fused reads the unpaired pack
+        self._heads_w1 = (wt, torch.cat(bs), w.shape[0])
         self._packed_heads_ntile = nt
         for i, om in enumerate(self.out_modules):
             w2 = om.conv2.weight.detach().float().reshape(om.conv2.weight.shape[0], -1)
@@ -335,7 +369,7 @@ class UNet(nn.Module):
         d.cout, d.n_tile, d.ntaps = pk.cout, pk.n_tile, len(pk.taps)
         for i, (dy, dx) in enumerate(pk.taps):
             d.tap_dy[i], d.tap_dx[i] = dy, dx
-        d.row_fold = pk.fold
+        d.row_fold, d.cta_pair = pk.fold, int(pk.pair)
         d.act, d.out_mode = act, out_mode
         sy, oy, sx, ox = out_scale
         d.out_sy, d.out_oy, d.out_sx, d.out_ox = sy, oy, sx, ox
@@ -495,7 +529,10 @@ class UNet(nn.Module):
             if fpack is None:
                 raise ValueError("this head list does not fit abc_heads_fused (see include/abcnet_b200.h); use fused=False")
             w2pack, bias2 = fpack
-            pk1 = self._packed["heads.conv1"]
+            pk1 = self._packed["heads.conv1.plain"]
+            if pk1 is None:
+                wt1, b1, c1 = self._heads_w1
+                pk1 = self._packed["heads.conv1.plain"] = _Packed(wt1, b1, [(dy, dx) for (dy, dx, _, _) in _TAPS3], 256, c1, pair=False)
             d = AbcHeadsFusedDesc()
             d.in_, d.N, d.H, d.W, d.in_planes, d.in_plane_off = k2.data_ptr(), B, H4, W4, k2.shape[1], 0
             d.w1pack, d.bias1, d.n_heads = pk1.w.data_ptr(), pk1.bias.data_ptr(), len(self.heads)

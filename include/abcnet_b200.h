@@ -110,6 +110,14 @@ typedef struct AbcConvDesc {
    * n = (b * J + j) * 16 + i holds W[co = 16 b + i][ci][ky = r - j][kx = c] (zero unless 0 <= r - j <= 2);
    * bias[n] = bias of channel 16 b + i. */
   int row_fold;
+  /* Optional CTA-pair mode (0 = off) for layers with cin >= 128: the kernel is launched as (2,1,1) clusters and every
+   * tcgen05.mma is a cta_group::2 instruction with M = 256 (two 128-pixel tiles, one per SM of a TPC); each CTA loads half
+   * of every weight block, which halves the shared-memory operand traffic and the L2 -> SM weight stream per SM. The
+   * weight pack must hold, for every (n-tile, K chunk, tap) block, first the rows [0, n_tile / 2) then [n_tile / 2, n_tile),
+   * each half in the 128-byte swizzle layout of a K-major tcgen05 operand: bf16 [n_tiles][cin/64][ntaps][2][n_tile/2][64]
+   * where the 16-byte chunk c (channels 8c .. 8c+7) of row r is stored at chunk position c ^ (r % 8).
+   * Needs cin % 64 == 0, n_tile % 32 == 0, no row_fold / k_segments. */
+  int cta_pair;
 } AbcConvDesc;
 
 ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);

@@ -42,14 +42,14 @@ def bf16_round(x):
 
 
 def run_conv(x, w_taps, bias, taps, n_tile, act=0, out_mode=0, pool=False, out_planes_extra=0, out_plane_off=0,
-             in_plane_off=0, in_planes_extra=0, out_scale=(1, 0, 1, 0), out_hw=None, want_full=True, fold=1):
+             in_plane_off=0, in_planes_extra=0, out_scale=(1, 0, 1, 0), out_hw=None, want_full=True, fold=1, pair=False):
     """x: NCHW fp32 (bf16-representable). w_taps: [ntaps, cout, cin]. Returns (out NCHW fp32 or None, pooled or None)."""
     L = _lib()
     from abcnet_b200.unet import _Packed
     dev = torch.device("cuda")
     N, cin, H, W = x.shape
     cout = w_taps.shape[1]
-    pk = _Packed(w_taps.to(dev), bias.to(dev), taps, n_tile, cout, fold=fold)
+    pk = _Packed(w_taps.to(dev), bias.to(dev), taps, n_tile, cout, fold=fold, pair=pair)
     n_tile = pk.n_tile
     xin = x
     if in_planes_extra or in_plane_off:
@@ -64,7 +64,7 @@ def run_conv(x, w_taps, bias, taps, n_tile, act=0, out_mode=0, pool=False, out_p
     d.cout, d.n_tile, d.ntaps = cout, n_tile, len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
-    d.act, d.out_mode, d.row_fold = act, out_mode, fold
+    d.act, d.out_mode, d.row_fold, d.cta_pair = act, out_mode, fold, int(pair)
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = out_scale
     oH, oW = out_hw or (H, W)
     out = pooled = None
@@ -198,6 +198,30 @@ def test_igemm_row_folded_conv3x3(cin, cout, fold, N, H, W):
     assert torch.equal(got, plain) and torch.equal(pooled, plain_pool)
     _, pooled2 = run_conv(x, wt, b, TAPS3, cout, act=1, pool=True, want_full=False, fold=fold)
     assert torch.equal(pooled2, pooled)
+
+
+@pytest.mark.parametrize("cin,cout,n_tile,N,H,W,act", [
+    (128, 128, 128, 2, 32, 32, 1),      # two tiles per stage (mt = 2), even group count
+    (128, 128, 128, 3, 16, 8, 1),       # 3 groups of one tile: odd count -> the peer's last group is a dummy
+    (128, 1024, 256, 2, 32, 16, 2),     # the 8-head conv1: four n-tiles, N = 256 per pair, LeakyReLU
+    (256, 256, 256, 2, 16, 16, 1),
+    (512, 256, 256, 1, 16, 16, 1),      # 8 K chunks
+    (128, 128, 128, 1, 48, 40, 1),      # partial tiles
+    (64, 64, 64, 5, 32, 24, 2),         # small layer forced into pair mode
+])
+def test_igemm_cta_pair_matches_single_cta(cin, cout, n_tile, N, H, W, act):
+    """CTA-pair mode (cta_group::2, M = 256 per instruction, AbcConvDesc.cta_pair) == the single-CTA kernel bit for bit
+    (same products, same K order), and both within tolerance of the fp64 reference."""
+    x = bf16_round(rnd(cin + H, (N, cin, H, W)))
+    w = bf16_round(rnd(cout + W, (cout, cin, 3, 3)) * (2.0 / (cin * 9) ** 0.5))
+    b = rnd(5, (cout,))
+    wt = torch.stack([w[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
+    single, single_pool = run_conv(x, wt, b, TAPS3, n_tile, act=act, pool=True, out_planes_extra=2, out_plane_off=1)
+    got, pooled = run_conv(x, wt, b, TAPS3, n_tile, act=act, pool=True, out_planes_extra=2, out_plane_off=1, pair=True)
+    ref = ref_conv3(x, w, b, act)
+    assert_close(got[:, 8:8 + cout], ref, 2 ** -7, 2e-3, f"pair conv3x3 {cin}->{cout}")
+    assert (got[:, :8] == -5.0).all() and (got[:, 8 + cout:] == -5.0).all()
+    assert torch.equal(got, single) and torch.equal(pooled, single_pool)
 
 
 def test_igemm_nchw_fp32_heads():

@@ -16,12 +16,12 @@ from abcnet_b200.unet import _Packed  # noqa: E402
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
 
-def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, mt=None, iters=5, act=1, nacc=None, fold=1, want_full=True):
+def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, mt=None, iters=5, act=1, nacc=None, fold=1, want_full=True, pair=False):
     dev = torch.device("cuda")
     g = torch.Generator(device="cuda").manual_seed(0)
     src = (torch.rand((B, cin // 8, H, W, 8), device=dev, generator=g) - 0.5).to(torch.bfloat16)
     w = (torch.rand((len(taps), cout, cin), device=dev, generator=g) - 0.5) * 0.05
-    pk = _Packed(w, torch.zeros(cout, device=dev), taps, n_tile, cout, fold=fold)
+    pk = _Packed(w, torch.zeros(cout, device=dev), taps, n_tile, cout, fold=fold, pair=pair)
     n_tile = pk.n_tile
     d = _lib.AbcConvDesc()
     d.in_, d.N, d.H, d.W = src.data_ptr(), B, H, W
@@ -30,7 +30,7 @@ def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, 
     d.cout, d.n_tile, d.ntaps = cout, n_tile, len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
-    d.act, d.out_mode, d.row_fold = act, out_mode, fold
+    d.act, d.out_mode, d.row_fold, d.cta_pair = act, out_mode, fold, int(pair)
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = 1, 0, 1, 0
     d.out_H, d.out_W = H, W
     if out_mode in (0, 2):
@@ -68,7 +68,7 @@ def bench(name, B, cin, cout, H, W, n_tile, taps=TAPS3, out_mode=0, pool=False, 
     ms = a.elapsed_time(b) / iters
     flops = 2.0 * B * H * W * cout * cin * len(taps)
     byts = src.numel() * 2 + out_bytes
-    print(f"{name:28s} B={B:3d} {cin:4d}->{cout:4d} @{H}x{W} n_tile={n_tile:3d} mt={mt} nacc={nacc} fold={fold}  {ms:8.3f} ms  "
+    print(f"{name:28s} B={B:3d} {cin:4d}->{cout:4d} @{H}x{W} n_tile={n_tile:3d} mt={mt} nacc={nacc} fold={fold} pair={int(pair)}  {ms:8.3f} ms  "
           f"{flops / ms / 1e9:8.1f} TFLOP/s  {byts / ms / 1e6:8.1f} GB/s", flush=True)
     return ms
 
@@ -94,6 +94,23 @@ if __name__ == "__main__":
         for fold in (1, 2):
             bench("16->32@256", 64, 16, 32, 256, 256, 32, fold=fold, iters=10)
             bench("32->32@256 pool only", 64, 32, 32, 256, 256, 32, pool=True, want_full=False, fold=fold, iters=10)
+    if which == "pair":                       # A/B of the CTA-pair (cta_group::2) variant
+        for pair in (False, True, False, True):
+            bench("heads 128->1024@128", 256, 128, 1024, 128, 128, 256, act=2, pair=pair)
+        for pair in (False, True, False, True):
+            bench("128->128@128", 256, 128, 128, 128, 128, 128, pair=pair)
+        for pair in (False, True):
+            bench("256->256@32", 256, 256, 256, 32, 32, 256, pair=pair)
+            bench("512->512@16", 256, 512, 512, 16, 16, 256, pair=pair)
+            bench("512->256@32", 256, 512, 256, 32, 32, 256, pair=pair)
+            bench("256->128@64", 256, 256, 128, 64, 64, 128, pair=pair)
+            bench("128->128@64", 256, 128, 128, 64, 64, 128, pair=pair)
+    if which == "pairdbg":
+        for dbg in ("0", "1"):
+            os.environ["ABCNET_PAIR_DBG"] = dbg
+            bench(f"heads pair dbg={dbg}", 256, 128, 1024, 128, 128, 256, act=2, pair=True)
+            bench(f"128->128 pair dbg={dbg}", 256, 128, 128, 128, 128, 128, pair=True)
+        os.environ.pop("ABCNET_PAIR_DBG")
     if which == "heads":
         for mt256 in (None, "2", None, "2"):
             if mt256:
