@@ -73,12 +73,32 @@ class PeakDecoder:
         check(lib.abc_decode_peaks(C.byref(d), _lib.current_stream_ptr()), "abc_decode_peaks")
         return N
 
+    def fetch_async(self, N):
+        """Enqueue the D2H copy of the compact records behind the decode kernel and record an event; ``collect`` waits for
+        that event only, so the host can already enqueue the next batch on the same stream (use one PeakDecoder per batch in
+        flight)."""
+        self.h_counts[:N].copy_(self.d_counts[:N], non_blocking=True)
+        self.h_atoms[:N].copy_(self.d_atoms[:N], non_blocking=True)
+        self.h_bonds[:N].copy_(self.d_bonds[:N], non_blocking=True)
+        if getattr(self, "_done", None) is None:
+            self._done = torch.cuda.Event()
+        self._done.record(torch.cuda.current_stream())
+        return N
+
+    def collect(self, N):
+        """Wait for the copy enqueued by ``fetch_async`` and return per-image numpy record arrays."""
+        self._done.synchronize()
+        return self._parse(N)
+
     def fetch(self, N):
         """One async D2H of the compact records + a single stream sync; returns per-image numpy record arrays."""
         self.h_counts[:N].copy_(self.d_counts[:N], non_blocking=True)
         self.h_atoms[:N].copy_(self.d_atoms[:N], non_blocking=True)
         self.h_bonds[:N].copy_(self.d_bonds[:N], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        return self._parse(N)
+
+    def _parse(self, N):
         counts = self.h_counts[:N].numpy()
         if (counts[:, 0] > self.atom_cap).any() or (counts[:, 1] > self.bond_cap).any():
             raise RuntimeError(f"decode capacity exceeded: max atoms {counts[:, 0].max()} (cap {self.atom_cap}), "

@@ -297,8 +297,12 @@ def run_ours(args, rank, world, local_rank):
             xbuf[i % 2].copy_(host, non_blocking=True)
             copied[i % 2].record(copy_stream)
 
+    dec2 = [dec, abcnet_b200.PeakDecoder(B, atom_cap=args.atom_cap, bond_cap=args.bond_cap, device=dev)]
+    obufs = [out_bufs, None]
+
     def run_e2e(steps):
-        nonlocal out_bufs
+        """Every step: H2D of its own images (side stream, double-buffered), forward, decode, D2H of the records; the host
+        collects the records of step i - 1 (waiting on that step's event only) after it has enqueued step i."""
         for ev in consumed:
             ev.record(main_stream)
         enqueue_copy(0)
@@ -307,10 +311,13 @@ def run_ours(args, rank, world, local_rank):
             if i + 1 < steps:
                 enqueue_copy(i + 1)
             main_stream.wait_event(copied[i % 2])
-            out_bufs = model.infer(xbuf[i % 2], out_bufs, layout="p8f")
+            obufs[i % 2] = model.infer(xbuf[i % 2], obufs[i % 2], layout="p8f")
             consumed[i % 2].record(main_stream)
-            n = dec.launch(out_bufs)
-            recs = dec.fetch(n)
+            n = dec2[i % 2].launch(obufs[i % 2])
+            dec2[i % 2].fetch_async(n)
+            if i > 0:
+                recs = dec2[(i - 1) % 2].collect(n)
+        recs = dec2[(steps - 1) % 2].collect(B)
         return recs
 
     run_e2e(2)
