@@ -43,6 +43,48 @@ HEADS_CONV2_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 128 * 501        # the eight 1x1
 HEADS_FUSED_DRAM_BYTES_B256 = None                                # filled from the ncu capture of heads_fused_kernel
 
 
+def _conv_flops(cin, cout, hw, taps=9):
+    return 2.0 * cin * cout * taps * hw * hw
+
+
+# Per-image algorithmic work of every launch group of the forward pass: FLOPs for the
+# tensor-class layers, bytes (input read once + output written once, bf16 activations, fp32 logits) for the HBM class.
+LAYER_CLASSES = {
+    "first conv 1->16 @512 (HBM)": ("hbm", {"inc1.0": 512 * 512 * (4 + 32)}),
+    "16/32-channel convs @512/@256 (HBM)": ("hbm", {"inc1.3": 512 * 512 * 64, "inc2.0": 512 * 512 * 64, "inc2.3": 512 * 512 * 32 + 256 * 256 * 32,
+                                                    "down1.0": 256 * 256 * (32 + 64), "down1.3": 256 * 256 * 64 + 128 * 128 * 64}),
+    "32/64-channel convs @128 (tensor)": ("tensor", {"down2.0": _conv_flops(32, 64, 128), "down2.3": _conv_flops(64, 64, 128),
+                                                     "inc3.0": _conv_flops(64, 64, 128), "inc3.3": _conv_flops(64, 64, 128)}),
+    "deep encoder / decoder convs @64..@16 (tensor)": ("tensor", {
+        "down3.0": _conv_flops(64, 128, 64), "down3.3": _conv_flops(128, 128, 64), "down4.0": _conv_flops(128, 256, 32),
+        "down4.3": _conv_flops(256, 256, 32), "down5.0": _conv_flops(256, 512, 16), "down5.3": _conv_flops(512, 512, 16),
+        "up1.conv.0": _conv_flops(512, 256, 32), "up1.conv.3": _conv_flops(256, 256, 32), "up2.conv.0": _conv_flops(256, 128, 64),
+        "up2.conv.3": _conv_flops(128, 128, 64)}),
+    "up-sampling convs (tensor)": ("tensor", {"up1.up": _conv_flops(512, 256, 16), "up2.up": _conv_flops(256, 128, 32),
+                                              "up3.up": _conv_flops(128, 64, 64)}),
+    "mid U-Net 128->128 @128 (tensor)": ("tensor", {k: _conv_flops(128, 128, 128) for k in
+                                                    ("up3.conv.0", "up3.conv.3", "dconv1.0", "dconv1.3", "dconv2.0", "dconv2.3")}),
+    "8-head conv1 128->1024 @128 (tensor)": ("tensor", {"heads.conv1": _conv_flops(128, 1024, 128)}),
+    "8-head conv2 1x1 (HBM)": ("hbm", {"heads.conv2": 128 * 128 * (1024 * 2 + (1 + 16 + 8 + 8 + 1 + 360 + 64 + 64) * 4)}),
+}
+
+
+def layer_class_report(layers_ms, B, pk):
+    """Fraction of the relevant measured roofline per layer class (north_star), from the live per-launch CUDA-event times."""
+    out = {}
+    for name, (kind, members) in LAYER_CLASSES.items():
+        if not all(k in layers_ms for k in members):
+            continue
+        ms = sum(layers_ms[k] for k in members)
+        work = sum(members.values()) * B
+        if kind == "tensor":
+            ach, peak, unit = work / (ms * 1e-3) / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
+        else:
+            ach, peak, unit = work / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+        out[name] = {"ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+    return out
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -378,7 +420,8 @@ def run_ours(args, rank, world, local_rank):
                       "batch_per_gpu": B, "weights": "random-init (deterministic), BN folded, centre/omega biases calibrated",
                       "l2": "inputs (268 MB / batch) and activations exceed the 126 MB L2; no explicit flush",
                       "avg_atom_peaks": n_atoms, "avg_bond_records": n_bonds,
-                      "whole_forward_tflops": total_tflops, "layers_ms": layers},
+                      "whole_forward_tflops": total_tflops, "layers_ms": layers,
+                      "layer_classes": layer_class_report(layers, B, pk)},
            "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms_e2e / args.steps},
