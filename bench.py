@@ -114,9 +114,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples received between host times t0 and t1 (the timed region). nvidia-smi needs a second or
+        so to start, so the sampler is started before the warm-up; when the region is too short to contain a sample the
+        samples taken under load right before it (the warm-up steps) are used and the summary says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -124,12 +127,21 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = [r for _, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        window = "timed region"
+        if t0 is not None:
+            inside = [r for ts, r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit() and t0 <= ts <= t1 + 0.15]
+            if inside:
+                rows = inside
+            else:
+                rows = rows[-5:]
+                window = "last samples before the end of the timed region (region shorter than the sampling period)"
+        sm = [float(r[0]) for r in rows]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def make_weights(seed=0):
@@ -296,6 +308,8 @@ def run_ours(args, rank, world, local_rank):
         out_bufs = model.infer(x, out_bufs, layout="p8f")
         dec.launch(out_bufs)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                      # before the warm-up: nvidia-smi takes a moment to deliver its first row
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
@@ -310,9 +324,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- timed: device-resident inputs
     model.timing = []                                    # (name, start_event, end_event) per launch, filled by the model
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    t_host0 = time.time()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -321,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     launches = _lib.launch_count() - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_host0, time.time())
     ms = e0.elapsed_time(e1)
     timing, model.timing = model.timing, None
     # ---- timed: end to end through the public API with HOST buffers. Every step copies its own images host -> device
