@@ -56,7 +56,7 @@ class AbcDecodeDesc(C.Structure):
         ("thr", C.c_float), ("omega_mode", C.c_int),
         ("atoms", C.c_void_p), ("atom_cap", C.c_int),
         ("bonds", C.c_void_p), ("bond_cap", C.c_int),
-        ("counts", C.c_void_p), ("p8f_mask", C.c_int),
+        ("counts", C.c_void_p), ("p8f_mask", C.c_int), ("centre_prob", C.c_int), ("thr_omega", C.c_float),
     ]
 
 

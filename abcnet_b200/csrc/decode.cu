@@ -23,6 +23,8 @@ struct DecParams {
   int bond_cap;
   int32_t* counts;
   int p8f_mask;
+  int centre_prob;
+  float thr_omega;
 };
 
 // Element (image n, channel ch, pixel pix) of map k with C channels: NCHW fp32, or planar-8 fp32 [N][ceil(C/8)][HW][8].
@@ -73,6 +75,15 @@ __device__ __forceinline__ int block_exscan(int v, int* warp_sums, int* total) {
   *total = warp_sums[32];
   __syncthreads();
   return res;
+}
+
+// Centre-map value as the NMS sees it: the raw logit (img2smiles.py:62-68) or, in centre_prob mode, the clamped
+// probability clamp(sigmoid(z), 1e-5, 1 - 1e-5) of the training-time metric (train.py:95,100,145-151): saturated
+// logits then tie at the clamp and plateau into several peaks exactly as max_pool2d(p) == p does.
+__device__ __forceinline__ float centre_value(float z, int prob) {
+  if (!prob) return z;
+  const float s = 1.f / (1.f + expf(-z));
+  return fminf(fmaxf(s, 1e-5f), 1.f - 1e-5f);
 }
 
 __device__ __forceinline__ bool is_peak(const float* m, int y, int x, int H, int W, float thr) {
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
   const int p0 = tid * per, p1 = min(p0 + per, HW);
 
   // ------------------------------------------------------------------ atoms
-  for (int i = tid; i < HW; i += kDecThreads) map[i] = ldmap(p, 0, n, 0, i, 1);
+  for (int i = tid; i < HW; i += kDecThreads) map[i] = centre_value(ldmap(p, 0, n, 0, i, 1), p.centre_prob);
   __syncthreads();
   int cnt = 0;
   for (int i = p0; i < p1; ++i) cnt += is_peak(map, i / p.W, i % p.W, p.H, p.W, p.thr) ? 1 : 0;
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
   __syncthreads();
 
   // ------------------------------------------------------------------ bond peaks (ordered list in smem)
-  for (int i = tid; i < HW; i += kDecThreads) map[i] = ldmap(p, 4, n, 0, i, 1);
+  for (int i = tid; i < HW; i += kDecThreads) map[i] = centre_value(ldmap(p, 4, n, 0, i, 1), p.centre_prob);
   __syncthreads();
   cnt = 0;
   for (int i = p0; i < p1; ++i) cnt += is_peak(map, i / p.W, i % p.W, p.H, p.W, p.thr) ? 1 : 0;
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
     if (lane + 32 < p.n_omega) wz[warp][lane + 32] = ldmap(p, 7, n, lane + 32, pix, p.n_omega);
     __syncwarp();
     uint32_t lo, hi;
-    omega_survivors(wz[warp], p.n_omega, p.thr, p.omega_mode, &lo, &hi);
+    omega_survivors(wz[warp], p.n_omega, p.thr_omega, p.omega_mode, &lo, &hi);
     if (lane == 0) bcnt[b] = static_cast<uint8_t>(__popc(lo) + __popc(hi));
     __syncwarp();
   }
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
     if (lane + 32 < p.n_omega) wz[warp][lane + 32] = ldmap(p, 7, n, lane + 32, pix, p.n_omega);
     __syncwarp();
     uint32_t lo, hi;
-    omega_survivors(wz[warp], p.n_omega, p.thr, p.omega_mode, &lo, &hi);
+    omega_survivors(wz[warp], p.n_omega, p.thr_omega, p.omega_mode, &lo, &hi);
     const int base = boff[b];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -259,6 +270,8 @@ extern "C" int abc_decode_peaks(const AbcDecodeDesc* d, void* stream) {
   p.c_type = d->c_type; p.c_charge = d->c_charge; p.c_hs = d->c_hs; p.n_omega = d->n_omega; p.n_btype = d->n_btype;
   p.thr = d->thr; p.omega_mode = d->omega_mode;
   p.p8f_mask = d->p8f_mask & 0xff;
+  p.centre_prob = d->centre_prob ? 1 : 0;
+  p.thr_omega = p.centre_prob ? d->thr_omega : d->thr;
   p.atoms = d->atoms; p.atom_cap = d->atom_cap; p.bonds = d->bonds; p.bond_cap = d->bond_cap; p.counts = d->counts;
   const size_t smem = static_cast<size_t>(d->H) * d->W * 7;       // 4 B map + 2 B pixel list + 1 B survivor counts
   static size_t smem_set = 0;

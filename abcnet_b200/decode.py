@@ -35,8 +35,12 @@ class PeakDecoder:
         self.h_bonds = torch.empty((batch, bond_cap, 12), dtype=torch.uint8).pin_memory()
         self.h_counts = torch.empty((batch, 4), dtype=torch.int32).pin_memory()
 
-    def launch(self, outs, thr=-1.0, omega_mode="nms"):
-        """Enqueue the decode kernel on the current stream (no synchronisation)."""
+    def launch(self, outs, thr=-1.0, omega_mode="nms", apply_sigmoid=False, thr_omega=-1.0):
+        """Enqueue the decode kernel on the current stream (no synchronisation).
+
+        ``apply_sigmoid=True`` selects the training-time metric definition of a centre peak (train.py:95,100,145-151):
+        threshold ``thr`` (0.25 there) and 3x3 NMS on ``clamp(sigmoid(z), 1e-5, 1 - 1e-5)`` instead of on the raw logit
+        (img2smiles.py:62-68, ``thr = -1``); the omega NMS then uses the logit threshold ``thr_omega``."""
         if len(outs) != 8:
             raise ValueError("decode needs the 8 head outputs of the v2 model")
         for o in outs:
@@ -67,6 +71,7 @@ class PeakDecoder:
         d.p8f_mask = mask
         d.thr = float(thr)
         d.omega_mode = {"nms": 0, "raw": 1}[omega_mode]
+        d.centre_prob, d.thr_omega = int(bool(apply_sigmoid)), float(thr_omega)
         d.atoms, d.atom_cap = self.d_atoms.data_ptr(), self.atom_cap
         d.bonds, d.bond_cap = self.d_bonds.data_ptr(), self.bond_cap
         d.counts = self.d_counts.data_ptr()
@@ -107,8 +112,8 @@ class PeakDecoder:
         bonds = self.h_bonds[:N].numpy().view(BOND_DT).reshape(N, self.bond_cap)
         return [(atoms[i, :counts[i, 0]].copy(), bonds[i, :counts[i, 1]].copy(), int(counts[i, 2])) for i in range(N)]
 
-    def __call__(self, outs, thr=-1.0, omega_mode="nms"):
-        return self.fetch(self.launch(outs, thr, omega_mode))
+    def __call__(self, outs, thr=-1.0, omega_mode="nms", apply_sigmoid=False, thr_omega=-1.0):
+        return self.fetch(self.launch(outs, thr, omega_mode, apply_sigmoid, thr_omega))
 
 
 def records_to_lists(atoms, bonds, n_bond_peaks=None, n_omega=60):

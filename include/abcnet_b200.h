@@ -177,7 +177,7 @@ ABC_API int abc_heads_fused_pack_sizes(int n_heads, const int* cout, int64_t* w2
  *          compares counts with capacities after its D2H copy.
  * omega_mode 0: candidates = circular 3-tap NMS & (z > thr) (img2smiles.py:74-80, img2smiles3.py)
  *            1: candidates = every omega whose logit != 0 (img2smiles2.py:139)
- * thr is the logit threshold (-1 in the reference, img2smiles.py:64).
+ * thr is the logit threshold (-1 in the reference, img2smiles.py:64), or a probability when centre_prob = 1.
  */
 typedef struct AbcAtomRec {
   uint16_t x, y;
@@ -203,6 +203,10 @@ typedef struct AbcDecodeDesc {
   int p8f_mask;            /* bit k set: maps[k] is planar-8 fp32 [N][ceil(C/8)][H][W][8] (abc_conv_igemm out_mode 2)
                               instead of NCHW: 8 channels of a pixel share one 32-byte sector, so the per-peak gathers
                               of the fused inference+decode path touch ~8x fewer sectors */
+  int centre_prob;         /* 0: threshold + 3x3 NMS on the raw centre logits (img2smiles.py:62-68, thr = -1).
+                              1: on p = clamp(sigmoid(z), 1e-5, 1 - 1e-5), the training-time metric definition
+                              (train.py:95,100,145-151, thr = 0.25); the omega candidates (mode 0) keep using thr_omega */
+  float thr_omega;         /* logit threshold of the omega NMS when centre_prob = 1 (ignored otherwise: thr is used) */
 } AbcDecodeDesc;
 ABC_API int abc_decode_peaks(const AbcDecodeDesc* desc, void* stream);
 

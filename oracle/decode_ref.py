@@ -66,8 +66,17 @@ def omega_survives(zw: np.ndarray, w: int) -> bool:
     return True
 
 
-def decode_records(outs, thr: float = -1.0, omega_mode: str = "nms"):
-    """outs: the 8 logit maps of ONE image as float32 arrays
+def centre_probability(z: np.ndarray) -> np.ndarray:
+    """train.py:95,100: ``torch.clamp(torch.sigmoid(z), 1e-5, 1-1e-5)`` -- executed by torch itself (fp32)."""
+    import torch
+    return torch.clamp(torch.sigmoid(torch.from_numpy(np.ascontiguousarray(z, np.float32))), 1e-5, 1 - 1e-5).numpy()
+
+
+def decode_records(outs, thr: float = -1.0, omega_mode: str = "nms", apply_sigmoid: bool = False, thr_omega: float = -1.0):
+    """``apply_sigmoid``: centre peaks by the training-time metric rule (train.py:145-151: NMS and ``> thr`` on the
+    clamped probabilities, thr = 0.25 there); the omega NMS keeps the logit threshold ``thr_omega``.
+
+    outs: the 8 logit maps of ONE image as float32 arrays
     (atom[1,H,W], type[14,H,W], charge[3,H,W], hs[2,H,W], bond[1,H,W], btype[6*n_w,H,W], rho[n_w,H,W], omega[n_w,H,W]).
 
     Returns (atoms, bonds): atoms int array [n_a, 5] = (x, y, type, charge, hs) in row-major peak
@@ -78,8 +87,13 @@ def decode_records(outs, thr: float = -1.0, omega_mode: str = "nms"):
     n_w = zw.shape[0]
     n_t = zbt.shape[0] // n_w
     H, W = za.shape[-2:]
-    apk = _peaks2d(za.reshape(H, W), thr)
-    bpk = _peaks2d(zb.reshape(H, W), thr)
+    if apply_sigmoid:
+        apk = _peaks2d(centre_probability(za.reshape(H, W)), thr)
+        bpk = _peaks2d(centre_probability(zb.reshape(H, W)), thr)
+    else:
+        apk = _peaks2d(za.reshape(H, W), thr)
+        bpk = _peaks2d(zb.reshape(H, W), thr)
+        thr_omega = thr
     atoms = []
     for x, y in zip(*np.nonzero(apk)):
         atoms.append((x, y, int(zt[:, x, y].argmax()), int(zc[:, x, y].argmax()), int(zh[:, x, y].argmax())))
@@ -87,7 +101,7 @@ def decode_records(outs, thr: float = -1.0, omega_mode: str = "nms"):
     zbt5 = zbt.reshape(n_t, n_w, H, W)
     for x, y in zip(*np.nonzero(bpk)):
         col = zw[:, x, y]
-        cand = omega_candidates(col, thr, omega_mode)
+        cand = omega_candidates(col, thr_omega, omega_mode)
         for w in np.nonzero(cand)[0]:
             if not omega_survives(col, int(w)):
                 continue

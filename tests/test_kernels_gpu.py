@@ -126,6 +126,55 @@ def test_first_conv():
     assert (got[:, :8] == -5.0).all()                      # plane 0 untouched (plane offset honoured)
 
 
+def _first_conv_expected_bits(img, w, b, relu=True):
+    """Bit-exact model of the kernels' arithmetic on a {0,1} image: a = bias; for tap k in row-major order
+    a = fmaf(v_k, w_k, a), which for v in {0,1} is a single fp32 addition (or nothing); ReLU; round to bf16."""
+    N, _, H, W = img.shape
+    pad = F.pad(img, (1, 1, 1, 1)).numpy().astype(np.float32)
+    wn, acc = w.reshape(16, 9).numpy().astype(np.float32), np.empty((N, 16, H, W), np.float32)
+    acc[:] = b.numpy().astype(np.float32)[None, :, None, None]
+    for k in range(9):
+        v = pad[:, :, k // 3:k // 3 + H, k % 3:k % 3 + W]
+        acc = np.where(v != 0, (acc + wn[None, :, k, None, None]).astype(np.float32), acc)
+    if relu:
+        acc = np.maximum(acc, np.float32(0))
+    return torch.from_numpy(acc).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 72), (1, 17, 132), (3, 64, 516), (2, 9, 70)])
+@pytest.mark.parametrize("u8", [False, True])
+def test_first_conv_binary_bit_exact(shape, u8):
+    """Table path (W % 4 == 0), its arithmetic fallback and the one-pixel kernel (W % 4 != 0) give the same bits on binary
+    images, through both entry points (fp32 image of utils.py:80-81 and the uint8 transport format)."""
+    L = _lib()
+    N, H, W = shape
+    img = (rnd(4, (N, 1, H, W), 0, 1) < 0.3).float()
+    w, b = rnd(5, (16, 1, 3, 3)), rnd(6, (16,))
+    want = _first_conv_expected_bits(img, w, b)
+    d_w, d_b = w.reshape(16, 9).contiguous().cuda(), b.cuda()
+    out = torch.zeros((N, 2, H, W, 8), dtype=torch.bfloat16, device="cuda")
+    d_img = img.to(torch.uint8).cuda() if u8 else img.cuda()
+    fn = L.lib.abc_conv3x3_c1_u8 if u8 else L.lib.abc_conv3x3_c1
+    L.check(fn(d_img.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), out.data_ptr(), N, H, W, 2, 0, 0), "c1")
+    torch.cuda.synchronize()
+    got = out.cpu().permute(0, 1, 4, 2, 3).reshape(N, 16, H, W)
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    if not u8 and W % 4 == 0:
+        # one non-binary pixel sends its warp down the arithmetic path; pixels whose 3x3 window misses it keep their bits
+        img2 = img.clone()
+        img2[0, 0, H // 2, W // 2] = 0.5
+        d_img2 = img2.cuda()
+        out2 = torch.zeros_like(out)
+        L.check(fn(d_img2.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), out2.data_ptr(), N, H, W, 2, 0, 0), "c1")
+        torch.cuda.synchronize()
+        got2 = out2.cpu().permute(0, 1, 4, 2, 3).reshape(N, 16, H, W)
+        far = torch.ones(N, 1, H, W, dtype=torch.bool)
+        far[0, 0, H // 2 - 1:H // 2 + 2, W // 2 - 1:W // 2 + 2] = False
+        assert torch.equal(got2.view(torch.int16)[far.expand(-1, 16, -1, -1)], want.view(torch.int16)[far.expand(-1, 16, -1, -1)])
+        ref2 = F.relu(F.conv2d(img2, w, b, padding=1))
+        assert_close(got2.float(), ref2, 2 ** -8, 1e-6, "conv3x3_c1 arithmetic path")
+
+
 @pytest.mark.parametrize("cin,cout,n_tile", [(16, 16, 16), (64, 32, 32), (128, 64, 64)])
 def test_igemm_1x1_single_tile(cin, cout, n_tile):
     """Smallest possible GEMM: one 16x8 tile, one tap, no halo -> isolates TMA box, descriptors, TMEM epilogue."""

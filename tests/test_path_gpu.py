@@ -136,6 +136,34 @@ def test_decode_planted_batch_bit_exact(golden_dir, mode, suffix):
         assert assemble_ref.records_to_molblock(L) == g["molblock"]
 
 
+def test_decode_probability_mode_matches_training_metric_rule():
+    """train.py:145-151 finds centre peaks on clamp(sigmoid(z), 1e-5, 1-1e-5) with `> 0.25` instead of on the
+    logits with `> -1`. Differences that must show: logits in (-1.0986, -1] become peaks, and saturated neighbours
+    (z = 15 next to z = 20: both clamp to 1-1e-5) tie into a plateau of two peaks."""
+    import abcnet_b200
+    planted = [synth.planted_logits(seed)[0] for seed in range(3)]
+    planted = [[np.array(m, np.float32, copy=True) for m in p] for p in planted]
+    planted[0][0][0, 60, 60:62] = (15.0, 20.0)          # saturated pair on the atom map
+    planted[1][4][0, 90, 17] = -1.05                    # between logit(0.25) and -1 on the bond map
+    planted[1][7][:, 90, 17] = -3.0
+    planted[1][7][11, 90, 17] = 2.0
+    maps = [torch.from_numpy(np.stack([p[i] for p in planted])).cuda() for i in range(8)]
+    dec = abcnet_b200.PeakDecoder(3, atom_cap=256, bond_cap=4096)
+    res_p = dec(maps, thr=0.25, apply_sigmoid=True, thr_omega=-1.0)
+    res_z = dec(maps, thr=-1.0)
+    for j in range(3):
+        ra, rb = decode_ref.decode_records(planted[j], 0.25, "nms", apply_sigmoid=True, thr_omega=-1.0)
+        _recs_equal(res_p[j], ra, rb)
+        ra, rb = decode_ref.decode_records(planted[j], -1.0, "nms")
+        _recs_equal(res_z[j], ra, rb)
+
+    def has(rec, x, y):
+        return bool(((rec["x"] == x) & (rec["y"] == y)).any())
+    assert has(res_p[0][0], 60, 60) and has(res_p[0][0], 60, 61)
+    assert not has(res_z[0][0], 60, 60) and has(res_z[0][0], 60, 61)
+    assert has(res_p[1][1], 90, 17) and not has(res_z[1][1], 90, 17)
+
+
 def test_decode_empty_and_capacity():
     import abcnet_b200
     outs, _ = synth.planted_logits(7, n_atoms=0, n_bonds=5, edge_cases=False)
