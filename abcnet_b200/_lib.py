@@ -35,7 +35,7 @@ class AbcConvDesc(C.Structure):
         ("out_sy", C.c_int), ("out_oy", C.c_int), ("out_sx", C.c_int), ("out_ox", C.c_int),
         ("pool_out", C.c_void_p), ("pool_planes", C.c_int), ("pool_plane_off", C.c_int),
         ("k_segments", C.c_int), ("seg_tap0", C.c_int * 4), ("seg_ntaps", C.c_int * 4),
-        ("row_fold", C.c_int), ("cta_pair", C.c_int),
+        ("row_fold", C.c_int), ("cta_pair", C.c_int), ("swap_mn", C.c_int),
     ]
 
 

@@ -2,6 +2,7 @@
 // Replaces nn.Conv2d(1,16,3,padding=1) + BatchNorm2d + ReLU of inc1 (/root/reference/src/unet.py:12-14 via :83,:101).
 // Bandwidth class: reads 4 B/pixel (fp32 image as the reference's DataLoader delivers it, utils.py:80-81) and writes
 // 32 B/pixel (two bf16 P8 planes); one thread per pixel, 128-bit coalesced stores.
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -53,14 +54,20 @@ __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const T* __restrict__ i
   }
 }
 
-// Fast variant (W % 4 == 0): one thread computes FOUR horizontally adjacent pixels.
+// Streaming variant (the default): one warp owns a 128-pixel-wide, kC1Rows-high strip and walks down its rows.
 //  * The input is a binarised drawing (utils.py:80-81: values in {0, 1}), so the 16 outputs of a pixel are a function of
 //    the 9-bit pattern of its 3x3 neighbourhood: a 512-entry table of finished (bias + taps, ReLU, bf16-packed) outputs
-//    is built once per block in shared memory (16 KB) and a pixel costs ~10 integer instructions + two LDS.128 + two
-//    STG.128 -- the kernel becomes a pure streaming kernel. Table entries are accumulated in tap order with the same
-//    fmaf sequence as the arithmetic path (fmaf(0, w, a) == a), so both paths give identical bits.
-//  * A warp that sees any value other than 0 / 1 falls back to the arithmetic path for its pixels (one LDS.128 of
-//    weights feeds 16 FMAs), so arbitrary fp32 images still work.
+//    is built once per block in shared memory (16 KB). Table entries are accumulated in tap order with the same fmaf
+//    sequence as the arithmetic path (fmaf(0, w, a) == a), so both paths give identical bits.
+//  * Lane l loads pixels x0 + 32k + l (k = 0..3) of an input row -- four fully coalesced 128-byte requests -- and four
+//    ballots turn the row into a 128-bit ink mask held by every lane (plus the two pixels left / right of the strip).
+//    Three such row masks (a rotating window) give every lane the 9-bit pattern of its four output pixels by plain shifts.
+//  * Stores are lane-contiguous: one STG.128 per (k, plane) writes 512 contiguous bytes. (The earlier four-pixels-per-
+//    thread kernel stored 16-byte pieces 64 bytes apart: ncu showed the L2 at 59 % busy for 35 % of the DRAM peak.)
+//  * Rows whose 3-row window holds any value other than 0 / 1 take the arithmetic path (same fmaf order), so arbitrary
+//    fp32 images still work.
+constexpr int kC1Rows = 16;
+
 __device__ __forceinline__ uint4 c1_pack8(const float* a) {
   __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]);
   __nv_bfloat162 p1 = __floats2bfloat162_rn(a[2], a[3]);
@@ -74,55 +81,38 @@ __device__ __forceinline__ uint4 c1_pack8(const float* a) {
   return q;
 }
 
-// Arithmetic path for four pixels (non-binary inputs): one LDS.128 of weights feeds 16 FMAs. Kept out of line so that its
-// registers do not burden the table path.
-__device__ __noinline__ void c1_fma_path(const float (&t)[3][6], const float4* w4, int relu, uint4* o0, uint4* o1) {
+// Arithmetic path for one pixel (non-binary inputs); ws = [tap][co] weights followed by bias[co]. Out of line: rare.
+template <typename T>
+__device__ __noinline__ void c1_generic_pixel(const T* __restrict__ im, int y, int x, int H, int W, const float* ws, int relu,
+                                              uint4* o0, uint4* o1) {
+  float t[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+    t[k] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? static_cast<float>(__ldg(im + static_cast<size_t>(yy) * W + xx)) : 0.f;
+  }
 #pragma unroll
   for (int pl = 0; pl < 2; ++pl) {
-    float acc[4][8];                                          // [pixel][channel of this plane]
+    float v[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float4 bb = w4[36 + pl * 2 + h];
+    for (int c8 = 0; c8 < 8; ++c8) {
+      const int co = pl * 8 + c8;
+      float a = ws[144 + co];
 #pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        acc[px][h * 4 + 0] = bb.x; acc[px][h * 4 + 1] = bb.y; acc[px][h * 4 + 2] = bb.z; acc[px][h * 4 + 3] = bb.w;
-      }
+      for (int k = 0; k < 9; ++k) a = fmaf(t[k], ws[k * 16 + co], a);
+      v[c8] = relu ? fmaxf(a, 0.f) : a;
     }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 ww = w4[k * 4 + pl * 2 + h];
-#pragma unroll
-        for (int px = 0; px < 4; ++px) {
-          const float v = t[k / 3][px + k % 3];
-          acc[px][h * 4 + 0] = fmaf(v, ww.x, acc[px][h * 4 + 0]);
-          acc[px][h * 4 + 1] = fmaf(v, ww.y, acc[px][h * 4 + 1]);
-          acc[px][h * 4 + 2] = fmaf(v, ww.z, acc[px][h * 4 + 2]);
-          acc[px][h * 4 + 3] = fmaf(v, ww.w, acc[px][h * 4 + 3]);
-        }
-      }
-    }
-    uint4* o = pl ? o1 : o0;
-#pragma unroll
-    for (int px = 0; px < 4; ++px) {
-      float* a = acc[px];
-      if (relu) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], 0.f);
-      }
-      o[px] = c1_pack8(a);
-    }
+    *(pl ? o1 : o0) = c1_pack8(v);
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 3) conv3x3_c1_x4_kernel(const T* __restrict__ img, const float* __restrict__ w,
-                                                            const float* __restrict__ b, uint4* __restrict__ out, int N, int H, int W,
-                                                            int out_planes, int out_plane_off, int relu) {
+__global__ void __launch_bounds__(256, 4) conv3x3_c1_rows_kernel(const T* __restrict__ img, const float* __restrict__ w,
+                                                              const float* __restrict__ b, uint4* __restrict__ out, int N, int H, int W,
+                                                              int out_planes, int out_plane_off, int relu) {
   __shared__ __align__(16) float ws[9 * 16 + 16];          // [tap][co], then bias[co]
   __shared__ __align__(16) uint4 lut[512][2];              // [pattern][plane]: 8 bf16 channels each
-  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int tid = threadIdx.x;
   if (tid < 144) ws[(tid % 9) * 16 + tid / 9] = w[tid];    // w is [co][tap]
   if (tid < 16) ws[144 + tid] = b[tid];
   __syncthreads();
@@ -143,61 +133,79 @@ __global__ void __launch_bounds__(256, 3) conv3x3_c1_x4_kernel(const T* __restri
     }
   }
   __syncthreads();
-  const int tiles_x = (W / 4 + 31) / 32, tiles_y = (H + 7) / 8;
-  const int tiles = tiles_x * tiles_y * N;
-  const float4* w4 = reinterpret_cast<const float4*>(ws);
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int n = tile / (tiles_x * tiles_y);
-    const int rem = tile - n * (tiles_x * tiles_y);
-    const int x0 = ((rem % tiles_x) * 32 + threadIdx.x) * 4;
-    const int y = (rem / tiles_x) * 8 + threadIdx.y;
-    const bool inside = x0 < W && y < H;
-    const T* im = img + static_cast<size_t>(n) * H * W;
-    float t[3][6];
-    bool binary = true;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = (W + 127) >> 7, strips = (H + kC1Rows - 1) / kC1Rows;
+  const long long items = static_cast<long long>(N) * strips * tiles_x;
+  const size_t plane = static_cast<size_t>(H) * W;
+  for (long long it = static_cast<long long>(blockIdx.x) * 8 + warp; it < items; it += static_cast<long long>(gridDim.x) * 8) {
+    const int n = static_cast<int>(it / (strips * tiles_x));
+    const int rem = static_cast<int>(it - static_cast<long long>(n) * (strips * tiles_x));
+    const int x0 = (rem % tiles_x) << 7, y0 = (rem / tiles_x) * kC1Rows;
+    const int y1 = min(y0 + kC1Rows, H);
+    const T* im = img + static_cast<size_t>(n) * plane;
+    uint4* o_img = out + (static_cast<size_t>(n) * out_planes + out_plane_off) * plane;
+    const int xe = lane == 0 ? x0 - 1 : x0 + 128;           // lanes 0 / 1 also fetch the pixels beside the strip
+    const bool edge_ok = lane < 2 && xe >= 0 && xe < W;
+    uint32_t m[3][4], e[3];                                 // ink masks of rows y-1, y, y+1 (bit l of m[r][k] = pixel x0+32k+l)
+    bool nb[3];                                             // row holds a value other than 0 / 1
+    auto load_row = [&](int yy, uint32_t (&mm)[4], uint32_t& ee, bool& nbin) {
+      float v[4], ve = 0.f;
+      const bool in = yy >= 0 && yy < H;
+      const T* row = im + static_cast<size_t>(in ? yy : 0) * W;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int yy = y + dy - 1;
-      if (inside && yy >= 0 && yy < H) {
-        const T* row = im + static_cast<size_t>(yy) * W + x0;
-        if constexpr (sizeof(T) == 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(row));
-          t[dy][1] = v.x; t[dy][2] = v.y; t[dy][3] = v.z; t[dy][4] = v.w;
-        } else {
-          const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(row));
-          t[dy][1] = v.x; t[dy][2] = v.y; t[dy][3] = v.z; t[dy][4] = v.w;
+      for (int k = 0; k < 4; ++k) {
+        const int x = x0 + 32 * k + lane;
+        v[k] = (in && x < W) ? static_cast<float>(__ldg(row + x)) : 0.f;
+      }
+      if (in && edge_ok) ve = static_cast<float>(__ldg(row + xe));
+      bool bad = (ve != 0.f) && (ve != 1.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        mm[k] = __ballot_sync(0xffffffffu, v[k] != 0.f);
+        bad = bad || ((v[k] != 0.f) && (v[k] != 1.f));
+      }
+      ee = __ballot_sync(0xffffffffu, ve != 0.f);
+      nbin = __any_sync(0xffffffffu, bad);
+    };
+    load_row(y0 - 1, m[0], e[0], nb[0]);
+    load_row(y0, m[1], e[1], nb[1]);
+    for (int y = y0; y < y1; ++y) {
+      load_row(y + 1, m[2], e[2], nb[2]);
+      uint4* o0 = o_img + static_cast<size_t>(y) * W;
+      uint4* o1 = o0 + plane;
+      if (!(nb[0] || nb[1] || nb[2])) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t pat = 0;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const uint32_t lo = k == 0 ? (e[r] & 1u) : (m[r][k - 1] >> 31);
+            const uint32_t hi = k == 3 ? ((e[r] >> 1) & 1u) : (m[r][k + 1] & 1u);
+            // bits (x-1, x, x+1) of the row: the 34-bit string [hi | 32 pixels | lo] shifted right by the lane index
+            const uint64_t wide = (static_cast<uint64_t>(hi) << 33) | (static_cast<uint64_t>(m[r][k]) << 1) | lo;
+            pat |= (static_cast<uint32_t>(wide >> lane) & 7u) << (3 * r);
+          }
+          const int x = x0 + 32 * k + lane;
+          if (x < W) {
+            o0[x] = lut[pat][0];
+            o1[x] = lut[pat][1];
+          }
         }
-        t[dy][0] = x0 > 0 ? static_cast<float>(__ldg(row - 1)) : 0.f;
-        t[dy][5] = x0 + 4 < W ? static_cast<float>(__ldg(row + 4)) : 0.f;
       } else {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) t[dy][i] = 0.f;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const int x = x0 + 32 * k + lane;
+          if (x < W) c1_generic_pixel<T>(im, y, x, H, W, ws, relu, o0 + x, o1 + x);
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) binary = binary && (t[dy][i] == 0.f || t[dy][i] == 1.f);
+      for (int k = 0; k < 4; ++k) {
+        m[0][k] = m[1][k];
+        m[1][k] = m[2][k];
+      }
+      e[0] = e[1]; e[1] = e[2];
+      nb[0] = nb[1]; nb[1] = nb[2];
     }
-    const bool warp_binary = __all_sync(0xffffffffu, binary);
-    if (!inside) continue;
-    uint4* o0 = out + ((static_cast<size_t>(n) * out_planes + out_plane_off) * H + y) * W + x0;
-    uint4* o1 = o0 + static_cast<size_t>(H) * W;
-    if (warp_binary) {
-      uint32_t rb[3];
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        uint32_t r = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) r |= (t[dy][i] != 0.f ? 1u : 0u) << i;
-        rb[dy] = r;
-      }
-#pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        const uint32_t e = ((rb[0] >> px) & 7u) | (((rb[1] >> px) & 7u) << 3) | (((rb[2] >> px) & 7u) << 6);
-        o0[px] = lut[e][0];
-        o1[px] = lut[e][1];
-      }
-      continue;
-    }
-    c1_fma_path(t, w4, relu, o0, o1);
   }
 }
 
@@ -213,15 +221,17 @@ static int conv3x3_c1_launch(const T* img, const float* w, const float* b, void*
   ABC_REQUIRE(out_plane_off >= 0 && out_plane_off + 2 <= out_planes, "abc_conv3x3_c1: output plane range");
   ABC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "abc_conv3x3_c1: output must be 16-byte aligned");
   dim3 block(32, 8);
-  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0) {
-    // persistent blocks (the 512-entry output table is built once per block): a few per SM, looping over 128 x 8 pixel tiles
-    const long long tiles = static_cast<long long>((W / 4 + 31) / 32) * ((H + 7) / 8) * N;
+  static const bool simple = getenv("ABCNET_C1_SIMPLE") != nullptr;      // debugging: the one-thread-per-pixel kernel
+  if (!simple) {
+    // persistent blocks (the 512-entry output table is built once per block): four per SM, one warp per 128 x 16 strip
+    const long long items = static_cast<long long>((W + 127) / 128) * ((H + kC1Rows - 1) / kC1Rows) * N;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
-    const int gx = static_cast<int>(tiles < 8LL * sms ? tiles : 8LL * sms);
-    conv3x3_c1_x4_kernel<T><<<gx, block, 0, static_cast<cudaStream_t>(stream)>>>(img, w, b, static_cast<uint4*>(out), N, H, W,
-                                                                                  out_planes, out_plane_off, relu);
-    return launch_check("conv3x3_c1_x4_kernel");
+    const long long want = (items + 7) / 8;
+    const int gx = static_cast<int>(want < 4LL * sms ? want : 4LL * sms);
+    conv3x3_c1_rows_kernel<T><<<gx, 256, 0, static_cast<cudaStream_t>(stream)>>>(img, w, b, static_cast<uint4*>(out), N, H, W,
+                                                                                 out_planes, out_plane_off, relu);
+    return launch_check("conv3x3_c1_rows_kernel");
   }
   dim3 grid((W + 31) / 32, (H + 7) / 8, N);
   conv3x3_c1_kernel<T><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(img, w, b, static_cast<uint4*>(out), H, W,

@@ -36,6 +36,11 @@ constexpr uint32_t kHeaderBytes = 2048;
 constexpr uint32_t kSmemBudget = 232448;   // 227 KB opt-in limit per CTA
 constexpr int kThreads = 384;          // warps 0-3: producers / MMA / TMEM, warps 4-11: epilogue
 constexpr int kTmemCols = 512;
+// operand-swap mode: per epilogue warp a [16 pixels][32 channels] bf16 transposition buffer, rows padded to 80 bytes so
+// that both the 2-byte column writes and the 16-byte row reads are bank-conflict free
+constexpr uint32_t kSwapRowBytes = 80;
+constexpr uint32_t kSwapWarpBytes = 16 * kSwapRowBytes;
+constexpr uint32_t kSwapStageBytes = 8 * kSwapWarpBytes;   // 10240
 
 struct ConvKParams {
   int N, H, W, tiles_x, tiles_y, groups_x, num_groups;   // a group = mt horizontally adjacent 16x8 tiles
@@ -46,6 +51,7 @@ struct ConvKParams {
   uint32_t tap_off[18];
   int dbg;                                   // experiments only (ABCNET_PAIR_DBG)
   int fold;                                  // row folding J (1, 2, 4): GEMM column = (16-channel block, row j, channel)
+  int tile_rows;                             // image rows per tile: 16 * fold, or 32 in operand-swap mode
   uint32_t smem_a_off, smem_b_off;
   const uint8_t* wpack;
   const float* bias;
@@ -117,10 +123,13 @@ __device__ __forceinline__ uint4 pool_max_bf16x8(uint4 q) {
 // CG2: CTA-pair mode (cta_group::2, launched as (2,1,1) clusters): the two CTAs of a pair take two consecutive groups,
 // each loads its own activation tiles and HALF of every weight block (n_tile / 2 rows), the leader's MMA warp issues
 // M = 256 instructions for both, and each CTA's epilogue drains its own 128 TMEM lanes. See ptx_sm100.cuh.
-template <int KSTEPS, bool RESIDENT, bool CG2>
+// SWAP: operand-swap mode (AbcConvDesc.swap_mn): M = the 128 output channels of the n-tile (the weight block is the A
+// operand), N = 256 pixels (one 32 x 8 tile per pipeline stage is the B operand); accumulator = [channel][pixel].
+template <int KSTEPS, bool RESIDENT, bool CG2, bool SWAP = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p) {
   static_assert(!(CG2 && RESIDENT), "the CTA-pair variant streams its weights");
+  static_assert(!(CG2 && SWAP), "operand swap is a single-CTA mode");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = static_cast<int>(warp_id_uniform());   // provably warp-uniform
@@ -196,7 +205,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       const int rem = g - n * groups_per_img;
       const int ty = rem / p.groups_x;
       const int tx0 = (rem - ty * p.groups_x) * p.mt;
-      const int c1 = ty * 16 * p.fold - p.halo;
+      const int c1 = ty * p.tile_rows - p.halo;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait(bar_a_empty + 8 * stage, phase ^ 1);
         if (elect_one()) {
@@ -272,10 +281,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_bf16(CG2 ? 256 : 128, p.n_tile, 0, 0);
+    const uint32_t idesc = SWAP ? umma_idesc_bf16(128, 256, 0, 0) : umma_idesc_bf16(CG2 ? 256 : 128, p.n_tile, 0, 0);
     const int b_rows = CG2 ? p.n_tile >> 1 : p.n_tile;          // weight rows held by this CTA
     auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t a_hi_, uint32_t b_lo, uint32_t b_hi_, uint32_t acc_) {
       if (CG2) umma_bf16_lohi_pair(d, a_lo, a_hi_, b_lo, b_hi_, idesc, acc_);
+      else if (SWAP) umma_bf16_lohi(d, b_lo, b_hi_, a_lo, a_hi_, idesc, acc_);     // weights = A (M), pixels = B (N)
       else umma_bf16_lohi(d, a_lo, a_hi_, b_lo, b_hi_, idesc, acc_);
     };
     auto commit = [&](uint32_t bar) {
@@ -411,6 +421,74 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       }
       if (elect_one()) umma_commit(bar_acc_full + 8 * acc);
       __syncwarp();
+      if (++acc == p.nacc) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4 && SWAP) {
+    // ------------------------------------------------------------------ epilogue, operand-swap mode
+    // Accumulator: TMEM lane = output channel of the n-tile, column = pixel r * 8 + c of the 32 x 8 tile. Warp (q, eh)
+    // drains channels [32 q, 32 q + 32) of tile rows [16 eh, 16 eh + 16): 16 columns (two tile rows) per TMEM load with
+    // the next load in flight, bias + activation, bf16, then an 8 x 8 (channel x pixel) transposition through the warp's
+    // private shared-memory buffer: lane (g, i) ends up with the 8 channels of plane g for pixel column i -> one 16-byte
+    // store per lane, 128 contiguous bytes per (plane, tile row).
+    const int q = warp & 3;
+    const int eh = (warp - 4) >> 2;
+    const int n0 = blockIdx.y * p.n_tile;
+    const float bias = bias_s[q * 32 + lane];
+    const float slope = p.act == 1 ? 0.f : (p.act == 2 ? 0.01f : 1.f);     // act(v) = max(v, slope * v)
+    const int g8 = lane >> 3, i8 = lane & 7;
+    uint8_t* stage = smem + kHeaderBytes + (warp - 4) * kSwapWarpBytes;
+    __nv_bfloat16* st_w = reinterpret_cast<__nv_bfloat16*>(stage) + lane;                     // + pixel * (kSwapRowBytes / 2)
+    const uint4* st_r = reinterpret_cast<const uint4*>(stage + i8 * kSwapRowBytes + g8 * 16);  // + row * 8 * kSwapRowBytes / 16
+    const bool plane_ok = (n0 + q * 32 + g8 * 8) < p.cout;
+    const size_t out_plane_px = static_cast<size_t>(p.out_H) * p.out_W;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int g = g_first; g < p.num_groups; g += gridDim.x) {
+      const int n = g / groups_per_img;
+      const int rem = g - n * groups_per_img;
+      const int ty = rem / p.groups_x;
+      const int tx = rem - ty * p.groups_x;
+      const int x = tx * 8 + i8;
+      const int y0 = ty * 32 + eh * 16;
+      uint4* obase = reinterpret_cast<uint4*>(p.out) +
+                     (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + (n0 >> 3) + q * 4 + g8) * out_plane_px +
+                     static_cast<size_t>(p.out_oy) * p.out_W + (x * p.out_sx + p.out_ox);
+      const bool col_ok = plane_ok && x < p.W;
+      const uint32_t tbase = tmem_base + acc * p.acc_cols + (static_cast<uint32_t>(q * 32) << 16) + eh * 128;
+      mbar_wait(bar_acc_full + 8 * acc, acc_phase);
+      tc_fence_after();
+      auto process = [&](uint32_t (&raw)[16], int it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t = __uint_as_float(raw[i]) + bias;
+          st_w[i * (kSwapRowBytes / 2)] = __float2bfloat16_rn(fmaxf(t, t * slope));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const uint4 val = st_r[rr * (8 * kSwapRowBytes / 16)];
+          const int y = y0 + it * 2 + rr;
+          if (col_ok && y < p.H) obase[static_cast<size_t>(y * p.out_sy) * p.out_W] = val;
+        }
+        __syncwarp();
+      };
+      uint32_t raw_a[16], raw_b[16];
+      tmem_ld16(tbase, raw_a);
+#pragma unroll 1
+      for (int it = 0; it < 8; it += 2) {
+        tmem_ld_wait();
+        tmem_ld16(tbase + (it + 1) * 16, raw_b);
+        process(raw_a, it);
+        tmem_ld_wait();
+        if (it + 2 < 8) tmem_ld16(tbase + (it + 2) * 16, raw_a);
+        process(raw_b, it + 1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
       if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1;
@@ -638,6 +716,13 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
     ABC_REQUIRE(d->out_mode == 0 && d->out_sy == 1 && d->out_sx == 1 && d->out_oy == 0 && d->out_ox == 0,
                 "abc_conv_igemm: row_fold supports plain P8 outputs only");
   }
+  const bool swap = d->swap_mn != 0;
+  if (swap) {
+    ABC_REQUIRE(d->n_tile == 128 && fold == 1 && d->k_segments <= 1 && !d->cta_pair,
+                "abc_conv_igemm: swap_mn needs n_tile == 128 and no row_fold / k_segments / cta_pair");
+    ABC_REQUIRE(d->out_mode == 0 && d->out != nullptr && d->pool_out == nullptr,
+                "abc_conv_igemm: swap_mn supports plain P8 outputs only (no pool_out)");
+  }
   int halo = 0;
   for (int t = 0; t < d->ntaps; ++t) {
     ABC_REQUIRE(d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1,
@@ -668,7 +753,8 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.tiles_x = (d->W + 7) / 8;
   p.fold = fold;
   p.dbg = getenv("ABCNET_PAIR_DBG") ? atoi(getenv("ABCNET_PAIR_DBG")) : 0;
-  p.tiles_y = (d->H + 16 * fold - 1) / (16 * fold);
+  p.tile_rows = swap ? 32 : 16 * fold;
+  p.tiles_y = (d->H + p.tile_rows - 1) / p.tile_rows;
   p.in_plane_off = d->in_plane_off;
   const int kc = conv_kc(d->cin);
   p.kp = kc / 8;
@@ -676,7 +762,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.ntaps = fold > 1 ? 3 * (fold + 2) : d->ntaps;
   p.halo = halo;
   p.n_tile = d->n_tile;
-  const int rows = 16 * fold + 2 * halo, cols = 8 + 2 * halo;
+  const int rows = p.tile_rows + 2 * halo, cols = 8 + 2 * halo;
   p.a_row_bytes = cols * 16;
   p.a_plane_bytes = rows * p.a_row_bytes;
   p.a_tile_bytes = p.kp * p.a_plane_bytes;
@@ -708,10 +794,11 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
     p.b_block_bytes /= 2;                                  // this CTA's half of every weight block
   }
   const uint32_t total_b = want_pair ? (1u << 30) : static_cast<uint32_t>(p.blocks_per_ntile) * p.b_block_bytes;
-  p.smem_a_off = kHeaderBytes;
+  p.smem_a_off = kHeaderBytes + (swap ? kSwapStageBytes : 0u);
+  const uint32_t hdr = p.smem_a_off;
   // mt = tiles per pipeline stage: amortises the per-stage barrier round trips and puts more bytes in flight per SM.
   // Bounded by TMEM (two accumulator stages of mt * n_tile <= 256 columns each) and by shared memory.
-  int mt_max = 256 / d->n_tile;
+  int mt_max = swap ? 1 : 256 / d->n_tile;
   // n_tile = 256: with one tile per stage every CTA streams the layer's full weight set per 128 pixels (64 B/clk/SM at
   // the MMA rate, above the ~43 B/clk/SM the L2 delivers); two tiles per weight block halve that at the price of a
   // single accumulator stage (512 TMEM columns): the epilogue no longer overlaps the next group's MMAs.
@@ -723,22 +810,22 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.mt = 0;
   for (int mt = mt_max; mt >= 1 && !p.mt; --mt) {          // prefer resident weights
     const uint32_t a_stage = mt * p.a_tile_bytes;
-    if (total_b < (1u << 20) && kHeaderBytes + 2 * a_stage + total_b <= kSmemBudget) {
+    if (total_b < (1u << 20) && hdr + 2 * a_stage + total_b <= kSmemBudget) {
       p.mt = mt; p.resident_b = 1; p.nb = 1;
-      int na = static_cast<int>((kSmemBudget - kHeaderBytes - total_b) / a_stage);
+      int na = static_cast<int>((kSmemBudget - hdr - total_b) / a_stage);
       p.na = na > kMaxNA ? kMaxNA : na;
       p.a_stage_bytes = a_stage;
-      p.smem_b_off = kHeaderBytes + p.na * a_stage;
+      p.smem_b_off = hdr + p.na * a_stage;
       smem_bytes = p.smem_b_off + total_b;
     }
   }
   for (int mt = mt_max; mt >= 1 && !p.mt; --mt) {          // otherwise stream weight blocks through a ring
     const uint32_t a_stage = mt * p.a_tile_bytes;
-    if (kHeaderBytes + 2 * a_stage + 4 * p.b_block_bytes <= kSmemBudget) {
+    if (hdr + 2 * a_stage + 4 * p.b_block_bytes <= kSmemBudget) {
       p.mt = mt; p.resident_b = 0; p.na = 2;
-      if (kHeaderBytes + 3 * a_stage + 6 * p.b_block_bytes <= kSmemBudget) p.na = 3;
+      if (hdr + 3 * a_stage + 6 * p.b_block_bytes <= kSmemBudget) p.na = 3;
       p.a_stage_bytes = a_stage;
-      p.smem_b_off = kHeaderBytes + p.na * a_stage;
+      p.smem_b_off = hdr + p.na * a_stage;
       if (want_pair) p.smem_b_off = (p.smem_b_off + 1023u) & ~1023u;   // swizzled blocks start on 1024-byte boundaries
       int nb = static_cast<int>((kSmemBudget - p.smem_b_off) / p.b_block_bytes);
       p.nb = nb > kMaxNB ? kMaxNB : nb;
@@ -746,7 +833,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
     }
   }
   ABC_REQUIRE(p.mt >= 1, "abc_conv_igemm: cin=%d n_tile=%d does not fit in shared memory", d->cin, d->n_tile);
-  p.acc_cols = p.mt * d->n_tile;
+  p.acc_cols = swap ? 256 : p.mt * d->n_tile;
   p.nacc = kTmemCols / p.acc_cols;
   if (p.nacc > kMaxAcc) p.nacc = kMaxAcc;
   if (const char* e = getenv("ABCNET_NACC")) { int v = atoi(e); if (v >= 2 && v < p.nacc) p.nacc = v; }
@@ -791,12 +878,18 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
                              conv_igemm_kernel<3, false, false>, conv_igemm_kernel<4, false, false>},
                             {nullptr, conv_igemm_kernel<1, true, false>, conv_igemm_kernel<2, true, false>,
                              conv_igemm_kernel<3, true, false>, conv_igemm_kernel<4, true, false>}};
+  KernelFn swap_kernels[2][5] = {{nullptr, conv_igemm_kernel<1, false, false, true>, conv_igemm_kernel<2, false, false, true>,
+                                  conv_igemm_kernel<3, false, false, true>, conv_igemm_kernel<4, false, false, true>},
+                                 {nullptr, conv_igemm_kernel<1, true, false, true>, conv_igemm_kernel<2, true, false, true>,
+                                  conv_igemm_kernel<3, true, false, true>, conv_igemm_kernel<4, true, false, true>}};
   KernelFn pair_kernel = conv_igemm_kernel<4, false, true>;
   static bool attr_set = false;
   if (!attr_set) {
     for (int r = 0; r < 2; ++r)
-      for (int k = 1; k <= 4; ++k)
+      for (int k = 1; k <= 4; ++k) {
         ABC_CUDA(cudaFuncSetAttribute(kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        ABC_CUDA(cudaFuncSetAttribute(swap_kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+      }
     ABC_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
@@ -831,6 +924,6 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   }
   if (gx > p.num_groups) gx = p.num_groups;
   dim3 grid(gx, n_tiles, 1);
-  kernels[p.resident_b ? 1 : 0][ksteps]<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
-  return launch_check("conv_igemm_kernel");
+  (swap ? swap_kernels : kernels)[p.resident_b ? 1 : 0][ksteps]<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
+  return launch_check(swap ? "conv_igemm_kernel<swap>" : "conv_igemm_kernel");
 }

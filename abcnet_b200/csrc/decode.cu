@@ -4,6 +4,8 @@
 // Replaces, bit-exactly, the dense tensor statements and the per-scalar .cpu().item() loop of
 // /root/reference/src/img2smiles.py:62-80, :115-124 and the gather part of :134-182 (see include/abcnet_b200.h).
 // Only the two centre maps are read densely (2 x H x W x 4 B); every other map is touched at peaks only.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace abc {
@@ -246,6 +248,168 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Split decoder (default): grid (N, 2) -- blockIdx.y = 0 decodes the atoms of image n, 1 its bonds; the two halves share
+// nothing (img2smiles.py:134-171 vs :177-193), so splitting doubles the CTAs in flight and halves the dependent phases
+// per CTA. 512 threads; the centre map (HW fp32, float4 loads) is the only large shared-memory object (~70 KB per CTA
+// -> three CTAs per SM), peaks are kept as one 64-bit flag word per thread (<= 64 consecutive pixels each) instead of
+// index lists, and bond peaks are handled by the warp that owns their pixel range, in row-major order, so record
+// offsets only need one 16-entry scan over warps.
+constexpr int kDec2Threads = 512;
+constexpr int kDec2Warps = kDec2Threads / 32;
+
+template <int NW>
+__device__ __forceinline__ int block_exscan_nw(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < NW ? warp_sums[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_sums[lane] = winc - w;
+    if (lane == 31) warp_sums[32] = winc;
+  }
+  __syncthreads();
+  *total = warp_sums[32];
+  return warp_sums[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(kDec2Threads) decode_split_kernel(const DecParams p) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  float* map = reinterpret_cast<float*>(dsm);                                  // [HW]
+  __shared__ int warp_sums[33];
+  __shared__ int warp_cnt[kDec2Warps];
+  __shared__ float wz[kDec2Warps][64];
+
+  const int HW = p.H * p.W;
+  const int n = blockIdx.x, bonds = blockIdx.y;
+  const int k = bonds ? 4 : 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ------------------------------------------------------------------ centre map -> shared memory
+  const float* src = p.maps[k] + static_cast<size_t>(n) * HW;
+  if (!((p.p8f_mask >> k) & 1) && (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* m4 = reinterpret_cast<float4*>(map);
+    for (int i = tid; i < (HW >> 2); i += kDec2Threads) {
+      float4 v = __ldg(s4 + i);
+      v.x = centre_value(v.x, p.centre_prob);
+      v.y = centre_value(v.y, p.centre_prob);
+      v.z = centre_value(v.z, p.centre_prob);
+      v.w = centre_value(v.w, p.centre_prob);
+      m4[i] = v;
+    }
+  } else {
+    for (int i = tid; i < HW; i += kDec2Threads) map[i] = centre_value(ldmap(p, k, n, 0, i, 1), p.centre_prob);
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ peaks of this thread's pixel run (<= 64 pixels)
+  const int per = (HW + kDec2Threads - 1) / kDec2Threads;
+  const int p0 = min(tid * per, HW), p1 = min(p0 + per, HW);
+  unsigned long long flags = 0ull;
+  {
+    int y = p0 / p.W, x = p0 - y * p.W;
+    for (int i = p0; i < p1; ++i) {
+      if (is_peak(map, y, x, p.H, p.W, p.thr)) flags |= 1ull << (i - p0);
+      if (++x == p.W) {
+        x = 0;
+        ++y;
+      }
+    }
+  }
+  int total_peaks;
+  int idx = block_exscan_nw<kDec2Warps>(__popcll(flags), warp_sums, &total_peaks);
+
+  if (!bonds) {
+    // ---------------------------------------------------------------- atoms: one record per peak, row-major order
+    while (flags) {
+      const int i = p0 + __ffsll(static_cast<long long>(flags)) - 1;
+      flags &= flags - 1;
+      if (idx < p.atom_cap) {
+        AbcAtomRec r;
+        r.x = static_cast<uint16_t>(i / p.W);          // reference naming: x = row, y = column (img2smiles.py:178)
+        r.y = static_cast<uint16_t>(i % p.W);
+        r.type = static_cast<uint8_t>(argmax_map(p, 1, n, 0, 1, p.c_type, p.c_type, i));
+        r.charge = static_cast<uint8_t>(argmax_map(p, 2, n, 0, 1, p.c_charge, p.c_charge, i));
+        r.hs = static_cast<uint8_t>(argmax_map(p, 3, n, 0, 1, p.c_hs, p.c_hs, i));
+        r.pad = 0;
+        p.atoms[static_cast<size_t>(n) * p.atom_cap + idx] = r;
+      }
+      ++idx;
+    }
+    if (tid == 0) p.counts[n * 4 + 0] = total_peaks;
+    return;
+  }
+
+  // ------------------------------------------------------------------ bonds: each warp walks the peaks of its own pixel
+  // range in order (lane 0's run first); pass 0 counts the surviving omega bins, pass 1 emits the records
+  int off = 0, total_bonds = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int wcount = 0;
+    for (int sl = 0; sl < 32; ++sl) {
+      unsigned long long fl = __shfl_sync(0xffffffffu, flags, sl);
+      const int base = min((warp * 32 + sl) * per, HW);
+      while (fl) {                                                           // warp-uniform
+        const int pix = base + __ffsll(static_cast<long long>(fl)) - 1;
+        fl &= fl - 1;
+        if (lane < p.n_omega) wz[warp][lane] = ldmap(p, 7, n, lane, pix, p.n_omega);
+        if (lane + 32 < p.n_omega) wz[warp][lane + 32] = ldmap(p, 7, n, lane + 32, pix, p.n_omega);
+        __syncwarp();
+        uint32_t lo, hi;
+        omega_survivors(wz[warp], p.n_omega, p.thr_omega, p.omega_mode, &lo, &hi);
+        if (pass == 1) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t mine = h == 0 ? lo : hi;
+            if ((mine >> lane) & 1u) {
+              const int w = lane + 32 * h;
+              const int o = off + wcount + __popc(mine & ((1u << lane) - 1u)) + (h == 1 ? __popc(lo) : 0);
+              if (o < p.bond_cap) {
+                AbcBondRec r;
+                r.x = static_cast<uint16_t>(pix / p.W);
+                r.y = static_cast<uint16_t>(pix % p.W);
+                r.omega = static_cast<uint8_t>(w);
+                r.type = static_cast<uint8_t>(argmax_map(p, 5, n, w, p.n_omega, p.n_btype, p.n_btype * p.n_omega, pix));
+                r.pad = 0;
+                r.rho = fabsf(ldmap(p, 6, n, w, pix, p.n_omega));
+                p.bonds[static_cast<size_t>(n) * p.bond_cap + o] = r;
+              }
+            }
+          }
+        }
+        wcount += __popc(lo) + __popc(hi);
+        __syncwarp();
+      }
+    }
+    if (pass == 0) {
+      if (lane == 0) warp_cnt[warp] = wcount;
+      __syncthreads();
+      for (int w = 0; w < kDec2Warps; ++w) {
+        const int c = warp_cnt[w];
+        if (w < warp) off += c;
+        total_bonds += c;
+      }
+    }
+  }
+  if (tid == 0) {
+    p.counts[n * 4 + 1] = total_bonds;
+    p.counts[n * 4 + 2] = total_peaks;
+    p.counts[n * 4 + 3] = 0;
+  }
+}
+
 }  // namespace abc
 
 extern "C" int abc_decode_peaks(const AbcDecodeDesc* d, void* stream) {
@@ -273,6 +437,17 @@ extern "C" int abc_decode_peaks(const AbcDecodeDesc* d, void* stream) {
   p.centre_prob = d->centre_prob ? 1 : 0;
   p.thr_omega = p.centre_prob ? d->thr_omega : d->thr;
   p.atoms = d->atoms; p.atom_cap = d->atom_cap; p.bonds = d->bonds; p.bond_cap = d->bond_cap; p.counts = d->counts;
+  static const bool v1 = getenv("ABCNET_DECODE_V1") != nullptr;     // the one-CTA-per-image kernel (kept for comparison)
+  if (!v1) {
+    const size_t smem2 = static_cast<size_t>(d->H) * d->W * 4;
+    static size_t smem2_set = 0;
+    if (smem2 > 40 * 1024 && smem2 > smem2_set) {
+      ABC_CUDA(cudaFuncSetAttribute(decode_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+      smem2_set = smem2;
+    }
+    decode_split_kernel<<<dim3(d->N, 2, 1), kDec2Threads, smem2, static_cast<cudaStream_t>(stream)>>>(p);
+    return launch_check("decode_split_kernel");
+  }
   const size_t smem = static_cast<size_t>(d->H) * d->W * 7;       // 4 B map + 2 B pixel list + 1 B survivor counts
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {

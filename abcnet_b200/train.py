@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import AbcBnActBwdDesc, AbcBnActDesc, AbcConvDesc, AbcWgradDesc, check, lib
-from .unet import fold_rows, pair_pack, row_fold_for, use_cta_pair
+from .unet import fold_rows, pair_pack, row_fold_for, use_cta_pair, use_swap
 
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 _seed_counter = itertools.count(0x5EED)
@@ -105,6 +105,7 @@ def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_sca
         for i, (t0, nt) in enumerate(pk.segments):
             d.seg_tap0[i], d.seg_ntaps[i] = t0, nt
     d.row_fold, d.cta_pair = pk.fold, int(pk.pair)
+    d.swap_mn = int(use_swap(pk, out_mode, dst, pool))
     d.act, d.out_mode = act, out_mode
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = out_scale
     if dst is not None:

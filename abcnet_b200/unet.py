@@ -89,6 +89,16 @@ def use_cta_pair(cin, ntaps, n_tile):
     return cin % 64 == 0 and n_tile % 32 == 0 and cin * ntaps * n_tile * 2 > 160 * 1024
 
 
+def use_swap(pk, out_mode, dst, pool):
+    """Operand-swap mode (AbcConvDesc.swap_mn) for the launches whose n-tile is exactly 128 output channels and whose output is
+    a plain bf16 P8 map: the mid-U-Net 128 -> 128 layers, the cout = 128 decoder layers, their data gradients and the data
+    gradient of the 8-head conv1. One N = 256-pixel MMA replaces two N = 128-channel ones. ABCNET_NO_SWAP=1 disables."""
+    if os.environ.get("ABCNET_NO_SWAP"):
+        return False
+    return (pk.n_tile == 128 and pk.fold == 1 and not pk.pair and not getattr(pk, "segments", None) and out_mode == 0
+            and dst is not None and pool is None)
+
+
 def pair_pack(w_taps, n_tiles, n_tile):
     """Weight blocks of the CTA-pair mode: [n_tiles][cin/64][ntaps][2 halves][n_tile/2 rows][64 channels], each row 128-byte
     swizzled (16-byte chunk c of row r at chunk position c ^ (r % 8)); w_taps: [ntaps, n_tiles * n_tile, cin] fp32."""
@@ -370,6 +380,7 @@ class UNet(nn.Module):
         for i, (dy, dx) in enumerate(pk.taps):
             d.tap_dy[i], d.tap_dx[i] = dy, dx
         d.row_fold, d.cta_pair = pk.fold, int(pk.pair)
+        d.swap_mn = int(use_swap(pk, out_mode, dst, pool))
         d.act, d.out_mode = act, out_mode
         sy, oy, sx, ox = out_scale
         d.out_sy, d.out_oy, d.out_sx, d.out_ox = sy, oy, sx, ox

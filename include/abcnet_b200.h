@@ -118,6 +118,16 @@ typedef struct AbcConvDesc {
    * where the 16-byte chunk c (channels 8c .. 8c+7) of row r is stored at chunk position c ^ (r % 8).
    * Needs cin % 64 == 0, n_tile % 32 == 0, no row_fold / k_segments. */
   int cta_pair;
+  /* Optional operand swap (0 = off) for layers with n_tile == 128 (the mid-U-Net 128 -> 128 convolutions and their data
+   * gradients): the GEMM is issued as D^T = W * A^T, i.e. M = the 128 output channels of the n-tile (weights = tcgen05 A
+   * operand) and N = 256 pixels (a 32 x 8 pixel tile = B operand). A tcgen05.mma pays a fixed cost for fetching its
+   * 128 x 16 A operand from shared memory, so one N = 256 instruction replaces two N = 128 ones (measured on the same
+   * kernel: N = 256 layers reach 1.38 - 1.64 PFLOP/s stand-alone, N = 128 layers 1.22). The accumulator then holds
+   * [channel = TMEM lane][pixel = column]; the epilogue transposes 8 channels x 8 pixels through shared memory so that the
+   * bf16 P8 stores stay 16 bytes per pixel and 128 contiguous bytes per tile row. Same weight pack, same results as the
+   * unswapped kernel bit for bit (identical K order per output element). Needs out_mode 0, no pool_out, no row_fold /
+   * k_segments / cta_pair. */
+  int swap_mn;
 } AbcConvDesc;
 
 ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);

@@ -42,7 +42,8 @@ def bf16_round(x):
 
 
 def run_conv(x, w_taps, bias, taps, n_tile, act=0, out_mode=0, pool=False, out_planes_extra=0, out_plane_off=0,
-             in_plane_off=0, in_planes_extra=0, out_scale=(1, 0, 1, 0), out_hw=None, want_full=True, fold=1, pair=False):
+             in_plane_off=0, in_planes_extra=0, out_scale=(1, 0, 1, 0), out_hw=None, want_full=True, fold=1, pair=False,
+             swap=False):
     """x: NCHW fp32 (bf16-representable). w_taps: [ntaps, cout, cin]. Returns (out NCHW fp32 or None, pooled or None)."""
     L = _lib()
     from abcnet_b200.unet import _Packed
@@ -64,7 +65,7 @@ def run_conv(x, w_taps, bias, taps, n_tile, act=0, out_mode=0, pool=False, out_p
     d.cout, d.n_tile, d.ntaps = cout, n_tile, len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
-    d.act, d.out_mode, d.row_fold, d.cta_pair = act, out_mode, fold, int(pair)
+    d.act, d.out_mode, d.row_fold, d.cta_pair, d.swap_mn = act, out_mode, fold, int(pair), int(swap)
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = out_scale
     oH, oW = out_hw or (H, W)
     out = pooled = None
@@ -271,6 +272,51 @@ def test_igemm_cta_pair_matches_single_cta(cin, cout, n_tile, N, H, W, act):
     assert_close(got[:, 8:8 + cout], ref, 2 ** -7, 2e-3, f"pair conv3x3 {cin}->{cout}")
     assert (got[:, :8] == -5.0).all() and (got[:, 8 + cout:] == -5.0).all()
     assert torch.equal(got, single) and torch.equal(pooled, single_pool)
+
+
+@pytest.mark.parametrize("cin,cout,N,H,W,act,taps", [
+    (128, 128, 2, 64, 32, 1, "3x3"),      # dconv / up3.conv class: weights streamed, full 32 x 8 tiles
+    (128, 128, 1, 48, 40, 2, "3x3"),      # partial tiles in y (48 = 32 + 16) and LeakyReLU
+    (64, 128, 3, 32, 24, 1, "3x3"),       # down3.0 class: one K chunk
+    (256, 128, 1, 32, 16, 0, "3x3"),      # up2.conv.0 class: four K chunks, no activation
+    (1024, 128, 1, 32, 16, 0, "3x3"),     # data gradient of the 8-head conv1: K = 9216
+    (32, 128, 2, 40, 8, 0, "1x1"),        # 1x1 data gradient of a head conv2 (weights resident, no halo), H % 32 != 0
+    (384, 256, 1, 32, 24, 1, "1x1"),      # two n-tiles of 128
+])
+def test_igemm_operand_swap_matches_unswapped(cin, cout, N, H, W, act, taps):
+    """Operand-swap mode (AbcConvDesc.swap_mn: M = 128 output channels, N = 256 pixels, transposing epilogue) == the
+    unswapped kernel bit for bit (same products, same K order per output element), plane offsets honoured, and both within
+    tolerance of the fp64 reference."""
+    x = bf16_round(rnd(cin + H, (N, cin, H, W)))
+    b = rnd(5, (cout,))
+    if taps == "3x3":
+        w = bf16_round(rnd(cout + W, (cout, cin, 3, 3)) * (2.0 / (cin * 9) ** 0.5))
+        wt, tp = torch.stack([w[:, :, dy + 1, dx + 1] for dy, dx in TAPS3]), TAPS3
+        ref = ref_conv3(x, w, b, act)
+    else:
+        w = bf16_round(rnd(cout + W, (cout, cin)) * (2.0 / cin ** 0.5))
+        wt, tp = w.unsqueeze(0), [(0, 0)]
+        ref = torch.einsum("nchw,oc->nohw", x.double(), w.double()) + b.double().view(1, -1, 1, 1)
+        ref = (F.relu(ref) if act == 1 else ref).float()
+    plain, _ = run_conv(x, wt, b, tp, 128, act=act, out_planes_extra=3, out_plane_off=2)
+    got, _ = run_conv(x, wt, b, tp, 128, act=act, out_planes_extra=3, out_plane_off=2, swap=True)
+    assert_close(got[:, 16:16 + cout], ref, 2 ** -7, 2e-3, f"swapped conv {cin}->{cout}")
+    assert (got[:, :16] == -5.0).all() and (got[:, 16 + cout:] == -5.0).all()
+    assert torch.equal(got, plain)
+
+
+def test_igemm_operand_swap_strided_output():
+    """swap_mn with the output mapping of an up-sampling phase (pixel (y, x) -> (2y + 1, 2x), concat slot)."""
+    cin, cout, N, H, W = 256, 128, 2, 32, 16
+    x = bf16_round(rnd(7, (N, cin, H, W)))
+    w = bf16_round(rnd(8, (cout, cin)) * (2.0 / cin ** 0.5))
+    b = rnd(9, (cout,))
+    kw = dict(out_planes_extra=16, out_plane_off=16, out_scale=(2, 1, 2, 0), out_hw=(2 * H, 2 * W))
+    plain, _ = run_conv(x, w.unsqueeze(0), b, [(0, 0)], 128, **kw)
+    got, _ = run_conv(x, w.unsqueeze(0), b, [(0, 0)], 128, swap=True, **kw)
+    ref = (torch.einsum("nchw,oc->nohw", x.double(), w.double()) + b.double().view(1, -1, 1, 1)).float()
+    assert_close(got[:, 128:256, 1::2, 0::2], ref, 2 ** -7, 2e-3, "swapped strided")
+    assert torch.equal(got, plain)
 
 
 def test_igemm_nchw_fp32_heads():

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Lean GPU-box visit: parity tests, bench line (+ reference arm), ncu launch list of the bench command,
+# one ncu --set full capture of a named kernel.  gpurun --timeout 1200 -- 'bash tools/gpu_check3.sh <tag> [kernel-regex] [batch]'
+TAG=${1:-run}; KRE=${2:-conv3x3_c1}; PB=${3:-256}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/${TAG}_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
+tail -3 gpurun_out/${TAG}_pytest.log
+timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+echo "bench exit $?"; tail -c 2500 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:conv|decode|heads" -s 191 -c 96 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/${TAG}_ncu_bench.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:${KRE} -c 1 -f -o gpurun_out/${TAG}_${KRE} \
+    python tools/prof_forward.py ${PB} > gpurun_out/${TAG}_ncu_full.log 2>&1
+echo done
