@@ -69,10 +69,21 @@ LAYER_CLASSES = {
 }
 
 
-def layer_class_report(layers_ms, B, pk):
+def decode_bytes_per_image(n_atoms, n_bpeaks, n_brecs, hw=128 * 128):
+    """Algorithmic bytes of the peak decoder per image: the two centre maps are read densely
+    (2 x HW x 4 B); every other map is touched at peaks only, counted as the 32-byte sectors of the planar-8 fp32 layout:
+    per atom peak type (14 ch = 2 sectors) + charge + H-count = 4 sectors and an 8-byte record; per bond-centre peak the 60
+    omega logits = 8 sectors; per emitted bond record 6 bond-type sectors + 1 rho sector and a 12-byte record; 16 B of counts."""
+    return 2 * hw * 4 + n_atoms * (4 * 32 + 8) + n_bpeaks * 8 * 32 + n_brecs * (7 * 32 + 12) + 16
+
+
+def layer_class_report(layers_ms, B, pk, decode_bytes=None):
     """Fraction of the relevant measured roofline per layer class (north_star), from the live per-launch CUDA-event times."""
     out = {}
-    for name, (kind, members) in LAYER_CLASSES.items():
+    classes = dict(LAYER_CLASSES)
+    if decode_bytes is not None:
+        classes["peak decode (HBM; latency-bound at this size)"] = ("hbm", {"decode": decode_bytes})
+    for name, (kind, members) in classes.items():
         if not all(k in layers_ms for k in members):
             continue
         ms = sum(layers_ms[k] for k in members)
@@ -306,7 +317,14 @@ def run_ours(args, rank, world, local_rank):
     def step_device():
         nonlocal out_bufs
         out_bufs = model.infer(x, out_bufs, layout="p8f")
-        dec.launch(out_bufs)
+        if model.timing is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dec.launch(out_bufs)
+            b.record()
+            model.timing.append(("decode", a, b))
+        else:
+            dec.launch(out_bufs)
 
     sampler = ClockSampler(local_rank)
     sampler.start()                                      # before the warm-up: nvidia-smi takes a moment to deliver its first row
@@ -316,6 +334,7 @@ def run_ours(args, rank, world, local_rank):
     counts = dec.fetch(B)
     n_atoms = float(np.mean([len(a) for a, _, _ in counts]))
     n_bonds = float(np.mean([len(b) for _, b, _ in counts]))
+    n_bpeaks = float(np.mean([c for _, _, c in counts]))
 
     def barrier():
         if world > 1:
@@ -432,9 +451,9 @@ def run_ours(args, rank, world, local_rank):
            "config": {"workload": f"ABC-Net v2 U-Net fwd + fused peak decode, batch {B} x 1x512x512 per GPU (BASELINE configs[1])",
                       "batch_per_gpu": B, "weights": "random-init (deterministic), BN folded, centre/omega biases calibrated",
                       "l2": "inputs (268 MB / batch) and activations exceed the 126 MB L2; no explicit flush",
-                      "avg_atom_peaks": n_atoms, "avg_bond_records": n_bonds,
+                      "avg_atom_peaks": n_atoms, "avg_bond_records": n_bonds, "avg_bond_centre_peaks": n_bpeaks,
                       "whole_forward_tflops": total_tflops, "layers_ms": layers,
-                      "layer_classes": layer_class_report(layers, B, pk)},
+                      "layer_classes": layer_class_report(layers, B, pk, decode_bytes_per_image(n_atoms, n_bpeaks, n_bonds))},
            "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms_e2e / args.steps},
