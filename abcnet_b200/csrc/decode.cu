@@ -40,11 +40,16 @@ __device__ __forceinline__ float ldmap(const DecParams& p, int k, int n, int ch,
 __device__ __forceinline__ int argmax_map(const DecParams& p, int k, int n, int ch0, int chstride, int C, int Ctot, int pix) {
   float best = ldmap(p, k, n, ch0, pix, Ctot);
   int bi = 0;
-  for (int c = 1; c < C; ++c) {
-    const float v = ldmap(p, k, n, ch0 + c * chstride, pix, Ctot);
-    if (v > best) {                               // first maximum wins (torch.argmax)
-      best = v;
-      bi = c;
+  for (int c0 = 1; c0 < C; c0 += 8) {             // eight independent loads in flight, then the ordered comparison
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (c0 + i < C) ? ldmap(p, k, n, ch0 + (c0 + i) * chstride, pix, Ctot) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (c0 + i < C && v[i] > best) {            // first maximum wins (torch.argmax)
+        best = v[i];
+        bi = c0 + i;
+      }
     }
   }
   return bi;
@@ -254,41 +259,13 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_kernel(const DecParams 
 // per CTA. 512 threads; the centre map (HW fp32, float4 loads) is the only large shared-memory object (~70 KB per CTA
 // -> three CTAs per SM), peaks are kept as one 64-bit flag word per thread (<= 64 consecutive pixels each) instead of
 // index lists, and bond peaks are handled by the warp that owns their pixel range, in row-major order, so record
-// offsets only need one 16-entry scan over warps.
+// offsets only need 16-entry scans over warps.
 constexpr int kDec2Threads = 512;
 constexpr int kDec2Warps = kDec2Threads / 32;
-
-template <int NW>
-__device__ __forceinline__ int block_exscan_nw(int v, int* warp_sums, int* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) warp_sums[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    const int w = lane < NW ? warp_sums[lane] : 0;
-    int winc = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, winc, o);
-      if (lane >= o) winc += t;
-    }
-    warp_sums[lane] = winc - w;
-    if (lane == 31) warp_sums[32] = winc;
-  }
-  __syncthreads();
-  *total = warp_sums[32];
-  return warp_sums[warp] + inc - v;
-}
 
 __global__ void __launch_bounds__(kDec2Threads) decode_split_kernel(const DecParams p) {
   extern __shared__ __align__(16) uint8_t dsm[];
   float* map = reinterpret_cast<float*>(dsm);                                  // [HW]
-  __shared__ int warp_sums[33];
   __shared__ int warp_cnt[kDec2Warps];
   __shared__ float wz[kDec2Warps][64];
 
@@ -302,80 +279,123 @@ __global__ void __launch_bounds__(kDec2Threads) decode_split_kernel(const DecPar
   if (!((p.p8f_mask >> k) & 1) && (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
     float4* m4 = reinterpret_cast<float4*>(map);
-    for (int i = tid; i < (HW >> 2); i += kDec2Threads) {
-      float4 v = __ldg(s4 + i);
-      v.x = centre_value(v.x, p.centre_prob);
-      v.y = centre_value(v.y, p.centre_prob);
-      v.z = centre_value(v.z, p.centre_prob);
-      v.w = centre_value(v.w, p.centre_prob);
-      m4[i] = v;
+    const int n4 = HW >> 2;
+    for (int i0 = tid; i0 < n4; i0 += 8 * kDec2Threads) {         // eight 16-byte loads in flight per thread (64 KB per CTA at once)
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * kDec2Threads;
+        if (i < n4) v[u] = __ldg(s4 + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * kDec2Threads;
+        if (i < n4) {
+          v[u].x = centre_value(v[u].x, p.centre_prob);
+          v[u].y = centre_value(v[u].y, p.centre_prob);
+          v[u].z = centre_value(v[u].z, p.centre_prob);
+          v[u].w = centre_value(v[u].w, p.centre_prob);
+          m4[i] = v[u];
+        }
+      }
     }
   } else {
     for (int i = tid; i < HW; i += kDec2Threads) map[i] = centre_value(ldmap(p, k, n, 0, i, 1), p.centre_prob);
   }
   __syncthreads();
 
-  // ------------------------------------------------------------------ peaks of this thread's pixel run (<= 64 pixels)
+  // ------------------------------------------------------------------ peaks
+  // Warp w owns the pixel range [w * per * 32, (w + 1) * per * 32), per = ceil(HW / 512) <= 64. In iteration j its lanes
+  // test the 32 consecutive pixels of run j (consecutive lanes -> consecutive shared-memory words: conflict-free; one
+  // thread per 32-pixel run put all lanes of a warp on the same bank) and the ballot becomes the flag word of run j, kept
+  // by lane j % 32 (runs 0..31 in `lo`, runs 32..63 in `hi`). Row-major order = warp, then lo runs by lane, then hi runs.
   const int per = (HW + kDec2Threads - 1) / kDec2Threads;
-  const int p0 = min(tid * per, HW), p1 = min(p0 + per, HW);
-  unsigned long long flags = 0ull;
-  {
-    int y = p0 / p.W, x = p0 - y * p.W;
-    for (int i = p0; i < p1; ++i) {
-      if (is_peak(map, y, x, p.H, p.W, p.thr)) flags |= 1ull << (i - p0);
-      if (++x == p.W) {
-        x = 0;
-        ++y;
-      }
+  const int wbase = warp * per * 32;
+  uint32_t lo = 0, hi = 0;
+  for (int j = 0; j < per; ++j) {
+    const int i = wbase + j * 32 + lane;
+    bool pk = false;
+    if (i < HW) {
+      const int y = i / p.W;
+      pk = is_peak(map, y, i - y * p.W, p.H, p.W, p.thr);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, pk);
+    if ((j & 31) == lane) {
+      if (j < 32) lo = m;
+      else hi = m;
     }
   }
-  int total_peaks;
-  int idx = block_exscan_nw<kDec2Warps>(__popcll(flags), warp_sums, &total_peaks);
+  const int cnt_lo = __popc(lo), cnt_hi = __popc(hi);
+  int inc_lo = cnt_lo, inc_hi = cnt_hi;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, inc_lo, o), b = __shfl_up_sync(0xffffffffu, inc_hi, o);
+    if (lane >= o) {
+      inc_lo += a;
+      inc_hi += b;
+    }
+  }
+  const int tot_lo = __shfl_sync(0xffffffffu, inc_lo, 31), tot_hi = __shfl_sync(0xffffffffu, inc_hi, 31);
+  if (lane == 0) warp_cnt[warp] = tot_lo + tot_hi;
+  __syncthreads();
+  int warp_off = 0, total_peaks = 0;
+  for (int w = 0; w < kDec2Warps; ++w) {
+    const int c = warp_cnt[w];
+    if (w < warp) warp_off += c;
+    total_peaks += c;
+  }
+  __syncthreads();                                                   // warp_cnt is reused below
 
   if (!bonds) {
     // ---------------------------------------------------------------- atoms: one record per peak, row-major order
-    while (flags) {
-      const int i = p0 + __ffsll(static_cast<long long>(flags)) - 1;
-      flags &= flags - 1;
-      if (idx < p.atom_cap) {
-        AbcAtomRec r;
-        r.x = static_cast<uint16_t>(i / p.W);          // reference naming: x = row, y = column (img2smiles.py:178)
-        r.y = static_cast<uint16_t>(i % p.W);
-        r.type = static_cast<uint8_t>(argmax_map(p, 1, n, 0, 1, p.c_type, p.c_type, i));
-        r.charge = static_cast<uint8_t>(argmax_map(p, 2, n, 0, 1, p.c_charge, p.c_charge, i));
-        r.hs = static_cast<uint8_t>(argmax_map(p, 3, n, 0, 1, p.c_hs, p.c_hs, i));
-        r.pad = 0;
-        p.atoms[static_cast<size_t>(n) * p.atom_cap + idx] = r;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      uint32_t fl = h ? hi : lo;
+      int idx = warp_off + (h ? tot_lo + inc_hi - cnt_hi : inc_lo - cnt_lo);
+      const int base = wbase + (lane + 32 * h) * 32;
+      while (fl) {
+        const int i = base + __ffs(fl) - 1;
+        fl &= fl - 1;
+        if (idx < p.atom_cap) {
+          AbcAtomRec r;
+          r.x = static_cast<uint16_t>(i / p.W);          // reference naming: x = row, y = column (img2smiles.py:178)
+          r.y = static_cast<uint16_t>(i % p.W);
+          r.type = static_cast<uint8_t>(argmax_map(p, 1, n, 0, 1, p.c_type, p.c_type, i));
+          r.charge = static_cast<uint8_t>(argmax_map(p, 2, n, 0, 1, p.c_charge, p.c_charge, i));
+          r.hs = static_cast<uint8_t>(argmax_map(p, 3, n, 0, 1, p.c_hs, p.c_hs, i));
+          r.pad = 0;
+          p.atoms[static_cast<size_t>(n) * p.atom_cap + idx] = r;
+        }
+        ++idx;
       }
-      ++idx;
     }
     if (tid == 0) p.counts[n * 4 + 0] = total_peaks;
     return;
   }
 
   // ------------------------------------------------------------------ bonds: each warp walks the peaks of its own pixel
-  // range in order (lane 0's run first); pass 0 counts the surviving omega bins, pass 1 emits the records
+  // range in order; pass 0 counts the surviving omega bins, pass 1 emits the records
   int off = 0, total_bonds = 0;
   for (int pass = 0; pass < 2; ++pass) {
     int wcount = 0;
-    for (int sl = 0; sl < 32; ++sl) {
-      unsigned long long fl = __shfl_sync(0xffffffffu, flags, sl);
-      const int base = min((warp * 32 + sl) * per, HW);
+    for (int run = 0; run < per; ++run) {
+      uint32_t fl = __shfl_sync(0xffffffffu, run < 32 ? lo : hi, run & 31);
+      const int base = wbase + run * 32;
       while (fl) {                                                           // warp-uniform
-        const int pix = base + __ffsll(static_cast<long long>(fl)) - 1;
+        const int pix = base + __ffs(fl) - 1;
         fl &= fl - 1;
         if (lane < p.n_omega) wz[warp][lane] = ldmap(p, 7, n, lane, pix, p.n_omega);
         if (lane + 32 < p.n_omega) wz[warp][lane + 32] = ldmap(p, 7, n, lane + 32, pix, p.n_omega);
         __syncwarp();
-        uint32_t lo, hi;
-        omega_survivors(wz[warp], p.n_omega, p.thr_omega, p.omega_mode, &lo, &hi);
+        uint32_t slo, shi;
+        omega_survivors(wz[warp], p.n_omega, p.thr_omega, p.omega_mode, &slo, &shi);
         if (pass == 1) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint32_t mine = h == 0 ? lo : hi;
+            const uint32_t mine = h == 0 ? slo : shi;
             if ((mine >> lane) & 1u) {
               const int w = lane + 32 * h;
-              const int o = off + wcount + __popc(mine & ((1u << lane) - 1u)) + (h == 1 ? __popc(lo) : 0);
+              const int o = off + wcount + __popc(mine & ((1u << lane) - 1u)) + (h == 1 ? __popc(slo) : 0);
               if (o < p.bond_cap) {
                 AbcBondRec r;
                 r.x = static_cast<uint16_t>(pix / p.W);
@@ -389,7 +409,7 @@ __global__ void __launch_bounds__(kDec2Threads) decode_split_kernel(const DecPar
             }
           }
         }
-        wcount += __popc(lo) + __popc(hi);
+        wcount += __popc(slo) + __popc(shi);
         __syncwarp();
       }
     }

@@ -86,9 +86,64 @@ class Packed:
                 parts.append(w[t0:t0 + nt].permute(1, 3, 0, 4, 2, 5).reshape(n_tiles, -1, kc // 8, n_tile, 8))
             blocks = torch.cat(parts, 1)                               # [nt][blocks in consumption order][kp][n_tile][8]
             self.cin = K * len(segments)
-        self.w = blocks.contiguous().to(torch.bfloat16)
-        self.bias = bias.contiguous().float()
+        # index mode (PackArena): float64 "codes" instead of values -- the layout code above only moves elements around, so
+        # running it on element indices yields the gather map of the packed block; no cast then
+        raw = w_taps.dtype == torch.float64
+        self.w = blocks.contiguous() if raw else blocks.contiguous().to(torch.bfloat16)
+        self.bias = bias.contiguous() if raw else bias.contiguous().float()
         self.taps, self.n_tile, self.cout, self.segments = taps, n_tile, real_cout, segments
+
+
+class PackArena:
+    """Packed weights of every convolution of the training pass (forward and backward), rebuilt from the fp32 master
+    parameters by ONE ``abc_gather_pack`` launch per dtype and iteration.
+
+    The gather maps are derived by running the ordinary packing code (``Packed``: tap stacking, BN-free layouts, row folding,
+    K segmentation, zero padding) once on tensors of element *codes* ``(parameter id << 22 | offset) + 1`` (0 = zero
+    padding) instead of values. Views into the arenas are stable, so the launch sequence is CUDA-graph replayable."""
+
+    CAP_W = 48 * 1024 * 1024          # bf16 elements (the v2 network needs ~24 M: forward + data-gradient packs)
+    CAP_B = 1024 * 1024               # fp32 elements (biases)
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        assert len(self.params) < 1024 and all(p.numel() < (1 << 22) and p.dtype == torch.float32 for p in self.params)
+        self.pid = {id(p): i for i, p in enumerate(self.params)}
+        self.key = tuple(p.data_ptr() for p in self.params)
+        self.ptrs = torch.tensor(self.key, dtype=torch.int64, device=device)
+        self.dev = device
+        self.w = torch.zeros(self.CAP_W, dtype=torch.bfloat16, device=device)
+        self.wc = torch.full((self.CAP_W,), -1, dtype=torch.int32, device=device)
+        self.b = torch.zeros(self.CAP_B, dtype=torch.float32, device=device)
+        self.bc = torch.full((self.CAP_B,), -1, dtype=torch.int32, device=device)
+        self.used = {"w": 0, "b": 0}
+
+    def codes_of(self, p):
+        base = float((self.pid[id(p)] << 22) + 1)
+        return (torch.arange(p.numel(), dtype=torch.float64, device=self.dev) + base).view(p.shape)
+
+    def add(self, codes, kind):
+        """Append a block given by its float64 code tensor; returns the arena view (filled right away)."""
+        arena, carena = (self.w, self.wc) if kind == "w" else (self.b, self.bc)
+        n = codes.numel()
+        n_pad = (n + 63) // 64 * 64                                    # 128-byte aligned bf16 blocks
+        off = self.used[kind]
+        if off + n_pad > arena.numel():
+            raise RuntimeError("PackArena: capacity exceeded")
+        carena[off:off + n].copy_((codes.reshape(-1).to(torch.int64) - 1).to(torch.int32))     # 0 -> -1 = 0xFFFFFFFF = zero
+        self.used[kind] = off + n_pad
+        self._gather(kind, off, n_pad)
+        return arena[off:off + n].view(codes.shape)
+
+    def _gather(self, kind, off, n):
+        arena, carena = (self.w, self.wc) if kind == "w" else (self.b, self.bc)
+        check(lib.abc_gather_pack(self.ptrs.data_ptr(), carena[off:].data_ptr(), arena[off:].data_ptr(), n, 1 if kind == "w" else 0,
+                                  _st()), "abc_gather_pack")
+
+    def refresh(self):
+        for kind in ("w", "b"):
+            if self.used[kind]:
+                self._gather(kind, 0, self.used[kind])
 
 
 def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_scale=(1, 0, 1, 0), pool=None, pool_plane_off=0):
@@ -144,7 +199,7 @@ def phase_taps(parity, crop_first):
     return [(0, 0), (2, -1)] if parity == 0 else [(1, 0)]
 
 
-def upconv_backward(du, du_off, cout, x, w, crop_first):
+def upconv_backward(du, du_off, cout, x, w, crop_first, eng=None, key=None):
     """Backward of the up-sampling convolution. du: P8 gradient of the cropped output (planes [du_off, du_off+cout/8) of a
     [N, planes, 2H, 2W, 8] buffer); x: P8 input [N, cin/8, H, W, 8]; w: [cin, cout, 3, 3] fp32.
     Returns (dx P8 [N, cin/8, H, W, 8], dw fp32 [cin, cout, 3, 3])."""
@@ -170,7 +225,16 @@ def upconv_backward(du, du_off, cout, x, w, crop_first):
             g = wgrad(dph, phase * (cout // 8), cout, x, 0, cin, [(dy, dx) for (_, _, dy, dx) in fwd_taps])
             for i, (ky, kx, _, _) in enumerate(fwd_taps):
                 dw[:, :, ky, kx] = g[i].t()
-    pk = Packed(torch.stack(mats).float().contiguous(), torch.zeros(cin, device=dev), taps, segments=segments)
+    if eng is None:
+        pk = Packed(torch.stack(mats).float().contiguous(), torch.zeros(cin, device=dev), taps, segments=segments)
+    else:      # gather-packed from the live parameter (w is then only used for its shape above)
+        def make():
+            wi = eng._w(eng_param)
+            m_i = [wi[:, :, ky, kx] for py in (0, 1) for px in (0, 1) for (ky, dy) in phase_taps(py, crop_first)
+                   for (kx, dx_) in phase_taps(px, crop_first)]
+            return Packed(torch.stack(m_i).contiguous(), eng._zeros(cin), taps, segments=segments)
+        eng_param = key[1]
+        pk = eng._pk(key[0], make)
     dx = torch.empty((N, cin // 8, H, W, 8), dtype=torch.bfloat16, device=dev)
     conv(pk, dph, 0, dx)
     return dx, dw
@@ -183,6 +247,47 @@ class TrainEngine:
         self.m = model
         self.bufs = {}
         self.saved = {}
+        self.arena = None            # PackArena of the current parameter storage (ABCNET_NO_ARENA=1: re-pack with torch ops)
+        self._packs = {}
+        self._index_mode = False
+
+    # ------------------------------------------------------------------ packed weights
+    def _w(self, p):
+        """fp32 values of a parameter -- or, while a gather map is being derived, its element codes."""
+        return self.arena.codes_of(p) if self._index_mode else p.detach().float()
+
+    def _zeros(self, n):
+        return torch.zeros(n, dtype=torch.float64 if self._index_mode else torch.float32, device=self.m.s.device)
+
+    def _pk(self, key, make):
+        """Packed weights for ``key``: ``make()`` builds them from ``self._w(...)`` tensors. With the arena the layout is
+        derived once (index mode) and afterwards only refreshed by the per-iteration gather."""
+        if self.arena is None:
+            return make()
+        pk = self._packs.get(key)
+        if pk is None:
+            self._index_mode = True
+            try:
+                pk = make()
+            finally:
+                self._index_mode = False
+            pk.w = self.arena.add(pk.w, "w")
+            pk.bias = self.arena.add(pk.bias, "b")
+            self._packs[key] = pk
+        return pk
+
+    def _sync_arena(self):
+        """Called at the start of every forward: (re)build the arena when the parameter storage changed, else refresh it."""
+        import os
+        if os.environ.get("ABCNET_NO_ARENA"):
+            self.arena, self._packs = None, {}
+            return
+        params = [p for p in self.m.parameters()]
+        key = tuple(p.data_ptr() for p in params)
+        if self.arena is None or self.arena.key != key:
+            self.arena, self._packs = PackArena(params, self.m.s.device), {}
+        else:
+            self.arena.refresh()
 
     # ------------------------------------------------------------------ buffers
     def buf(self, key, shape, dtype=torch.bfloat16, zero=False):
@@ -303,6 +408,7 @@ class TrainEngine:
         x = x.contiguous().view(torch.uint8) if u8 else x.contiguous().float()
         B, _, H, W = x.shape
         plan = self._plan(H, W)
+        self._sync_arena()
         # dropout stream: a device-resident counter, advanced by a device op so that CUDA-graph replays draw new masks
         seed_t = self.bufs.get("seed")
         if seed_t is None:
@@ -314,27 +420,32 @@ class TrainEngine:
             if "up" in u:                                            # up-sampling conv: 4 sub-pixel phases, bias, no BN
                 src = self._tensor(u["src"], B, H, W, (B, u["cin"] // 8, h, w, 8))
                 cat = self._tensor(u["dst"], B, H, W)
-                wt = u["up"].weight.detach().float()
-                bias = u["up"].bias.detach().float()
                 for py in (0, 1):
                     for px in (0, 1):
                         ys, xs = phase_taps(py, m.crop_first), phase_taps(px, m.crop_first)
                         taps = [(dy, dx) for (ky, dy) in ys for (kx, dx) in xs]
-                        mats = torch.stack([wt[:, :, ky, kx].t() for (ky, dy) in ys for (kx, dx) in xs]).contiguous()
-                        conv(Packed(mats, bias, taps), src, 0, cat, out_plane_off=u["dst_off"], out_scale=(2, py, 2, px))
+
+                        def make(up=u["up"], ys=ys, xs=xs, taps=taps):
+                            wt = self._w(up.weight)
+                            mats = torch.stack([wt[:, :, ky, kx].t() for (ky, dy) in ys for (kx, dx) in xs]).contiguous()
+                            return Packed(mats, self._w(up.bias), taps)
+                        conv(self._pk(f"{u['name']}.{py}{px}", make), src, 0, cat, out_plane_off=u["dst_off"], out_scale=(2, py, 2, px))
                 continue
             cout = u["cout"]
             z = self.buf("z:" + u["name"], (B, cout // 8, h, w, 8))
-            wt = u["conv"].weight.detach().float()
-            bias = u["conv"].bias.detach().float()
             if u.get("first"):                                       # direct kernel, raw conv + bias (BN / ReLU follow)
-                w9 = wt.reshape(16, 9).contiguous()
+                w9 = u["conv"].weight.detach().float().reshape(16, 9).contiguous()
+                bias = u["conv"].bias.detach().float()
                 check(lib.abc_conv3x3_c1_raw(x.data_ptr(), 1 if u8 else 0, w9.data_ptr(), bias.data_ptr(), z.data_ptr(), B, h, w, 2, 0,
                                              _st()), "abc_conv3x3_c1_raw")
             else:
                 src = self._tensor(u["src"], B, H, W, (B, u["cin"] // 8, h, w, 8))
-                mats = torch.stack([wt[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
-                conv(Packed(mats, bias, TAPS3, fold=row_fold_for(u["cin"], cout)), src, u["src_off"], z)
+
+                def make(cv=u["conv"], cin=u["cin"], cout=cout):
+                    wt = self._w(cv.weight)
+                    mats = torch.stack([wt[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
+                    return Packed(mats, self._w(cv.bias), TAPS3, fold=row_fold_for(cin, cout))
+                conv(self._pk(u["name"], make), src, u["src_off"], z)
             dst = self._tensor(u["dst"], B, H, W, (B, cout // 8, h, w, 8)) if u["keep"] or u["dst"][0] == "cat" else None
             pool = self._tensor(u["pool"], B, H, W) if u["pool"] else None
             bn = u["bn"]
@@ -345,11 +456,14 @@ class TrainEngine:
         # heads: fused conv1 (N = 128 * heads) -> BN -> LeakyReLU -> Dropout -> per-head 1x1
         trunk = self._tensor(("a", "dconv2.3"), B, H, W, (B, 16, H // 4, W // 4, 8))
         nh = len(m.heads)
-        w1 = torch.cat([om.conv1.weight.detach().float() for om in m.out_modules], 0)
-        b1 = torch.cat([om.conv1.bias.detach().float() for om in m.out_modules])
         zh = self.buf("z:heads", (B, 16 * nh, H // 4, W // 4, 8))
-        conv(Packed(torch.stack([w1[:, :, dy + 1, dx + 1] for dy, dx in TAPS3]), b1, TAPS3, n_tile=256 if (128 * nh) % 256 == 0 else 128),
-             trunk, 0, zh)
+
+        def make_h1():
+            w1 = torch.cat([self._w(om.conv1.weight) for om in m.out_modules], 0)
+            b1 = torch.cat([self._w(om.conv1.bias) for om in m.out_modules])
+            return Packed(torch.stack([w1[:, :, dy + 1, dx + 1] for dy, dx in TAPS3]), b1, TAPS3,
+                          n_tile=256 if (128 * nh) % 256 == 0 else 128)
+        conv(self._pk("heads.conv1", make_h1), trunk, 0, zh)
         gam = torch.cat([om.bn.weight.detach() for om in m.out_modules]).float().contiguous()
         bet = torch.cat([om.bn.bias.detach() for om in m.out_modules]).float().contiguous()
         rme = torch.cat([om.bn.running_mean for om in m.out_modules]).float().contiguous()
@@ -365,9 +479,12 @@ class TrainEngine:
         outs = []
         for i, (h_, om) in enumerate(zip(m.heads, m.out_modules)):
             o = torch.empty((B, h_, H // 4, W // 4), dtype=torch.float32, device=x.device)
-            w2 = om.conv2.weight.detach().float().reshape(h_, -1)
             n_tile = 16 if h_ <= 16 else (64 if h_ <= 64 else 128)
-            conv(Packed(w2.unsqueeze(0).contiguous(), om.conv2.bias.detach().float(), [(0, 0)], n_tile=n_tile), hid, 16 * i, o, out_mode=1)
+
+            def make_h2(om=om, h_=h_, n_tile=n_tile):
+                w2 = self._w(om.conv2.weight).reshape(h_, -1)
+                return Packed(w2.unsqueeze(0).contiguous(), self._w(om.conv2.bias), [(0, 0)], n_tile=n_tile)
+            conv(self._pk(f"heads.{i}.conv2", make_h2), hid, 16 * i, o, out_mode=1)
             outs.append(o)
         return outs
 
@@ -400,14 +517,14 @@ class TrainEngine:
             dw2 = wgrad(dl, 0, c8, hd["hid"], 16 * i, 128, [(0, 0)])[0][:h_]
             sink(om.conv2.weight, dw2.reshape(h_, 128, 1, 1))
             sink(om.conv2.bias, db.float())
-            w2 = om.conv2.weight.detach().float().reshape(h_, 128)
-            w2p = torch.cat([w2, w2.new_zeros(c16 - h_, 128)], 0)            # K = padded logits channels
-            conv(Packed(w2p.t().contiguous().unsqueeze(0), torch.zeros(128, device=dev), [(0, 0)], n_tile=128), dl, 0, dhid,
-                 out_plane_off=16 * i)
+            def make_d2(om=om, h_=h_, c16=c16):
+                w2 = self._w(om.conv2.weight).reshape(h_, 128)
+                w2p = torch.cat([w2, w2.new_zeros(c16 - h_, 128)], 0)        # K = padded logits channels
+                return Packed(w2p.t().contiguous().unsqueeze(0), self._zeros(128), [(0, 0)], n_tile=128)
+            conv(self._pk(f"heads.{i}.conv2.dgrad", make_d2), dl, 0, dhid, out_plane_off=16 * i)
         dzh = self.buf("g:zheads", (B, 16 * nh, H4, W4, 8))
         s1, s2 = self._bn_backward("bn:heads", hd["z"], 128 * nh, hd["st"], 2, dhid, 0, None, dzh, hd["p_drop"], sv["seed"])
         dw1 = wgrad(dzh, 0, 128 * nh, hd["trunk"], 0, 128, TAPS3)            # [9][128*nh][128]
-        w1 = torch.cat([om.conv1.weight.detach().float() for om in m.out_modules], 0)
         for i, om in enumerate(m.out_modules):
             sl = slice(128 * i, 128 * (i + 1))
             sink(om.conv1.weight, dw1[:, sl].permute(1, 2, 0).reshape(128, 128, 3, 3))
@@ -415,8 +532,11 @@ class TrainEngine:
             sink(om.bn.weight, s2[sl].float())
             sink(om.bn.bias, s1[sl].float())
         g_trunk = self._tensor(("a", "dconv2.3"), B, H, W, (B, 16, H4, W4, 8), grad=True)
-        mats = torch.stack([w1[:, :, dy + 1, dx + 1].t() for dy, dx in TAPS3]).contiguous()   # [9][ci=128][co=1024]
-        conv(Packed(mats, torch.zeros(128, device=dev), [(-dy, -dx) for dy, dx in TAPS3], n_tile=128), dzh, 0, g_trunk)
+        def make_d1():
+            w1 = torch.cat([self._w(om.conv1.weight) for om in m.out_modules], 0)
+            mats = torch.stack([w1[:, :, dy + 1, dx + 1].t() for dy, dx in TAPS3]).contiguous()   # [9][ci=128][co=1024]
+            return Packed(mats, self._zeros(128), [(-dy, -dx) for dy, dx in TAPS3], n_tile=128)
+        conv(self._pk("heads.conv1.dgrad", make_d1), dzh, 0, g_trunk)
 
         for u in reversed(sv["plan"]):
             h, w = u["hw"]
@@ -424,7 +544,8 @@ class TrainEngine:
                 gcat = self._tensor(u["dst"], B, H, W, grad=True)
                 xin = self._tensor(u["src"], B, H, W, (B, u["cin"] // 8, h, w, 8))
                 wt = u["up"].weight.detach().float()
-                dx, dwu = upconv_backward(gcat, u["dst_off"], u["cout"], xin, wt, m.crop_first)
+                dx, dwu = upconv_backward(gcat, u["dst_off"], u["cout"], xin, wt, m.crop_first,
+                                          eng=self if self.arena is not None else None, key=(u["name"] + ".dgrad", u["up"].weight))
                 sink(u["up"].weight, dwu)
                 sm = self.buf("up.sum", (u["cout"],), torch.float64)
                 sq = self.buf("up.sq", (u["cout"],), torch.float64)
@@ -445,7 +566,6 @@ class TrainEngine:
             sink(u["bn"].weight, s2.float())
             sink(u["bn"].bias, s1.float())
             sink(u["conv"].bias, torch.zeros(cout, device=dev))
-            wt = u["conv"].weight.detach().float()
             if u.get("first"):
                 dwf = torch.zeros(144, dtype=torch.float32, device=dev)
                 check(lib.abc_conv3x3_c1_wgrad(sv["x"].data_ptr(), 1 if sv["u8"] else 0, dz.data_ptr(), 2, 0, B, h, w, dwf.data_ptr(), _st()),
@@ -456,9 +576,11 @@ class TrainEngine:
             dwt = wgrad(dz, 0, cout, src, u["src_off"], cin, TAPS3)               # [9][cout][cin]
             sink(u["conv"].weight, dwt.permute(1, 2, 0).reshape(cout, cin, 3, 3))
             gsrc = self._tensor(u["src"], B, H, W, (B, cin // 8, h, w, 8), grad=True)
-            mats = torch.stack([wt[:, :, dy + 1, dx + 1].t() for dy, dx in TAPS3]).contiguous()    # [9][ci][co]
-            conv(Packed(mats, torch.zeros(cin, device=dev), [(-dy, -dx) for dy, dx in TAPS3], fold=row_fold_for(cout, cin)), dz, 0, gsrc,
-                 out_plane_off=u["src_off"])
+            def make_d(cv=u["conv"], cin=cin, cout=cout):
+                wt = self._w(cv.weight)
+                mats = torch.stack([wt[:, :, dy + 1, dx + 1].t() for dy, dx in TAPS3]).contiguous()    # [9][ci][co]
+                return Packed(mats, self._zeros(cin), [(-dy, -dx) for dy, dx in TAPS3], fold=row_fold_for(cout, cin))
+            conv(self._pk(u["name"] + ".dgrad", make_d), dz, 0, gsrc, out_plane_off=u["src_off"])
 
 class _UNetTrainFn(torch.autograd.Function):
     @staticmethod

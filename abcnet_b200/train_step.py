@@ -91,6 +91,8 @@ class TrainStep:
             for dst, src in zip(self._tg, targets):
                 if src.data_ptr() != dst.data_ptr():
                     dst.copy_(src, non_blocking=True)
+        if self._opt_in_graph and hasattr(self.opt, "sync_hyperparams"):
+            self.opt.sync_hyperparams()                    # lr edits of param_groups reach the device before the replay
         self.graph.replay()
         if self.opt is not None and not self._opt_in_graph:
             self.opt.step()
@@ -133,7 +135,11 @@ class TrainStep:
         self.launches_per_step = _lib.launch_count() - l0      # kernels of this library inside one replay
 
 
-def make_optimizer(model, lr: float = 2.5e-4, weight_decay: float = 1e-8, capturable: bool = True):
-    """The reference's optimiser (``train.py:55``: Adam, lr 2.5e-4, L2 1e-8), graph-capturable."""
-    return torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr, weight_decay=weight_decay,
-                            capturable=capturable, foreach=True)
+def make_optimizer(model, lr: float = 2.5e-4, weight_decay: float = 1e-8, capturable: bool = True, fused: bool = True):
+    """The reference's optimiser (``train.py:55``: Adam, lr 2.5e-4, L2 1e-8), graph-capturable. ``fused=True`` (default):
+    ``abcnet_b200.FusedAdam`` -- one kernel launch for all parameters; ``fused=False``: ``torch.optim.Adam`` (foreach)."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    if fused:
+        from .optim import FusedAdam
+        return FusedAdam(params, lr=lr, weight_decay=weight_decay)
+    return torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, capturable=capturable, foreach=True)

@@ -296,6 +296,20 @@ ABC_API int abc_channel_sum(const void* x, int N, int H, int W, int planes, int 
 /* P8 [N][planes][2H][2W][8] -> [N][4*C/8][H][W][8], phase (py, px) stacked on the plane axis (backward of the
  * sub-pixel phases of the up-sampling convolution, unet.py:44). */
 ABC_API int abc_deinterleave2(const void* src, int src_planes, int src_plane_off, int C, void* dst, int N, int H, int W, void* stream);
+/* Per-step weight re-layout: out[i] = src_ptrs[code >> 22][code & 0x3FFFFF] converted to bf16
+ * (out_is_bf16 = 1) or copied as fp32 (0); code 0xFFFFFFFF writes 0. src_ptrs is a DEVICE array of fp32 parameter base
+ * pointers, codes a DEVICE uint32 array (n entries, n % 8 == 0, 16-byte aligned like out). One launch rebuilds the packed
+ * weight blocks of every convolution of the forward and backward pass from the fp32 master parameters. */
+ABC_API int abc_gather_pack(const void* src_ptrs, const void* codes, void* out, int64_t n, int out_is_bf16, void* stream);
+/* torch.optim.Adam(lr, betas, eps, weight_decay) of src/train.py:55,141 (L2 decay added to the gradient, bias-corrected
+ * moments) over all parameter tensors in one launch. p/g/m/v_ptrs: DEVICE arrays of per-tensor base pointers (fp32,
+ * contiguous), sizes: DEVICE int64 element counts, chunks: DEVICE int32 pairs (tensor index, chunk index) -- one thread
+ * block per pair handles elements [chunk * abc_adam_chunk_elems(), ...) of that tensor; hyper: DEVICE fp32
+ * {lr, beta1, beta2, eps, weight_decay}; step_dev: DEVICE fp32 count of completed steps, incremented by the call
+ * (CUDA-graph replayable). */
+ABC_API int abc_adam_chunk_elems(void);
+ABC_API int abc_adam_step(const void* p_ptrs, const void* g_ptrs, const void* m_ptrs, const void* v_ptrs, const int64_t* sizes,
+                          const int32_t* chunks, int n_chunks, const float* hyper, float* step_dev, void* stream);
 /* Weight gradient of a convolution on tcgen05 tensor cores (cuDNN backward-filter of the reference's autograd):
  * dw[tap][co][ci] (fp32, caller-zeroed, accumulated with atomicAdd) = sum_pixels dz[co](y, x) * in[ci](y + dy, x + dx). */
 typedef struct AbcWgradDesc {

@@ -217,3 +217,36 @@ def test_train_step_matches_autograd_path_and_graph_replays():
         for n in ba:                                                               # running statistics: exactly two updates
             assert _rel(b[n].float(), ba[n].float()) <= 1e-2, (mode, n)      # 2nd update sees a (noise-amplified) step-2 forward
         assert int(b["inc1.double_conv.1.num_batches_tracked"]) == 2
+
+
+def test_pack_arena_equals_torch_repack(monkeypatch):
+    """The per-iteration gather (PackArena, one abc_gather_pack per dtype) feeds the convolutions the same packed weights as
+    re-packing with torch ops (ABCNET_NO_ARENA=1): logits equal up to the rounding of the fp64-atomic BatchNorm sums, and
+    the arena tracks in-place parameter updates (optimiser steps) without being rebuilt."""
+    B, H, W, seed = 2, 64, 64, 13
+    outs = {}
+    for mode in ("arena", "torch"):
+        if mode == "torch":
+            monkeypatch.setenv("ABCNET_NO_ARENA", "1")
+        else:
+            monkeypatch.delenv("ABCNET_NO_ARENA", raising=False)
+        m, sd, x = _setup(seed, B, H, W)
+        res = []
+        for it in range(2):
+            o = m(x.cuda())
+            res.append([t.detach().clone() for t in o])
+            sum((t * t).sum() for t in o).backward()
+            with torch.no_grad():                                    # in-place update between the two forwards
+                for p in m.parameters():
+                    p.mul_(1.01)
+        eng = m._engine
+        assert (eng.arena is not None) == (mode == "arena")
+        if mode == "arena":
+            assert eng.arena.used["w"] > 15_000_000 and len(eng._packs) > 60
+        outs[mode] = (res, {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None})
+    for it in range(2):
+        for a, b in zip(outs["arena"][0][it], outs["torch"][0][it]):
+            assert _rel(a, b) <= 1e-6, (it, _rel(a, b))
+    for n, ga in outs["arena"][1].items():
+        gb = outs["torch"][1][n]
+        assert _rel(ga, gb) <= 1e-3 or gb.abs().max().item() == 0.0, (n, _rel(ga, gb))

@@ -201,3 +201,54 @@ def test_fused_loss_mode_and_scaled_p8_conversion():
         assert torch.equal(got[:, :Cc], bf16_round(ref)), i
         assert (got[:, Cc:] == 0).all()
         assert_close(db.cpu().float(), ref.double().sum((0, 2, 3)).float(), 1e-5, 1e-9, f"dbias {i}")
+
+
+def test_gather_pack_kernel():
+    """abc_gather_pack: out[i] = params[code >> 22][code & 0x3FFFFF] (bf16 or fp32), 0xFFFFFFFF -> 0."""
+    import ctypes as C
+    from abcnet_b200 import _lib as L
+    g = torch.Generator().manual_seed(3)
+    params = [torch.randn(n, generator=g).cuda() for n in (5, 4096, 1 << 20, 77)]
+    ptrs = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64, device="cuda")
+    n = 8 * 4001
+    pid = torch.randint(0, len(params), (n,), generator=g)
+    off = (torch.rand(n, generator=g) * torch.tensor([p.numel() for p in params])[pid]).long()
+    codes = (pid << 22) | off
+    zero = torch.rand(n, generator=g) < 0.1
+    codes[zero] = -1
+    want = torch.stack([params[i].cpu()[o] for i, o in zip(pid.tolist(), off.tolist())])
+    want[zero] = 0
+    dcodes = codes.to(torch.int32).cuda()
+    for bf16 in (1, 0):
+        out = torch.full((n,), 7.0, dtype=torch.bfloat16 if bf16 else torch.float32, device="cuda")
+        L.check(L.lib.abc_gather_pack(ptrs.data_ptr(), dcodes.data_ptr(), out.data_ptr(), n, bf16, torch.cuda.current_stream().cuda_stream),
+                "abc_gather_pack")
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), want.to(out.dtype))
+
+
+def test_fused_adam_matches_torch_adam():
+    """abcnet_b200.FusedAdam == torch.optim.Adam(lr, weight_decay) (train.py:55) over several steps, including an lr change
+    (train.py:84-85) and tensors smaller / larger than one chunk."""
+    import abcnet_b200
+    g = torch.Generator().manual_seed(4)
+    shapes = [(10,), (128, 128, 3, 3), (16, 1, 3, 3), (4097,), (360, 128, 1, 1)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = abcnet_b200.FusedAdam(pa, lr=2.5e-4, weight_decay=1e-8)
+    ob = torch.optim.Adam(pb, lr=2.5e-4, weight_decay=1e-8)
+    for it in range(6):
+        if it == 3:
+            oa.param_groups[0]["lr"] = ob.param_groups[0]["lr"] = 2.5e-5
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).cuda() * (0.0 if it == 4 else 1.0)     # it 4: pure weight-decay step
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), (a - b).abs().max().item()
+        sa, sb = oa.state[a], ob.state[b]
+        assert torch.allclose(sa["exp_avg"], sb["exp_avg"], rtol=1e-4, atol=1e-7)
+        assert torch.allclose(sa["exp_avg_sq"], sb["exp_avg_sq"], rtol=1e-4, atol=1e-9)
+    assert float(oa.state[pa[0]]["step"]) == 6.0
