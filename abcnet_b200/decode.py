@@ -103,6 +103,14 @@ class PeakDecoder:
         torch.cuda.current_stream().synchronize()
         return self._parse(N)
 
+    def molblocks(self, N, n_threads=0):
+        """MOL-block text of the N images whose records were fetched last (``fetch`` / ``collect``), or ``None`` per image
+        without a molecule -- native multi-threaded host assembly, see ``assemble_molblocks``."""
+        counts = self.h_counts[:N].numpy()
+        if (counts[:, 0] > self.atom_cap).any() or (counts[:, 1] > self.bond_cap).any():
+            raise RuntimeError("decode capacity exceeded; enlarge the capacities")
+        return assemble_molblocks(self.h_atoms, self.h_bonds, self.h_counts[:N], n_threads=n_threads)
+
     def _parse(self, N):
         counts = self.h_counts[:N].numpy()
         if (counts[:, 0] > self.atom_cap).any() or (counts[:, 1] > self.bond_cap).any():
@@ -114,6 +122,49 @@ class PeakDecoder:
 
     def __call__(self, outs, thr=-1.0, omega_mode="nms", apply_sigmoid=False, thr_omega=-1.0):
         return self.fetch(self.launch(outs, thr, omega_mode, apply_sigmoid, thr_omega))
+
+
+_OMEGA_TABLES = {}
+
+
+def omega_tables(n_omega=60):
+    """(cos, sin) of the bin angles omega_w = w * pi / (n_omega / 2) + pi / n_omega - pi / 2 (img2smiles.py:160), float64."""
+    t = _OMEGA_TABLES.get(n_omega)
+    if t is None:
+        w = np.arange(n_omega, dtype=np.int64)
+        omega = w * (np.pi / (n_omega // 2)) + np.pi / n_omega - np.pi / 2
+        t = _OMEGA_TABLES[n_omega] = (np.ascontiguousarray(np.cos(omega)), np.ascontiguousarray(np.sin(omega)))
+    return t
+
+
+def assemble_molblocks(atoms, bonds, counts, n_omega=60, n_threads=0):
+    """Decoded records of a batch -> list of V2000 MOL-block strings (``None`` where the reference yields no molecule), through
+    the native multi-threaded assembler ``abc_assemble_molblocks``: the host loop of ``img2smiles.py:183-318`` plus the text
+    builder of ``generate_smiles.py:18-105`` (the string RDKit parses at ``:115-118``), byte-identical to feeding
+    ``records_to_lists`` into the unchanged Python statements.
+
+    atoms: uint8 [N, atom_cap, 8], bonds: uint8 [N, bond_cap, 12], counts: int32 [N, 4] -- host arrays / CPU tensors as filled
+    by ``PeakDecoder`` (``h_atoms`` / ``h_bonds`` / ``h_counts``)."""
+    def as_np(t, dt):
+        a = t.numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+        if a.dtype != dt or not a.flags.c_contiguous:
+            raise ValueError(f"assemble_molblocks: expected a C-contiguous {dt} host array")
+        return a
+    a, b, c = as_np(atoms, np.uint8), as_np(bonds, np.uint8), as_np(counts, np.int32)
+    N = c.shape[0]
+    if N == 0:
+        return []
+    if a.ndim != 3 or b.ndim != 3 or a.shape[2] != 8 or b.shape[2] != 12 or a.shape[0] < N or b.shape[0] < N or c.shape[1] != 4:
+        raise ValueError("assemble_molblocks: bad record array shapes")
+    cos_t, sin_t = omega_tables(n_omega)
+    n_at, n_bd = int(c[:, 0].max()), int(c[:, 1].max())
+    stride = 96 + 80 * n_at + 16 * n_bd + 230 * min(n_at, 2 * n_bd)          # header + atom lines + bond lines + CHG + implicit-H blocks
+    text = np.empty((N, stride), dtype=np.uint8)
+    lens = np.empty(N, dtype=np.int32)
+    check(lib.abc_assemble_molblocks(a.ctypes.data, a.shape[1], b.ctypes.data, b.shape[1], c.ctypes.data, N, cos_t.ctypes.data,
+                                     sin_t.ctypes.data, n_omega, n_threads, text.ctypes.data, stride, lens.ctypes.data),
+          "abc_assemble_molblocks")
+    return [None if lens[i] < 0 else text[i, :lens[i]].tobytes().decode("ascii") for i in range(N)]
 
 
 def records_to_lists(atoms, bonds, n_bond_peaks=None, n_omega=60):

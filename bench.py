@@ -374,9 +374,10 @@ def run_ours(args, rank, world, local_rank):
     dec2 = [dec, abcnet_b200.PeakDecoder(B, atom_cap=args.atom_cap, bond_cap=args.bond_cap, device=dev)]
     obufs = [out_bufs, None]
 
-    def run_e2e(steps):
+    def run_e2e(steps, mol=False):
         """Every step: H2D of its own images (side stream, double-buffered), forward, decode, D2H of the records; the host
-        collects the records of step i - 1 (waiting on that step's event only) after it has enqueued step i."""
+        collects the records of step i - 1 (waiting on that step's event only) after it has enqueued step i.
+        mol=True: the host additionally assembles every image's records into MOL-block text (native assembler)."""
         for ev in consumed:
             ev.record(main_stream)
         enqueue_copy(0)
@@ -391,7 +392,11 @@ def run_ours(args, rank, world, local_rank):
             dec2[i % 2].fetch_async(n)
             if i > 0:
                 recs = dec2[(i - 1) % 2].collect(n)
+                if mol:
+                    dec2[(i - 1) % 2].molblocks(n)
         recs = dec2[(steps - 1) % 2].collect(B)
+        if mol:
+            return dec2[(steps - 1) % 2].molblocks(B)
         return recs
 
     run_e2e(2)
@@ -403,10 +408,21 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_e2e = t0.elapsed_time(t1)
     d2h = int(sum(a.nbytes + b.nbytes for a, b, _ in recs) + 16 * B)
+    # same loop + native host assembly of the records into MOL-block text, and the assembler alone
+    barrier()
+    t0.record()
+    texts = run_e2e(args.steps, mol=True)
+    t1.record()
+    barrier()
+    ms_mol = t0.elapsed_time(t1)
+    th0 = time.perf_counter()
+    for _ in range(3):
+        dec2[(args.steps - 1) % 2].molblocks(B, n_threads=1)
+    asm_rate = 3 * B / (time.perf_counter() - th0)
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_mol], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+        ms, ms_e2e, ms_mol = t.tolist()
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     train = None
@@ -457,6 +473,11 @@ def run_ours(args, rank, world, local_rank):
            "roofline": roof, "cpu_baseline": cpu,
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms_e2e / args.steps},
+           "e2e_molblock": {"value": world * B * args.steps / (ms_mol * 1e-3), "unit": UNIT, "ms_per_step": ms_mol / args.steps,
+                            "what": "e2e loop + native multi-threaded host assembly of every image's records into V2000 MOL-block "
+                                    "text (abc_assemble_molblocks: img2smiles.py:183-318 + generate_smiles.py:18-105)",
+                            "molecules_per_step": int(sum(t is not None for t in texts)),
+                            "assembler_alone_images_per_s_1_thread": asm_rate},
            "gpu_launches": int(launches), "clocks": clocks, "train": train}
     print(json.dumps(out))
 

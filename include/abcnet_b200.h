@@ -221,6 +221,22 @@ typedef struct AbcDecodeDesc {
 ABC_API int abc_decode_peaks(const AbcDecodeDesc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Host-side assembly of the decoded records into V2000 MOL-block text (HOST memory in, HOST memory out, no GPU work):
+ * the per-image Python loop of src/img2smiles.py:183-318 (atom de-duplication, bond -> atom assignment by the anisotropic
+ * float64 distance, pair de-duplication, valence repair, re-indexing, implicit-H list) followed by the text builder of
+ * src/generate_smiles.py:18-105, multi-threaded over images. Byte-identical to the Python path on the same records.
+ *   atoms / bonds / counts : the arrays abc_decode_peaks filled, after the device -> host copy
+ *   cos_tab / sin_tab      : cos / sin of omega_w = w * (pi / (n_omega / 2)) + pi / n_omega - pi / 2, w < n_omega (float64,
+ *                            computed by the caller with the same library call as its Python path)
+ *   text                   : [N][text_stride] NUL-terminated MOL blocks; text_len[i] = strlen, or -1 when image i has no
+ *                            molecule (no atom or no bond-centre peak, img2smiles.py:126-129)
+ *   n_threads              : 0 = one per hardware thread
+ * Returns ABC_ERR_CAPACITY when a text does not fit text_stride (text_len then holds the required length). */
+ABC_API int abc_assemble_molblocks(const AbcAtomRec* atoms, int atom_cap, const AbcBondRec* bonds, int bond_cap,
+                                   const int32_t* counts, int N, const double* cos_tab, const double* sin_tab, int n_omega,
+                                   int n_threads, char* text, int64_t text_stride, int32_t* text_len);
+
+/* ---------------------------------------------------------------------------------------------------
  * Fused training losses, forward + backward in one pass. Replaces the ~60 ATen kernels (+ autograd) of
  * src/train.py:95-137 (= src/multi_gpu_train2.py:140-192 with class_weights = 0).
  * Pass 1 (abc_loss_partials) accumulates the 8 numerators and 8 denominators in fp64; when all eight dlogits pointers

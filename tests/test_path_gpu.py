@@ -134,6 +134,9 @@ def test_decode_planted_batch_bit_exact(golden_dir, mode, suffix):
                   "atoms_charge_list", "atoms_hs_list"):
             assert L[k] == g[k], k
         assert assemble_ref.records_to_molblock(L) == g["molblock"]
+    # the native host assembler on the decoder's own pinned buffers gives the reference's MOL-block text as well
+    texts = dec.molblocks(4)
+    assert texts == [gold[f"planted{seed}{suffix}"]["molblock"] for seed in range(4)]
 
 
 def test_decode_probability_mode_matches_training_metric_rule():
