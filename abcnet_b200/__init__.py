@@ -3,6 +3,7 @@
 Public surface (mirrors what the reference's scripts use):
   UNet(in_channels, heads)      drop-in for ``from unet import UNet`` (reference src/unet.py:77-119)
   PeakDecoder / records_to_lists  heat-map decoding (reference src/img2smiles.py:62-193)
+  SparseHeadsPipeline           opt-in fused inference + decode with the class heads evaluated at peaks only (bit-identical records)
   assemble_molblocks            native host assembly records -> MOL-block text (src/img2smiles.py:183-318, generate_smiles.py:18-105)
   HeatmapLoss                   fused training losses (reference src/train.py:95-137)
   TrainStep / make_optimizer    one whole training iteration (reference src/train.py:94-141), CUDA-graph replayable
@@ -13,7 +14,8 @@ from ._lib import LIB_PATH, launch_count, lib  # noqa: F401  (raises ImportError
 from .decode import PeakDecoder, assemble_molblocks, records_to_lists  # noqa: F401
 from .loss import HeatmapLoss  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .sparse import SparseHeadsPipeline  # noqa: F401
 from .train_step import TrainStep, make_optimizer  # noqa: F401
 from .unet import UNet  # noqa: F401
 
-__all__ = ["UNet", "HeatmapLoss", "TrainStep", "make_optimizer", "FusedAdam", "PeakDecoder", "records_to_lists", "assemble_molblocks", "launch_count", "LIB_PATH"]
+__all__ = ["UNet", "HeatmapLoss", "TrainStep", "make_optimizer", "FusedAdam", "PeakDecoder", "records_to_lists", "assemble_molblocks", "SparseHeadsPipeline", "launch_count", "LIB_PATH"]

@@ -27,11 +27,18 @@ struct DecParams {
   int p8f_mask;
   int centre_prob;
   float thr_omega;
+  // sparse-heads path (AbcDecodeDesc.sparse_mode): peak lists [N][2][peak_cap] / raw counts [N][2]; hw_gather = pixels per
+  // "image" of the maps the gathers read: H * W, or the number of compact slots N * 2 * peak_cap in finish mode
+  int32_t* peak_pix;
+  int32_t* peak_cnt;
+  int peak_cap;
+  int mode;
+  int hw_gather;
 };
 
 // Element (image n, channel ch, pixel pix) of map k with C channels: NCHW fp32, or planar-8 fp32 [N][ceil(C/8)][HW][8].
 __device__ __forceinline__ float ldmap(const DecParams& p, int k, int n, int ch, int pix, int C) {
-  const size_t hw = static_cast<size_t>(p.H) * p.W;
+  const size_t hw = static_cast<size_t>(p.hw_gather);
   if ((p.p8f_mask >> k) & 1)
     return p.maps[k][((static_cast<size_t>(n) * ((C + 7) >> 3) + (ch >> 3)) * hw + pix) * 8 + (ch & 7)];
   return p.maps[k][(static_cast<size_t>(n) * C + ch) * hw + pix];
@@ -346,6 +353,24 @@ __global__ void __launch_bounds__(kDec2Threads) decode_split_kernel(const DecPar
   }
   __syncthreads();                                                   // warp_cnt is reused below
 
+  if (p.mode == 1) {
+    // ---------------------------------------------------------------- sparse heads, step 1: ordered peak lists only
+    int32_t* list = p.peak_pix + static_cast<size_t>(n * 2 + bonds) * p.peak_cap;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      uint32_t fl = h ? hi : lo;
+      int idx = warp_off + (h ? tot_lo + inc_hi - cnt_hi : inc_lo - cnt_lo);
+      const int base = wbase + (lane + 32 * h) * 32;
+      while (fl) {
+        if (idx < p.peak_cap) list[idx] = base + __ffs(fl) - 1;
+        fl &= fl - 1;
+        ++idx;
+      }
+    }
+    if (tid == 0) p.peak_cnt[n * 2 + bonds] = total_peaks;
+    return;
+  }
+
   if (!bonds) {
     // ---------------------------------------------------------------- atoms: one record per peak, row-major order
 #pragma unroll 1
@@ -430,14 +455,174 @@ __global__ void __launch_bounds__(kDec2Threads) decode_split_kernel(const DecPar
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sparse heads: the class / offset heads are only read at peaks, so the fused inference + decode
+// path evaluates them only there. Slot s = (n * 2 + which) * peak_cap + i holds peak i (row-major order) of image n
+// (which = 0 atoms, 1 bond centres). gather_patches_kernel writes, for every valid slot, the 3x3 neighbourhood of the trunk
+// (zero outside the image = the conv padding) as one "pixel" of a compact P8 tensor [1][9 * planes][P / 8][8][8] whose
+// plane order (64-channel chunk, tap, plane) is the K order of the dense 3x3 implicit GEMM: a 1x1 abc_conv_igemm over it
+// with the SAME packed conv1 weights performs, per output element, the same MMA sequence as the dense layer -> identical
+// bits. One warp per slot.
+__global__ void __launch_bounds__(256) gather_patches_kernel(const uint4* __restrict__ trunk, int H, int W, int planes,
+                                                            const int32_t* __restrict__ peak_pix, const int32_t* __restrict__ peak_cnt,
+                                                            int cap, uint4* __restrict__ out, int P) {
+  const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (slot >= P) return;
+  const int g = slot / cap, i = slot - g * cap;
+  if (i >= min(peak_cnt[g], cap)) return;                      // unused slot: keeps its (finite) old contents
+  const int n = g >> 1;
+  const int pix = peak_pix[slot];
+  const int y = pix / W, x = pix - y * W;
+  const int nq = 9 * planes;
+  const size_t rows = static_cast<size_t>(P >> 3);
+  for (int q = lane; q < nq; q += 32) {
+    const int kc = q / 72, r = q - kc * 72;                     // 72 = 9 taps x 8 planes per 64-channel chunk
+    const int t = r >> 3, pl = r & 7;
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v = __ldg(trunk + ((static_cast<size_t>(n) * planes + kc * 8 + pl) * H + yy) * W + xx);
+    out[(q * rows + (slot >> 3)) * 8 + (slot & 7)] = v;
+  }
+}
+
+constexpr int kMaxPeakCap = 1024;
+
+// Step 3: records from the peak lists and the COMPACT class / offset logits (maps[1..3, 5..7] are [1][C][P] or planar-8
+// [1][ceil(C/8)][P][8] with P = N * 2 * peak_cap slots; ldmap is called with n = 0, pix = slot). Same record logic as
+// decode_split_kernel; grid (N, 2).
+__global__ void __launch_bounds__(kDec2Threads) decode_finish_kernel(const DecParams p) {
+  __shared__ int warp_cnt[kDec2Warps];
+  __shared__ float wz[kDec2Warps][64];
+  __shared__ uint8_t bcnt[kMaxPeakCap];
+  __shared__ int boff[kMaxPeakCap];
+  const int n = blockIdx.x, bonds = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int raw = p.peak_cnt[n * 2 + bonds];
+  const int cnt = min(raw, p.peak_cap);
+  const int slot0 = (n * 2 + bonds) * p.peak_cap;
+  const int32_t* list = p.peak_pix + slot0;
+  if (!bonds) {
+    for (int i = tid; i < cnt; i += kDec2Threads) {
+      if (i >= p.atom_cap) break;
+      const int pix = list[i], slot = slot0 + i;
+      AbcAtomRec r;
+      r.x = static_cast<uint16_t>(pix / p.W);
+      r.y = static_cast<uint16_t>(pix % p.W);
+      r.type = static_cast<uint8_t>(argmax_map(p, 1, 0, 0, 1, p.c_type, p.c_type, slot));
+      r.charge = static_cast<uint8_t>(argmax_map(p, 2, 0, 0, 1, p.c_charge, p.c_charge, slot));
+      r.hs = static_cast<uint8_t>(argmax_map(p, 3, 0, 0, 1, p.c_hs, p.c_hs, slot));
+      r.pad = 0;
+      p.atoms[static_cast<size_t>(n) * p.atom_cap + i] = r;
+    }
+    if (tid == 0) p.counts[n * 4 + 0] = raw;
+    return;
+  }
+  // pass A: surviving omega bins per bond-centre peak
+  for (int b = warp; b < cnt; b += kDec2Warps) {
+    const int slot = slot0 + b;
+    if (lane < p.n_omega) wz[warp][lane] = ldmap(p, 7, 0, lane, slot, p.n_omega);
+    if (lane + 32 < p.n_omega) wz[warp][lane + 32] = ldmap(p, 7, 0, lane + 32, slot, p.n_omega);
+    __syncwarp();
+    uint32_t slo, shi;
+    omega_survivors(wz[warp], p.n_omega, p.thr_omega, p.omega_mode, &slo, &shi);
+    if (lane == 0) bcnt[b] = static_cast<uint8_t>(__popc(slo) + __popc(shi));
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive offsets over the peaks (each thread owns `per` consecutive peaks)
+  const int per = (cnt + kDec2Threads - 1) / kDec2Threads;
+  const int b0 = min(tid * per, cnt), b1 = min(b0 + per, cnt);
+  int c = 0;
+  for (int b = b0; b < b1; ++b) c += bcnt[b];
+  int inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_cnt[warp] = inc;
+  __syncthreads();
+  int woff = 0, total_bonds = 0;
+  for (int w = 0; w < kDec2Warps; ++w) {
+    const int v = warp_cnt[w];
+    if (w < warp) woff += v;
+    total_bonds += v;
+  }
+  int off = woff + inc - c;
+  for (int b = b0; b < b1; ++b) {
+    boff[b] = off;
+    off += bcnt[b];
+  }
+  __syncthreads();
+  // pass B: emit
+  for (int b = warp; b < cnt; b += kDec2Warps) {
+    if (bcnt[b] == 0) continue;
+    const int slot = slot0 + b, pix = list[b];
+    if (lane < p.n_omega) wz[warp][lane] = ldmap(p, 7, 0, lane, slot, p.n_omega);
+    if (lane + 32 < p.n_omega) wz[warp][lane + 32] = ldmap(p, 7, 0, lane + 32, slot, p.n_omega);
+    __syncwarp();
+    uint32_t slo, shi;
+    omega_survivors(wz[warp], p.n_omega, p.thr_omega, p.omega_mode, &slo, &shi);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t mine = h == 0 ? slo : shi;
+      if ((mine >> lane) & 1u) {
+        const int w = lane + 32 * h;
+        const int o = boff[b] + __popc(mine & ((1u << lane) - 1u)) + (h == 1 ? __popc(slo) : 0);
+        if (o < p.bond_cap) {
+          AbcBondRec r;
+          r.x = static_cast<uint16_t>(pix / p.W);
+          r.y = static_cast<uint16_t>(pix % p.W);
+          r.omega = static_cast<uint8_t>(w);
+          r.type = static_cast<uint8_t>(argmax_map(p, 5, 0, w, p.n_omega, p.n_btype, p.n_btype * p.n_omega, slot));
+          r.pad = 0;
+          r.rho = fabsf(ldmap(p, 6, 0, w, slot, p.n_omega));
+          p.bonds[static_cast<size_t>(n) * p.bond_cap + o] = r;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (tid == 0) {
+    p.counts[n * 4 + 1] = total_bonds;
+    p.counts[n * 4 + 2] = raw;
+    p.counts[n * 4 + 3] = 0;
+  }
+}
+
 }  // namespace abc
+
+extern "C" int abc_gather_patches(const void* trunk, int N, int H, int W, int planes, const int32_t* peak_pix, const int32_t* peak_cnt,
+                                  int peak_cap, void* out, void* stream) {
+  using namespace abc;
+  if (int rc = device_check()) return rc;
+  ABC_REQUIRE(trunk && peak_pix && peak_cnt && out, "abc_gather_patches: null pointer");
+  ABC_REQUIRE(N > 0 && H > 0 && W > 0 && planes > 0 && planes % 8 == 0, "abc_gather_patches: planes=%d must be a multiple of 8 (64-channel chunks)", planes);
+  ABC_REQUIRE(peak_cap >= 64 && peak_cap % 64 == 0 && peak_cap <= kMaxPeakCap, "abc_gather_patches: peak_cap=%d (multiple of 64, <= %d)", peak_cap, kMaxPeakCap);
+  const long long P = 2LL * N * peak_cap;
+  ABC_REQUIRE(P < (1LL << 30), "abc_gather_patches: too many slots");
+  gather_patches_kernel<<<static_cast<int>((P + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(trunk), H, W, planes, peak_pix, peak_cnt, peak_cap, static_cast<uint4*>(out), static_cast<int>(P));
+  return launch_check("gather_patches_kernel");
+}
 
 extern "C" int abc_decode_peaks(const AbcDecodeDesc* d, void* stream) {
   using namespace abc;
   if (int rc = device_check()) return rc;
   ABC_REQUIRE(d != nullptr, "abc_decode_peaks: null descriptor");
-  for (int i = 0; i < 8; ++i) ABC_REQUIRE(d->maps[i] != nullptr, "abc_decode_peaks: map %d is null", i);
-  ABC_REQUIRE(d->atoms && d->bonds && d->counts, "abc_decode_peaks: null output");
+  const int mode = d->sparse_mode;
+  ABC_REQUIRE(mode >= 0 && mode <= 2, "abc_decode_peaks: sparse_mode=%d", mode);
+  for (int i = 0; i < 8; ++i) {
+    const bool centre = i == 0 || i == 4;
+    const bool needed = mode == 0 || (mode == 1 && centre) || (mode == 2 && !centre);
+    ABC_REQUIRE(!needed || d->maps[i] != nullptr, "abc_decode_peaks: map %d is null", i);
+  }
+  ABC_REQUIRE(mode == 1 || (d->atoms && d->bonds && d->counts), "abc_decode_peaks: null output");
+  if (mode != 0)
+    ABC_REQUIRE(d->peak_pix && d->peak_cnt && d->peak_cap >= 64 && d->peak_cap % 64 == 0 && d->peak_cap <= kMaxPeakCap,
+                "abc_decode_peaks: sparse modes need peak_pix / peak_cnt and peak_cap (multiple of 64, <= %d)", kMaxPeakCap);
   ABC_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "abc_decode_peaks: bad geometry");
   ABC_REQUIRE(static_cast<int64_t>(d->H) * d->W <= 32768 && d->H <= 65535 && d->W <= 65535,
               "abc_decode_peaks: H*W=%lld exceeds the 32768-pixel per-image limit of the shared-memory decoder",
@@ -446,7 +631,7 @@ extern "C" int abc_decode_peaks(const AbcDecodeDesc* d, void* stream) {
   ABC_REQUIRE(d->c_type >= 1 && d->c_type <= 255 && d->c_charge >= 1 && d->c_charge <= 255 && d->c_hs >= 1 &&
                   d->c_hs <= 255 && d->n_btype >= 1 && d->n_btype <= 255,
               "abc_decode_peaks: class counts out of range");
-  ABC_REQUIRE(d->atom_cap > 0 && d->bond_cap > 0, "abc_decode_peaks: capacities must be positive");
+  ABC_REQUIRE(mode == 1 || (d->atom_cap > 0 && d->bond_cap > 0), "abc_decode_peaks: capacities must be positive");
   ABC_REQUIRE(d->omega_mode == 0 || d->omega_mode == 1, "abc_decode_peaks: omega_mode=%d", d->omega_mode);
   DecParams p;
   for (int i = 0; i < 8; ++i) p.maps[i] = d->maps[i];
@@ -457,8 +642,14 @@ extern "C" int abc_decode_peaks(const AbcDecodeDesc* d, void* stream) {
   p.centre_prob = d->centre_prob ? 1 : 0;
   p.thr_omega = p.centre_prob ? d->thr_omega : d->thr;
   p.atoms = d->atoms; p.atom_cap = d->atom_cap; p.bonds = d->bonds; p.bond_cap = d->bond_cap; p.counts = d->counts;
+  p.peak_pix = d->peak_pix; p.peak_cnt = d->peak_cnt; p.peak_cap = d->peak_cap; p.mode = mode;
+  p.hw_gather = mode == 2 ? 2 * d->N * d->peak_cap : d->H * d->W;
+  if (mode == 2) {
+    decode_finish_kernel<<<dim3(d->N, 2, 1), kDec2Threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return launch_check("decode_finish_kernel");
+  }
   static const bool v1 = getenv("ABCNET_DECODE_V1") != nullptr;     // the one-CTA-per-image kernel (kept for comparison)
-  if (!v1) {
+  if (!v1 || mode == 1) {
     const size_t smem2 = static_cast<size_t>(d->H) * d->W * 4;
     static size_t smem2_set = 0;
     if (smem2 > 40 * 1024 && smem2 > smem2_set) {

@@ -217,8 +217,27 @@ typedef struct AbcDecodeDesc {
                               1: on p = clamp(sigmoid(z), 1e-5, 1 - 1e-5), the training-time metric definition
                               (train.py:95,100,145-151, thr = 0.25); the omega candidates (mode 0) keep using thr_omega */
   float thr_omega;         /* logit threshold of the omega NMS when centre_prob = 1 (ignored otherwise: thr is used) */
+  /* Sparse heads (0 = off): the class / offset maps are only read at peaks, so the fused
+   * inference + decode path may evaluate those heads only there. Slot s = (n * 2 + which) * peak_cap + i is peak i
+   * (row-major) of image n, which = 0 atom centres / 1 bond centres; P = 2 * N * peak_cap slots.
+   *   sparse_mode 1 ("find")  : only maps[0] and maps[4] are read; writes peak_pix[N][2][peak_cap] (pixel index y * W + x,
+   *                             truncated at peak_cap) and the untruncated counts peak_cnt[N][2]; no records.
+   *   sparse_mode 2 ("finish"): maps[1..3] and maps[5..7] are COMPACT logits over the slots -- [1][C][P] fp32, or planar-8
+   *                             [1][ceil(C/8)][P][8] where p8f_mask says so -- as produced by running the heads on the
+   *                             output of abc_gather_patches; records and counts as in mode 0 (counts[0] / counts[2] are
+   *                             the untruncated peak counts: the caller checks them against peak_cap). */
+  int32_t* peak_pix;
+  int32_t* peak_cnt;
+  int peak_cap;            /* multiple of 64, <= 1024 */
+  int sparse_mode;
 } AbcDecodeDesc;
 ABC_API int abc_decode_peaks(const AbcDecodeDesc* desc, void* stream);
+/* Sparse heads, step 2: for every valid slot the 3x3 neighbourhood of the trunk (P8 bf16 [N][planes][H][W][8], zero outside the
+ * image) becomes one pixel of the compact P8 tensor out = [1][9 * planes][P / 8][8][8], planes ordered (64-channel chunk, tap,
+ * plane) = the K order of the dense 3x3 abc_conv_igemm. A 1x1 abc_conv_igemm over `out` (cin = 72 * planes, H = P / 8, W = 8)
+ * with the packed weights of the dense 3x3 layer then reproduces that layer's outputs at the peaks bit for bit. */
+ABC_API int abc_gather_patches(const void* trunk, int N, int H, int W, int planes, const int32_t* peak_pix, const int32_t* peak_cnt,
+                               int peak_cap, void* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Host-side assembly of the decoded records into V2000 MOL-block text (HOST memory in, HOST memory out, no GPU work):
