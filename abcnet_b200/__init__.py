@@ -7,6 +7,7 @@ Public surface (mirrors what the reference's scripts use):
   assemble_molblocks            native host assembly records -> MOL-block text (src/img2smiles.py:183-318, generate_smiles.py:18-105)
   HeatmapLoss                   fused training losses (reference src/train.py:95-137)
   TrainStep / make_optimizer    one whole training iteration (reference src/train.py:94-141), CUDA-graph replayable
+  TargetRasteriser / parse_labels  dense training targets stamped on the GPU from label strings (src/utils.py:83-228)
   FusedAdam                     the reference's Adam (src/train.py:55) as one launch over all parameters
 All compute goes through ``libabcnet_b200.so`` (``include/abcnet_b200.h``); there is no CPU fallback.
 """
@@ -15,7 +16,8 @@ from .decode import PeakDecoder, assemble_molblocks, records_to_lists  # noqa: F
 from .loss import HeatmapLoss  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .sparse import SparseHeadsPipeline  # noqa: F401
+from .targets import TargetRasteriser, parse_labels  # noqa: F401
 from .train_step import TrainStep, make_optimizer  # noqa: F401
 from .unet import UNet  # noqa: F401
 
-__all__ = ["UNet", "HeatmapLoss", "TrainStep", "make_optimizer", "FusedAdam", "PeakDecoder", "records_to_lists", "assemble_molblocks", "SparseHeadsPipeline", "launch_count", "LIB_PATH"]
+__all__ = ["UNet", "HeatmapLoss", "TrainStep", "make_optimizer", "FusedAdam", "PeakDecoder", "records_to_lists", "assemble_molblocks", "SparseHeadsPipeline", "TargetRasteriser", "parse_labels", "launch_count", "LIB_PATH"]

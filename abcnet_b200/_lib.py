@@ -18,7 +18,7 @@ EXPORTS = (
     "abc_loss_partials", "abc_loss_backward",
     "abc_bn_stats", "abc_bn_finalize", "abc_bn_act", "abc_bn_act_backward", "abc_nchw_to_p8", "abc_channel_sum",
     "abc_nchw_to_p8_ex", "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
-    "abc_heads_fused", "abc_heads_fused_pack_sizes", "abc_gather_pack", "abc_adam_step", "abc_adam_chunk_elems", "abc_assemble_molblocks", "abc_gather_patches",
+    "abc_heads_fused", "abc_heads_fused_pack_sizes", "abc_gather_pack", "abc_adam_step", "abc_adam_chunk_elems", "abc_assemble_molblocks", "abc_gather_patches", "abc_rasterise_targets",
 )
 
 
@@ -58,6 +58,17 @@ class AbcDecodeDesc(C.Structure):
         ("bonds", C.c_void_p), ("bond_cap", C.c_int),
         ("counts", C.c_void_p), ("p8f_mask", C.c_int), ("centre_prob", C.c_int), ("thr_omega", C.c_float),
         ("peak_pix", C.c_void_p), ("peak_cnt", C.c_void_p), ("peak_cap", C.c_int), ("sparse_mode", C.c_int),
+    ]
+
+
+class AbcTargetsDesc(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("n_omega", C.c_int), ("n_btype", C.c_int), ("c_type", C.c_int),
+        ("c_charge", C.c_int), ("c_hs", C.c_int),
+        ("atoms", C.c_void_p), ("atom_off", C.c_void_p), ("bonds", C.c_void_p), ("bond_rho", C.c_void_p), ("bond_off", C.c_void_p),
+        ("atom_target", C.c_void_p), ("atom_type", C.c_void_p), ("atom_charge", C.c_void_p), ("atom_hs", C.c_void_p),
+        ("bond_target", C.c_void_p), ("bond_type", C.c_void_p), ("bond_rho_map", C.c_void_p), ("bond_omega", C.c_void_p),
+        ("f64", C.c_int), ("zero_first", C.c_int),
     ]
 
 
@@ -150,6 +161,7 @@ def _load():
     lib.abc_heads_fused_pack_sizes.argtypes = [ci, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     lib.abc_gather_pack.argtypes = [vp, vp, vp, C.c_int64, ci, vp]
     lib.abc_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp, vp, vp]
+    lib.abc_rasterise_targets.argtypes = [C.POINTER(AbcTargetsDesc), vp]
     lib.abc_gather_patches.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci, vp, vp]
     lib.abc_assemble_molblocks.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, ci, ci, vp, C.c_int64, vp]
     return lib

@@ -63,7 +63,8 @@ class SparseHeadsPipeline:
         return t
 
     @torch.no_grad()
-    def launch(self, x, thr=-1.0, omega_mode="nms"):
+    def launch(self, x, thr=-1.0, omega_mode="nms", apply_sigmoid=False, thr_omega=-1.0):
+        """Same decoding options as ``PeakDecoder.launch``."""
         m = self.m
         k2 = m.trunk(x)                                                  # also (re)packs the weights when they changed
         B, _, H4, W4, _ = k2.shape
@@ -84,7 +85,7 @@ class SparseHeadsPipeline:
         m._conv(P_["heads.0.conv2"], hid2, 0, za, act=0, out_mode=1, stream=st)
         m._conv(P_["heads.4.conv2"], hid2, 16, zb, act=0, out_mode=1, stream=st)
         # peak lists
-        d = self._desc(B, H4, W4, thr, omega_mode)
+        d = self._desc(B, H4, W4, thr, omega_mode, apply_sigmoid, thr_omega)
         d.maps[0], d.maps[4] = za.data_ptr(), zb.data_ptr()
         d.sparse_mode = 1
         check(lib.abc_decode_peaks(C.byref(d), st), "abc_decode_peaks[find]")
@@ -98,7 +99,7 @@ class SparseHeadsPipeline:
         for k in _CLASS_HEADS:
             m._conv(P_[f"heads.{k}.conv2"], self.hid_c, 16 * k, self.logits_c[k], act=0, out_mode=2, stream=st)
         # records
-        d = self._desc(B, H4, W4, thr, omega_mode)
+        d = self._desc(B, H4, W4, thr, omega_mode, apply_sigmoid, thr_omega)
         for k in _CLASS_HEADS:
             d.maps[k] = self.logits_c[k].data_ptr()
         d.p8f_mask = sum(1 << k for k in _CLASS_HEADS)
@@ -111,11 +112,12 @@ class SparseHeadsPipeline:
         view = _PackView(pk)
         self.m._conv(view, src, 0, dst, act=2, stream=st)
 
-    def _desc(self, B, H4, W4, thr, omega_mode):
+    def _desc(self, B, H4, W4, thr, omega_mode, apply_sigmoid=False, thr_omega=-1.0):
         d = AbcDecodeDesc()
         d.N, d.H, d.W = B, H4, W4
         d.c_type, d.c_charge, d.c_hs, d.n_omega, d.n_btype = 14, 3, 2, 60, 6
-        d.thr, d.thr_omega = float(thr), float(thr)
+        d.thr, d.thr_omega = float(thr), float(thr_omega)
+        d.centre_prob = int(bool(apply_sigmoid))
         d.omega_mode = {"nms": 0, "raw": 1}[omega_mode]
         d.atoms, d.atom_cap = self.dec.d_atoms.data_ptr(), self.dec.atom_cap
         d.bonds, d.bond_cap = self.dec.d_bonds.data_ptr(), self.dec.bond_cap

@@ -331,6 +331,28 @@ ABC_API int abc_channel_sum(const void* x, int N, int H, int W, int planes, int 
 /* P8 [N][planes][2H][2W][8] -> [N][4*C/8][H][W][8], phase (py, px) stacked on the plane axis (backward of the
  * sub-pixel phases of the up-sampling convolution, unet.py:44). */
 ABC_API int abc_deinterleave2(const void* src, int src_planes, int src_plane_off, int C, void* dst, int N, int H, int W, void* stream);
+/* Dense training targets on the device: the stamping part of src/utils.py:83-228. The host parses
+ * the label strings (abcnet_b200/targets.py: same float64 arithmetic as utils.py:94-160) into records; this call clears
+ * (zero_first) and stamps the eight target maps of a batch in HBM, items in label order, later stamps overwriting earlier
+ * ones exactly as the reference's Python loop does. All pointers are DEVICE pointers.
+ *   atoms    int32 [total atoms][5] = (x, y, type index, charge index, hs); hs outside {0, 1} leaves the H-count map alone
+ *   bonds    int32 [total bonds][6] = (x, y, type index, number of omega bins 1 | 2, bin0, bin1); bond_rho float64 [total]
+ *   atom_off / bond_off  int32 [N + 1] prefix offsets of the images into the record arrays
+ *   maps     atom_target [N][1][H][W], atom_type [N][c_type][H][W], atom_charge [N][c_charge][H][W], atom_hs [N][c_hs][H][W],
+ *            bond_target [N][1][H][W], bond_type [N][n_btype][n_omega][H][W] fp32; bond_rho_map / bond_omega
+ *            [N][n_omega][H][W] float64 (f64 = 1, the reference's dtype, utils.py:91-92) or float32 (f64 = 0)
+ * Coordinates / bins must be in range (the Python wrapper checks; the reference raises IndexError there). */
+typedef struct AbcTargetsDesc {
+  int N, H, W, n_omega, n_btype, c_type, c_charge, c_hs;
+  const int32_t* atoms; const int32_t* atom_off;
+  const int32_t* bonds; const double* bond_rho; const int32_t* bond_off;
+  float* atom_target; float* atom_type; float* atom_charge; float* atom_hs; float* bond_target; float* bond_type;
+  void* bond_rho_map; void* bond_omega;
+  int f64;
+  int zero_first;
+} AbcTargetsDesc;
+ABC_API int abc_rasterise_targets(const AbcTargetsDesc* desc, void* stream);
+
 /* Per-step weight re-layout: out[i] = src_ptrs[code >> 22][code & 0x3FFFFF] converted to bf16
  * (out_is_bf16 = 1) or copied as fp32 (0); code 0xFFFFFFFF writes 0. src_ptrs is a DEVICE array of fp32 parameter base
  * pointers, codes a DEVICE uint32 array (n entries, n % 8 == 0, 16-byte aligned like out). One launch rebuilds the packed

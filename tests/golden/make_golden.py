@@ -15,6 +15,7 @@ executed here:
     ``rdkit`` / ``indigo`` modules whose MolFromMolBlock/MolToSmiles return the MOL-block text.
   * losses: ``src/train.py`` lines 95-137 (and ``multi_gpu_train2.py`` 140-192) are exec'd on
     deterministic logits / dense targets; gradients come from autograd on those statements.
+  * dense training targets: ``src/utils.py`` lines 83-228 are exec'd on deterministic label strings.
 
 No reference source is copied into the repository: slices are read at run time.
 """
@@ -245,8 +246,45 @@ def golden_loss():
     print("loss goldens written", rec["train"]["loss"], rec["train2"]["loss"])
 
 
+# ----------------------------------------------------------------------------- dense training targets
+TARGET_NAMES = ("atom_target", "atom_type", "atom_charge", "atom_hs", "bond_target", "bond_type", "bond_rho", "bond_omega_type")
+TARGET_CASES = [(seed, sx, sy, ddx, ddy) for seed in range(4) for (sx, sy, ddx, ddy) in ((1, 1, 0, 0), (0.87, 1, 33, 0), (1, 0.93, 0, 17))]
+
+
+def run_reference_rasteriser(atoms_string, bonds_string, scale_x, scale_y, ddx, ddy):
+    """utils.py:83-228 (the body of MolDataset.__getitem__ after the image augmentation) exec'd on the given labels. The only
+    shim: ``np.math`` (removed in numpy 2) is mapped to the ``math`` module the reference's ``np.math.atan`` resolved to."""
+    import math
+
+    class NPShim:
+        def __getattr__(self, k):
+            return getattr(np, k)
+    shim = NPShim()
+    shim.math = math
+    ns = {"np": shim, "torch": torch}
+    exec(ref_lines("utils.py", 11, 16), ns)                         # device, vocabularies
+    ns.update(atoms_string=atoms_string, bonds_string=bonds_string, scale_x=scale_x, scale_y=scale_y, ddx=ddx, ddy=ddy)
+    exec(ref_lines("utils.py", 83, 228), ns)
+    return [ns[k] for k in TARGET_NAMES]
+
+
+def golden_targets():
+    from oracle import targets_ref
+    out = {}
+    for i, (seed, sx, sy, ddx, ddy) in enumerate(TARGET_CASES):
+        a, b = targets_ref.label_strings(seed)
+        for name, arr in zip(TARGET_NAMES, run_reference_rasteriser(a, b, sx, sy, ddx, ddy)):
+            nz = np.flatnonzero(arr)                                  # the maps are > 99.9 % zeros: store the support only
+            out[f"c{i}_{name}_idx"] = nz.astype(np.int32)
+            out[f"c{i}_{name}_val"] = arr.reshape(-1)[nz]
+            out[f"c{i}_{name}_shape"] = np.array(arr.shape, np.int32)
+    out["cases"] = np.array(TARGET_CASES, np.float64)                 # (label seed, scale_x, scale_y, ddx, ddy) per case
+    np.savez_compressed(os.path.join(HERE, "target_cases.npz"), **out)
+    print("target goldens written", len(TARGET_CASES), "cases")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "decode", "loss"]
+    which = sys.argv[1:] or ["unet", "decode", "loss", "targets"]
     torch.set_num_threads(os.cpu_count() or 1)
     if "unet" in which:
         golden_unet()
@@ -254,3 +292,5 @@ if __name__ == "__main__":
         golden_decode()
     if "loss" in which:
         golden_loss()
+    if "targets" in which:
+        golden_targets()

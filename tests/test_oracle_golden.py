@@ -103,3 +103,33 @@ def test_loss_oracle_matches_reference(golden_dir, key, cw):
     t64, _, _ = loss_ref.losses([o.detach() for o in outs], tg, s.detach(), class_weights=cw,
                                 compute_dtype=torch.float64)
     assert abs(t64.item() - g["loss"]) <= 1e-5 * abs(g["loss"])
+
+
+TARGET_NAMES = ("atom_target", "atom_type", "atom_charge", "atom_hs", "bond_target", "bond_type", "bond_rho", "bond_omega_type")
+
+
+def target_cases(golden_dir):
+    """(case index, label strings, (scale_x, scale_y, ddx, ddy), {name: dense array}) from tests/golden/target_cases.npz."""
+    from oracle import targets_ref
+    g = np.load(os.path.join(golden_dir, "target_cases.npz"))
+    for i, (seed, sx, sy, ddx, ddy) in enumerate(g["cases"].tolist()):
+        sx, sy = (int(sx) if sx == 1 else sx), (int(sy) if sy == 1 else sy)
+        dense = {}
+        for name in TARGET_NAMES:
+            arr = np.zeros(int(np.prod(g[f"c{i}_{name}_shape"])), g[f"c{i}_{name}_val"].dtype)
+            arr[g[f"c{i}_{name}_idx"]] = g[f"c{i}_{name}_val"]
+            dense[name] = arr.reshape(tuple(g[f"c{i}_{name}_shape"]))
+        yield i, targets_ref.label_strings(int(seed)), (sx, sy, int(ddx), int(ddy)), dense
+
+
+def test_target_rasteriser_oracle_matches_reference(golden_dir):
+    """oracle/targets_ref.py vs the maps produced by the reference's own statements (utils.py:83-228), all eight target
+    arrays, values and dtypes (float64 rho / omega), bit-exact."""
+    from oracle import targets_ref
+    n = 0
+    for i, (a, b), aug, dense in target_cases(golden_dir):
+        for name, arr in zip(TARGET_NAMES, targets_ref.rasterise(a, b, *aug)):
+            assert arr.dtype == dense[name].dtype and arr.shape == dense[name].shape, (i, name)
+            assert np.array_equal(arr, dense[name]), (i, name)
+        n += 1
+    assert n == 12
