@@ -37,8 +37,8 @@ UNIT = "images/s"
 FLOPS_PER_IMAGE = 93.98e9          # SURVEY.md section 6 (forward, v2 heads, 512x512)
 HEADS_CONV1_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 1024 * 1152      # fused 8-head 3x3 conv: M=16384, N=1024, K=1152
 # dram__bytes_read.sum + dram__bytes_write.sum of that launch at batch 256, from the committed `ncu --set full` capture
-# profiles/r01_heads_conv1_b256_v7.summary.txt (3.02 GB read + 8.54 GB written; algorithmic: 1.07 GB trunk in + 8.59 GB hidden out)
-HEADS_CONV1_DRAM_BYTES_B256 = 3.024684e9 + 8.543432e9
+# profiles/r01_heads_conv1_b256_v16.summary.txt (2.70 GB read + 8.54 GB written; algorithmic: 1.07 GB trunk in + 8.59 GB hidden out)
+HEADS_CONV1_DRAM_BYTES_B256 = 2.703330e9 + 8.539355e9
 HEADS_CONV2_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 128 * 501        # the eight 1x1 convs, algorithmic (unpadded) channels
 HEADS_FUSED_DRAM_BYTES_B256 = None                                # filled from the ncu capture of heads_fused_kernel
 
