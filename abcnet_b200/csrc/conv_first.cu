@@ -1,7 +1,8 @@
 // First convolution of the U-Net: 1 -> 16 channels on the binary 1 x H x W image, 3x3, pad 1, BatchNorm folded, ReLU.
 // Replaces nn.Conv2d(1,16,3,padding=1) + BatchNorm2d + ReLU of inc1 (/root/reference/src/unet.py:12-14 via :83,:101).
 // Bandwidth class: reads 4 B/pixel (fp32 image as the reference's DataLoader delivers it, utils.py:80-81) and writes
-// 32 B/pixel (two bf16 P8 planes); one thread per pixel, 128-bit coalesced stores.
+// 32 B/pixel (two bf16 P8 planes). conv3x3_c1_rows_kernel (table-driven, one warp per 128-pixel-wide strip) is the product
+// path; conv3x3_c1_kernel (one thread per pixel, plain arithmetic) is kept as the readable reference (ABCNET_C1_SIMPLE=1).
 #include <cstdlib>
 #include <cuda_bf16.h>
 

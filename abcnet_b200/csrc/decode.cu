@@ -1,5 +1,8 @@
 // Fused heat-map decoder: threshold + 3x3 NMS on the atom / bond centre maps, ordered (row-major) peak compaction,
-// per-peak class arg-max, circular omega NMS + half-circle test, rho / bond-type gather -- one CTA per image.
+// per-peak class arg-max, circular omega NMS + half-circle test, rho / bond-type gather.
+// Kernels: decode_split_kernel (default: one CTA for the atoms and one for the bonds of every image; also the peak-list
+// step of the sparse-heads path), decode_kernel (v1: one CTA per image, ABCNET_DECODE_V1=1), gather_patches_kernel and
+// decode_finish_kernel (sparse heads).
 //
 // Replaces, bit-exactly, the dense tensor statements and the per-scalar .cpu().item() loop of
 // /root/reference/src/img2smiles.py:62-80, :115-124 and the gather part of :134-182 (see include/abcnet_b200.h).
