@@ -42,4 +42,4 @@ def test_losses_on_device_targets_equal_losses_on_host_targets(golden_dir):
     crit = abcnet_b200.HeatmapLoss(class_weights=True)
     la = crit(logits, [torch.from_numpy(t).cuda().contiguous() for t in host], s)
     lb = crit(logits, [t.contiguous() for t in dev_t], s)
-    assert la.item() == lb.item()
+    assert abs(la.item() - lb.item()) <= 1e-12 * abs(la.item())      # identical targets; fp64 atomic sums are equal to rounding only
