@@ -119,6 +119,18 @@ if __name__ == "__main__":
                 os.environ.pop("ABCNET_MT256", None)
             bench(f"heads 128->1024@128 MT256={mt256}", 256, 128, 1024, 128, 128, 256, act=2, iters=5)
         os.environ.pop("ABCNET_MT256", None)
+    if which == "conv2":                      # the 1x1 head convolutions (HBM class): n_tile / mt variants, stand-alone
+        one = [(0, 0)]
+        for nt in (128, 192, 256, 96, 64):
+            for mt in (None, 1):
+                bench("head 128->360 p8f", 256, 128, 360, 128, 128, nt, taps=one, out_mode=2, act=0, mt=mt, iters=10)
+        for nt in (64, 128):
+            bench("head 128->60 p8f", 256, 128, 60, 128, 128, nt, taps=one, out_mode=2, act=0, iters=10)
+        for cout in (14, 3, 2):
+            for nt in (16, 32):
+                bench(f"head 128->{cout} p8f", 256, 128, cout, 128, 128, nt, taps=one, out_mode=2, act=0, iters=10)
+        for nt in (16, 32):
+            bench("head 128->1 nchw", 256, 128, 1, 128, 128, nt, taps=one, out_mode=1, act=0, iters=10)
     if which == "one16f":
         bench("16->16@512", 64, 16, 16, 512, 512, 16, fold=4, iters=1)
     if which == "one16":                      # single configuration for ncu captures: layer_bench.py one16 [mt]
