@@ -315,7 +315,10 @@ class UNet(nn.Module):
         for i, om in enumerate(self.out_modules):
             w2 = om.conv2.weight.detach().float().reshape(om.conv2.weight.shape[0], -1)
             h = w2.shape[0]
-            n_tile = 16 if h <= 16 else (64 if h <= 64 else 128)
+            # n-tile of the 1x1 head convolutions (HBM class). Measured stand-alone at B = 256 (tools/layer_bench.py conv2): the
+            # small heads run at 6.5 - 6.7 TB/s, 60 channels at 5.4; for 360 channels two tiles of 192 (4.63 TB/s) beat three of
+            # 128 (4.36) and two of 256 (3.9): fewer re-reads of the hidden tile at the same padding.
+            n_tile = 16 if h <= 16 else (64 if h <= 64 else (128 if h <= 128 else (192 if (h + 191) // 192 * 192 <= (h + 127) // 128 * 128 else 128)))
             P[f"heads.{i}.conv2"] = _Packed(w2.unsqueeze(0).contiguous(), om.conv2.bias.detach().float(), [(0, 0)], n_tile, h)
         P["heads.fused"] = self._pack_fused_heads(dev)
         self._packed = P

@@ -322,7 +322,7 @@ def test_igemm_operand_swap_strided_output():
 def test_igemm_nchw_fp32_heads():
     cin, N, H, W = 128, 2, 32, 24
     x = bf16_round(rnd(81, (N, 256, H, W)))
-    for cout, n_tile, off in ((1, 16, 0), (14, 16, 16), (360, 128, 0), (60, 64, 16)):
+    for cout, n_tile, off in ((1, 16, 0), (14, 16, 16), (360, 128, 0), (360, 192, 0), (60, 64, 16)):
         w = bf16_round(rnd(82 + cout, (cout, cin)) * 0.1)
         b = rnd(83, (cout,))
         xs = x[:, off * 8: off * 8 + cin]
