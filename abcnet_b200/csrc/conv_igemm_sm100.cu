@@ -439,10 +439,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const float bias = bias_s[q * 32 + lane];
     const float slope = p.act == 1 ? 0.f : (p.act == 2 ? 0.01f : 1.f);     // act(v) = max(v, slope * v)
     const int g8 = lane >> 3, i8 = lane & 7;
+    // row folding J: GEMM row m = j * (128 / J) + channel, pixel column (r, c) = image row (ty * 32 + r) * J + j. The 8-channel
+    // group this lane stores after the transposition starts at GEMM row m0.
+    const int J = p.fold, cpj = 128 / J;
+    const int m0 = q * 32 + g8 * 8;
+    const int fj = m0 / cpj, ch0 = m0 - fj * cpj;
     uint8_t* stage = smem + kHeaderBytes + (warp - 4) * kSwapWarpBytes;
     __nv_bfloat16* st_w = reinterpret_cast<__nv_bfloat16*>(stage) + lane;                     // + pixel * (kSwapRowBytes / 2)
     const uint4* st_r = reinterpret_cast<const uint4*>(stage + i8 * kSwapRowBytes + g8 * 16);  // + row * 8 * kSwapRowBytes / 16
-    const bool plane_ok = (n0 + q * 32 + g8 * 8) < p.cout;
+    const bool plane_ok = (n0 + ch0) < p.cout;
     const size_t out_plane_px = static_cast<size_t>(p.out_H) * p.out_W;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -452,9 +457,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       const int ty = rem / p.groups_x;
       const int tx = rem - ty * p.groups_x;
       const int x = tx * 8 + i8;
-      const int y0 = ty * 32 + eh * 16;
+      const int y0 = (ty * 32 + eh * 16) * J + fj;
       uint4* obase = reinterpret_cast<uint4*>(p.out) +
-                     (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + (n0 >> 3) + q * 4 + g8) * out_plane_px +
+                     (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + ((n0 + ch0) >> 3)) * out_plane_px +
                      static_cast<size_t>(p.out_oy) * p.out_W + (x * p.out_sx + p.out_ox);
       const bool col_ok = plane_ok && x < p.W;
       const uint32_t tbase = tmem_base + acc * p.acc_cols + (static_cast<uint32_t>(q * 32) << 16) + eh * 128;
@@ -470,7 +475,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const uint4 val = st_r[rr * (8 * kSwapRowBytes / 16)];
-          const int y = y0 + it * 2 + rr;
+          const int y = y0 + (it * 2 + rr) * J;
           if (col_ok && y < p.H) obase[static_cast<size_t>(y * p.out_sy) * p.out_W] = val;
         }
         __syncwarp();
@@ -718,8 +723,9 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   }
   const bool swap = d->swap_mn != 0;
   if (swap) {
-    ABC_REQUIRE(d->n_tile == 128 && fold == 1 && d->k_segments <= 1 && !d->cta_pair,
-                "abc_conv_igemm: swap_mn needs n_tile == 128 and no row_fold / k_segments / cta_pair");
+    // with row folding the 128 GEMM rows are (folded row j, channel): row_fold * cout == 128, weight pack rows ordered j * cout + co
+    ABC_REQUIRE(d->n_tile == 128 && (fold == 1 || fold == 2 || fold == 4) && d->k_segments <= 1 && !d->cta_pair,
+                "abc_conv_igemm: swap_mn needs n_tile == 128 and no k_segments / cta_pair");
     ABC_REQUIRE(d->out_mode == 0 && d->out != nullptr && d->pool_out == nullptr,
                 "abc_conv_igemm: swap_mn supports plain P8 outputs only (no pool_out)");
   }
@@ -753,7 +759,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.tiles_x = (d->W + 7) / 8;
   p.fold = fold;
   p.dbg = getenv("ABCNET_PAIR_DBG") ? atoi(getenv("ABCNET_PAIR_DBG")) : 0;
-  p.tile_rows = swap ? 32 : 16 * fold;
+  p.tile_rows = swap ? 32 * fold : 16 * fold;
   p.tiles_y = (d->H + p.tile_rows - 1) / p.tile_rows;
   p.in_plane_off = d->in_plane_off;
   const int kc = conv_kc(d->cin);
@@ -821,7 +827,8 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   }
   for (int mt = mt_max; mt >= 1 && !p.mt; --mt) {          // otherwise stream weight blocks through a ring
     const uint32_t a_stage = mt * p.a_tile_bytes;
-    if (hdr + 2 * a_stage + 4 * p.b_block_bytes <= kSmemBudget) {
+    // at least 4 weight blocks in the ring; the folded swap tiles of the 64-channel layers (2 x 84 KB of activations) leave room for 3
+    if (hdr + 2 * a_stage + (swap && fold > 1 ? 3 : 4) * p.b_block_bytes <= kSmemBudget) {
       p.mt = mt; p.resident_b = 0; p.na = 2;
       if (hdr + 3 * a_stage + 6 * p.b_block_bytes <= kSmemBudget) p.na = 3;
       p.a_stage_bytes = a_stage;

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import AbcBnActBwdDesc, AbcBnActDesc, AbcConvDesc, AbcWgradDesc, check, lib
-from .unet import fold_rows, pair_pack, row_fold_for, use_cta_pair, use_swap
+from .unet import fold_rows, fold_rows_swap, pair_pack, row_fold_for, swap_fold_for, use_cta_pair, use_swap
 
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 _seed_counter = itertools.count(0x5EED)
@@ -57,12 +57,13 @@ def _n_tile(cout):
 class Packed:
     """Packed bf16 weight blocks in the kernel's consumption order (see include/abcnet_b200.h)."""
 
-    def __init__(self, w_taps, bias, taps, n_tile=None, segments=None, fold=1):
+    def __init__(self, w_taps, bias, taps, n_tile=None, segments=None, fold=1, fold_swap=False):
         # w_taps: [ntaps, cout, K] fp32; without segments every tap sees all K channels. With segments =
         # [(tap0, ntaps), ...] the K axis of tap t covers only its segment's channels (K = channels per segment).
         self.fold, real_cout = fold, w_taps.shape[1]
+        self.fold_swap = bool(fold_swap) and fold > 1                  # folded rows in the operand-swap order (unet.swap_fold_for)
         if fold > 1:                                                   # row folding (AbcConvDesc.row_fold): Toeplitz along y
-            w_taps, bias = fold_rows(w_taps, bias, taps, fold)
+            w_taps, bias = (fold_rows_swap if self.fold_swap else fold_rows)(w_taps, bias, taps, fold)
             n_tile = fold * real_cout
         ntaps, cout, K = w_taps.shape
         n_tile = n_tile or _n_tile(cout)
@@ -444,7 +445,8 @@ class TrainEngine:
                 def make(cv=u["conv"], cin=u["cin"], cout=cout):
                     wt = self._w(cv.weight)
                     mats = torch.stack([wt[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
-                    return Packed(mats, self._w(cv.bias), TAPS3, fold=row_fold_for(cin, cout))
+                    js = swap_fold_for(cin, cout)                      # train-mode convolutions write plain maps (pooling is in bn_act)
+                    return Packed(mats, self._w(cv.bias), TAPS3, fold=js or row_fold_for(cin, cout), fold_swap=bool(js))
                 conv(self._pk(u["name"], make), src, u["src_off"], z)
             dst = self._tensor(u["dst"], B, H, W, (B, cout // 8, h, w, 8)) if u["keep"] or u["dst"][0] == "cat" else None
             pool = self._tensor(u["pool"], B, H, W) if u["pool"] else None
@@ -579,7 +581,8 @@ class TrainEngine:
             def make_d(cv=u["conv"], cin=cin, cout=cout):
                 wt = self._w(cv.weight)
                 mats = torch.stack([wt[:, :, dy + 1, dx + 1].t() for dy, dx in TAPS3]).contiguous()    # [9][ci][co]
-                return Packed(mats, self._zeros(cin), [(-dy, -dx) for dy, dx in TAPS3], fold=row_fold_for(cout, cin))
+                js = swap_fold_for(cout, cin)
+                return Packed(mats, self._zeros(cin), [(-dy, -dx) for dy, dx in TAPS3], fold=js or row_fold_for(cout, cin), fold_swap=bool(js))
             conv(self._pk(u["name"] + ".dgrad", make_d), dz, 0, gsrc, out_plane_off=u["src_off"])
 
 class _UNetTrainFn(torch.autograd.Function):

@@ -89,14 +89,24 @@ def use_cta_pair(cin, ntaps, n_tile):
     return cin % 64 == 0 and n_tile % 32 == 0 and cin * ntaps * n_tile * 2 > 160 * 1024
 
 
+def swap_fold_for(cin, cout, plain_output=True):
+    """Row folding combined with the operand swap for the 32- and 64-channel 3x3 layers whose output is a plain P8 map:
+    J = 128 / cout vertically adjacent pixels share one pixel column and the 128 GEMM rows are (row j, channel) -- one
+    M = 128 x N = 256 MMA per (tap, 16 channels) covers 256 * J pixels with 3 (J + 2) taps instead of 9 J.
+    Returns J (0 = not applicable). ABCNET_NO_SWAP / ABCNET_NO_FOLD disable."""
+    if os.environ.get("ABCNET_NO_SWAP") or os.environ.get("ABCNET_NO_FOLD") or os.environ.get("ABCNET_NO_SWAPFOLD") or not plain_output:
+        return 0
+    return {64: 2, 32: 4}.get(cout, 0)
+
+
 def use_swap(pk, out_mode, dst, pool):
     """Operand-swap mode (AbcConvDesc.swap_mn) for the launches whose n-tile is exactly 128 output channels and whose output is
     a plain bf16 P8 map: the mid-U-Net 128 -> 128 layers, the cout = 128 decoder layers, their data gradients and the data
     gradient of the 8-head conv1. One N = 256-pixel MMA replaces two N = 128-channel ones. ABCNET_NO_SWAP=1 disables."""
     if os.environ.get("ABCNET_NO_SWAP"):
         return False
-    return (pk.n_tile == 128 and pk.fold == 1 and not pk.pair and not getattr(pk, "segments", None) and out_mode == 0
-            and dst is not None and pool is None)
+    return (pk.n_tile == 128 and (pk.fold == 1 or getattr(pk, "fold_swap", False)) and not pk.pair
+            and not getattr(pk, "segments", None) and out_mode == 0 and dst is not None and pool is None)
 
 
 def pair_pack(w_taps, n_tiles, n_tile):
@@ -109,6 +119,22 @@ def pair_pack(w_taps, n_tiles, n_tile):
     src = (pos ^ r8).view(1, 1, 1, 1, 8, 1, 8, 1).expand(ntaps, n_tiles, 2, n_tile // 16, 8, cin // 64, 8, 8)
     w = torch.gather(w, 6, src)                                                     # out[..., r8, :, pos, :] = in[..., r8, :, pos ^ r8, :]
     return w.permute(1, 5, 0, 2, 3, 4, 6, 7)                                        # [nt][chunk][t][half][row group][r8][pos][e]
+
+
+def fold_rows_swap(w_taps, bias, taps, J):
+    """Toeplitz expansion along y for the operand-swap kernel: like ``fold_rows`` but GEMM row m = j * cout + co
+    (AbcConvDesc.swap_mn with row_fold). Returns (w [3 (J + 2), J * cout, cin], bias [J * cout])."""
+    ntaps, cout, cin = w_taps.shape
+    assert ntaps == 9 and J * cout == 128 and sorted(taps) == sorted((dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1))
+    by_off = {t: w_taps[i] for i, t in enumerate(taps)}
+    out = w_taps.new_zeros(3 * (J + 2), J, cout, cin)
+    for r in range(J + 2):
+        for c in range(3):
+            for j in range(J):
+                dy = r - 1 - j
+                if -1 <= dy <= 1:
+                    out[r * 3 + c, j] = by_off[(dy, c - 1)]
+    return out.view(3 * (J + 2), J * cout, cin), bias.view(1, cout).expand(J, cout).reshape(-1)
 
 
 def fold_rows(w_taps, bias, taps, J):
@@ -132,12 +158,13 @@ def fold_rows(w_taps, bias, taps, J):
 class _Packed:
     """Device-resident, kernel-ready form of one convolution: packed bf16 weights + fp32 bias + tap list."""
 
-    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1, pair=None):
+    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1, pair=None, fold_swap=False):
         # w_taps: fp32 [ntaps, cout, cin] (already BN-folded); taps: list of (dy, dx)
         # pair: CTA-pair mode (AbcConvDesc.cta_pair); None = decide from the layer size (weights too large to stay resident)
-        self.fold = fold
+        # fold_swap: row folding in the row order of the operand-swap kernel (the launch must then use swap_mn)
+        self.fold, self.fold_swap = fold, bool(fold_swap) and fold > 1
         if fold > 1:
-            w_taps, bias = fold_rows(w_taps, bias, taps, fold)
+            w_taps, bias = (fold_rows_swap if fold_swap else fold_rows)(w_taps, bias, taps, fold)
             n_tile = fold * cout
         ntaps, co, cin = w_taps.shape
         kc = min(cin, 64)
@@ -268,12 +295,15 @@ class UNet(nn.Module):
             raise RuntimeError("abcnet_b200.UNet runs on a CUDA (sm_100) device only; call .cuda() first -- there is no CPU path")
         P = {}
 
+        pooled = {"inc2.3", "down1.3", "inc3.3", "down3.3", "down4.3"}       # layers with a fused 2x2 max-pool output (see trunk())
+
         def pack3(name, conv, bn):
             w, b = _fold(conv.weight, conv.bias, bn)
             cout, cin = w.shape[:2]
             wt = torch.stack([w[:, :, ky, kx] for (_, _, ky, kx) in _TAPS3])
+            js = swap_fold_for(cin, cout, name not in pooled)
             P[name] = _Packed(wt, b, [(dy, dx) for (dy, dx, _, _) in _TAPS3], _default_n_tile(cin, cout), cout,
-                              fold=row_fold_for(cin, cout))
+                              fold=js or row_fold_for(cin, cout), fold_swap=bool(js))
 
         # first conv (1 -> 16): direct kernel, fp32 folded weights [16][9]
         c0, b0 = self.inc1.double_conv[0], self.inc1.double_conv[1]

@@ -125,8 +125,10 @@ typedef struct AbcConvDesc {
    * kernel: N = 256 layers reach 1.38 - 1.64 PFLOP/s stand-alone, N = 128 layers 1.22). The accumulator then holds
    * [channel = TMEM lane][pixel = column]; the epilogue transposes 8 channels x 8 pixels through shared memory so that the
    * bf16 P8 stores stay 16 bytes per pixel and 128 contiguous bytes per tile row. Same weight pack, same results as the
-   * unswapped kernel bit for bit (identical K order per output element). Needs out_mode 0, no pool_out, no row_fold /
-   * k_segments / cta_pair. */
+   * unswapped kernel bit for bit (identical K order per output element). Needs out_mode 0, no pool_out, no k_segments /
+   * cta_pair. May be combined with row_fold = J in {2, 4} for cout = 128 / J (the 64- and 32-channel layers): the 128 GEMM rows
+   * are then (folded row j, channel) -- weight pack rows ordered j * cout + co instead of row_fold's (16-channel block, j,
+   * channel) order, bias[j * cout + co] = bias of channel co -- and a pixel column stands for J vertically adjacent pixels. */
   int swap_mn;
 } AbcConvDesc;
 

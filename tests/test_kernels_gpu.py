@@ -43,14 +43,14 @@ def bf16_round(x):
 
 def run_conv(x, w_taps, bias, taps, n_tile, act=0, out_mode=0, pool=False, out_planes_extra=0, out_plane_off=0,
              in_plane_off=0, in_planes_extra=0, out_scale=(1, 0, 1, 0), out_hw=None, want_full=True, fold=1, pair=False,
-             swap=False):
+             swap=False, fold_swap=False):
     """x: NCHW fp32 (bf16-representable). w_taps: [ntaps, cout, cin]. Returns (out NCHW fp32 or None, pooled or None)."""
     L = _lib()
     from abcnet_b200.unet import _Packed
     dev = torch.device("cuda")
     N, cin, H, W = x.shape
     cout = w_taps.shape[1]
-    pk = _Packed(w_taps.to(dev), bias.to(dev), taps, n_tile, cout, fold=fold, pair=pair)
+    pk = _Packed(w_taps.to(dev), bias.to(dev), taps, n_tile, cout, fold=fold, pair=pair, fold_swap=fold_swap)
     n_tile = pk.n_tile
     xin = x
     if in_planes_extra or in_plane_off:
@@ -301,6 +301,28 @@ def test_igemm_operand_swap_matches_unswapped(cin, cout, N, H, W, act, taps):
     plain, _ = run_conv(x, wt, b, tp, 128, act=act, out_planes_extra=3, out_plane_off=2)
     got, _ = run_conv(x, wt, b, tp, 128, act=act, out_planes_extra=3, out_plane_off=2, swap=True)
     assert_close(got[:, 16:16 + cout], ref, 2 ** -7, 2e-3, f"swapped conv {cin}->{cout}")
+    assert (got[:, :16] == -5.0).all() and (got[:, 16 + cout:] == -5.0).all()
+    assert torch.equal(got, plain)
+
+
+@pytest.mark.parametrize("cin,cout,J,N,H,W,act", [
+    (64, 64, 2, 2, 128, 32, 1),          # down2.3 / inc3.0 class: two rows folded, weights streamed (3-block ring)
+    (32, 64, 2, 1, 72, 40, 1),           # down2.0 class, partial tiles in y (72 = 64 + 8) and x
+    (16, 32, 4, 2, 128, 24, 1),          # down1.0 class: four rows folded
+    (64, 32, 4, 1, 136, 16, 0),          # data gradient of 32 -> 64: 32 output channels, K = 64, partial tile
+    (64, 64, 2, 3, 64, 64, 2),           # LeakyReLU
+])
+def test_igemm_swap_with_row_fold_matches_plain(cin, cout, J, N, H, W, act):
+    """Operand swap combined with row folding (GEMM rows = (folded row j, channel), J * cout = 128) == the plain implicit
+    GEMM bit for bit (zero Toeplitz taps add exact zeros, same K order), plane offsets honoured."""
+    x = bf16_round(rnd(cin + H, (N, cin, H, W)))
+    w = bf16_round(rnd(cout + W, (cout, cin, 3, 3)) * (2.0 / (cin * 9) ** 0.5))
+    b = rnd(5, (cout,))
+    wt = torch.stack([w[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
+    plain, _ = run_conv(x, wt, b, TAPS3, cout, act=act, out_planes_extra=3, out_plane_off=2)
+    got, _ = run_conv(x, wt, b, TAPS3, cout, act=act, out_planes_extra=3, out_plane_off=2, fold=J, fold_swap=True, swap=True)
+    ref = ref_conv3(x, w, b, act)
+    assert_close(got[:, 16:16 + cout], ref, 2 ** -7, 2e-3, f"swap + fold conv3x3 {cin}->{cout} J={J}")
     assert (got[:, :16] == -5.0).all() and (got[:, 16 + cout:] == -5.0).all()
     assert torch.equal(got, plain)
 

@@ -4,7 +4,7 @@ layout variant the training pass uses (plain 3x3, row-folded, zero-padded 1x1, t
 import torch
 
 from abcnet_b200.train import TAPS3, Packed, phase_taps
-from abcnet_b200.unet import row_fold_for
+from abcnet_b200.unet import row_fold_for, swap_fold_for
 
 
 def _codes(t, pid):
@@ -31,13 +31,19 @@ def _check(make, params):
 
 def test_plain_and_folded_3x3():
     g = torch.Generator().manual_seed(0)
-    for cin, cout in ((16, 16), (32, 32), (16, 32), (64, 128), (128, 128)):
+    for cin, cout in ((16, 16), (32, 32), (16, 32), (32, 64), (64, 64), (64, 128), (128, 128)):
         w, b = torch.randn(cout, cin, 3, 3, generator=g), torch.randn(cout, generator=g)
 
         def make(ps, cin=cin, cout=cout):
             wt, bias = ps
             return Packed(torch.stack([wt[:, :, dy + 1, dx + 1] for dy, dx in TAPS3]), bias, TAPS3, fold=row_fold_for(cin, cout))
         _check(make, [w, b])
+
+        def make_s(ps, cin=cin, cout=cout):                       # row folding in the operand-swap order (32 / 64 channels)
+            wt, bias = ps
+            js = swap_fold_for(cin, cout)
+            return Packed(torch.stack([wt[:, :, dy + 1, dx + 1] for dy, dx in TAPS3]), bias, TAPS3, fold=js or 1, fold_swap=bool(js))
+        _check(make_s, [w, b])
 
         def make_d(ps, cin=cin, cout=cout):                       # data gradient: transposed, flipped taps, zero bias
             wt = ps[0]
