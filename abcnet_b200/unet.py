@@ -96,7 +96,10 @@ def swap_fold_for(cin, cout, plain_output=True):
     Returns J (0 = not applicable). ABCNET_NO_SWAP / ABCNET_NO_FOLD disable."""
     if os.environ.get("ABCNET_NO_SWAP") or os.environ.get("ABCNET_NO_FOLD") or os.environ.get("ABCNET_NO_SWAPFOLD") or not plain_output:
         return 0
-    return {64: 2, 32: 4}.get(cout, 0)
+    J = {64: 2, 32: 4}.get(cout, 0)
+    if J == 4 and cin > 32:          # a 128-row halo tile of 64 channels (166 KB per pipeline stage) does not fit twice in shared memory
+        return 0
+    return J
 
 
 def use_swap(pk, out_mode, dst, pool):

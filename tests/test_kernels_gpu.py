@@ -309,7 +309,7 @@ def test_igemm_operand_swap_matches_unswapped(cin, cout, N, H, W, act, taps):
     (64, 64, 2, 2, 128, 32, 1),          # down2.3 / inc3.0 class: two rows folded, weights streamed (3-block ring)
     (32, 64, 2, 1, 72, 40, 1),           # down2.0 class, partial tiles in y (72 = 64 + 8) and x
     (16, 32, 4, 2, 128, 24, 1),          # down1.0 class: four rows folded
-    (64, 32, 4, 1, 136, 16, 0),          # data gradient of 32 -> 64: 32 output channels, K = 64, partial tile
+    (32, 32, 4, 1, 136, 16, 0),          # 32 -> 32 (train-mode down1.3, data gradients), partial tile, no activation
     (64, 64, 2, 3, 64, 64, 2),           # LeakyReLU
 ])
 def test_igemm_swap_with_row_fold_matches_plain(cin, cout, J, N, H, W, act):
