@@ -117,6 +117,14 @@ def test_trained_network_end_to_end_identity():
         assert err[i] <= 0.08 * scale[i] + 0.05, f"map {i}: max abs err {err[i]} (scale {scale[i]})"
         assert rel[i] <= 0.05, f"map {i}: rel L2 {rel[i]}"
 
+    # the opt-in sparse-heads path on the same trained network and images: identical records to the dense product path
+    pipe = abcnet_b200.SparseHeadsPipeline(model, N_IMG, peak_cap=256, bond_cap=8192)
+    sparse = pipe.fetch(pipe.launch(x, thr=THR))
+    for j, ((da, db, dn), (sa, sb, sn)) in enumerate(zip(recs, sparse)):
+        assert dn == sn and np.array_equal(da, sa) and np.array_equal(db, sb), f"image {j}: sparse-heads records differ"
+    assert pipe.molblocks(N_IMG) == dec.molblocks(N_IMG)
+    del pipe
+
     report = dict(images=N_IMG, train_steps=STEPS, loss_curve=curve, logit_max_abs_err=err, logit_scale=scale, logit_rel_l2=rel,
                   differences=[], identical_images=0, molblocks_compared=0, labelled_atoms=0, found_atoms=0, ref_atom_peaks=0,
                   ref_bond_records=0)
