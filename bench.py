@@ -156,13 +156,13 @@ class ClockSampler:
 
 
 def make_weights(seed=0):
-    from oracle import unet_ref
-    return unet_ref.make_state_dict(seed=seed, variant="W1")
+    import synthdata                       # deterministic synthetic weights / inputs: not the oracle
+    return synthdata.make_state_dict(seed=seed, variant="W1")
 
 
 def make_images(seed, n, H=512, W=512):
-    from oracle import synth
-    return torch.from_numpy(synth.binary_images(seed, n, H, W, 0.05))
+    import synthdata
+    return torch.from_numpy(synthdata.binary_images(seed, n, H, W, 0.05))
 
 
 # ----------------------------------------------------------------------------------------- CPU arm (oracle port)
@@ -242,7 +242,7 @@ def run_train(args, rank, world, dev):
 
     import abcnet_b200
     from abcnet_b200.ddp import GradBuckets
-    from oracle import synth
+    import synthdata as synth
     B = args.train_batch
     model = abcnet_b200.UNet(1, HEADS).to(dev)
     model.load_state_dict(make_weights())

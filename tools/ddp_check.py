@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import abcnet_b200  # noqa: E402
 from abcnet_b200.ddp import GradBuckets  # noqa: E402
-from oracle import synth, unet_ref  # noqa: E402  (synthetic weights / images / targets only)
+import synthdata as synth  # noqa: E402  (deterministic synthetic weights / images / targets; the oracle is not used here)
+import synthdata as unet_ref  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)

@@ -10,7 +10,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import abcnet_b200  # noqa: E402
-from oracle import synth, unet_ref  # noqa: E402  (weights / images only; tooling, not product)
+import synthdata as synth  # noqa: E402  (deterministic synthetic weights / images / targets; the oracle is not used here)
+import synthdata as unet_ref  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 model = abcnet_b200.UNet(1, list(unet_ref.V2_HEADS)).cuda().eval()

@@ -12,7 +12,8 @@ from torch.profiler import ProfilerActivity, profile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import abcnet_b200  # noqa: E402
-from oracle import synth, unet_ref  # noqa: E402  (synthetic weights / images / targets only)
+import synthdata as synth  # noqa: E402  (deterministic synthetic weights / images / targets; the oracle is not used here)
+import synthdata as unet_ref  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 512
