@@ -52,6 +52,21 @@ def test_sparse_heads_records_equal_dense_path(B, H, W, q, mode):
         assert wn == gn and np.array_equal(wa, ga) and np.array_equal(wb, gb)
 
 
+def test_sparse_heads_probability_mode_equals_dense_path():
+    """The training-metric peak rule (train.py:145-151: NMS / threshold on the clamped sigmoid) through the sparse path."""
+    import abcnet_b200
+    m = _model(23)
+    x = torch.from_numpy(synth.binary_images(8, 2, 256, 256, 0.05)).cuda()
+    _calibrate(m, x, 0.99)
+    dense = abcnet_b200.PeakDecoder(2, atom_cap=1024, bond_cap=8192)
+    want = dense(m.infer(x, layout="p8f"), thr=0.25, apply_sigmoid=True, thr_omega=-1.0)
+    pipe = abcnet_b200.SparseHeadsPipeline(m, 2, peak_cap=1024, bond_cap=8192)
+    got = pipe.fetch(pipe.launch(x, thr=0.25, apply_sigmoid=True, thr_omega=-1.0))
+    assert sum(len(a) for a, _, _ in want) > 10
+    for (wa, wb, wn), (ga, gb, gn) in zip(want, got):
+        assert wn == gn and np.array_equal(wa, ga) and np.array_equal(wb, gb)
+
+
 def test_sparse_heads_capacity_overflow_raises():
     import abcnet_b200
     m = _model(22)
