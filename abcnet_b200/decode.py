@@ -95,6 +95,16 @@ class PeakDecoder:
         self._done.synchronize()
         return self._parse(N)
 
+    def wait(self, N):
+        """Wait for the copy enqueued by ``fetch_async`` and check the capacities, without building per-image arrays (for
+        callers that go straight to ``molblocks``). Returns the [N, 4] counts."""
+        self._done.synchronize()
+        counts = self.h_counts[:N].numpy()
+        if (counts[:, 0] > self.atom_cap).any() or (counts[:, 1] > self.bond_cap).any():
+            raise RuntimeError(f"decode capacity exceeded: max atoms {counts[:, 0].max()} (cap {self.atom_cap}), "
+                               f"max bond records {counts[:, 1].max()} (cap {self.bond_cap}); enlarge the capacities")
+        return counts
+
     def fetch(self, N):
         """One async D2H of the compact records + a single stream sync; returns per-image numpy record arrays."""
         self.h_counts[:N].copy_(self.d_counts[:N], non_blocking=True)

@@ -142,6 +142,12 @@ class SparseHeadsPipeline:
             raise RuntimeError("sparse heads: bond-centre peaks exceed peak_cap; use a larger peak_cap or the dense path")
         return recs
 
+    def wait(self, N):
+        counts = self.dec.wait(N)
+        if (counts[:, 2] > self.cap).any():
+            raise RuntimeError("sparse heads: bond-centre peaks exceed peak_cap; use a larger peak_cap or the dense path")
+        return counts
+
     def molblocks(self, N, n_threads=0):
         return self.dec.molblocks(N, n_threads)
 

@@ -397,13 +397,15 @@ def run_ours(args, rank, world, local_rank):
                 n = dec2[i % 2].launch(obufs[i % 2])
             sink[i % 2].fetch_async(n)
             if i > 0:
-                recs = sink[(i - 1) % 2].collect(n)
-                if mol:
+                if mol:                                  # records stay in the pinned buffers; the assembler reads them there
+                    sink[(i - 1) % 2].wait(n)
                     sink[(i - 1) % 2].molblocks(n)
-        recs = sink[(steps - 1) % 2].collect(B)
+                else:
+                    recs = sink[(i - 1) % 2].collect(n)
         if mol:
+            sink[(steps - 1) % 2].wait(B)
             return sink[(steps - 1) % 2].molblocks(B)
-        return recs
+        return sink[(steps - 1) % 2].collect(B)
 
     run_e2e(2)
     barrier()

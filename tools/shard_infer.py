@@ -76,7 +76,7 @@ def main():
     def finish(i):
         nonlocal n_mol
         a, b = ranges[i]
-        sinks[i % 2].collect(B)
+        sinks[i % 2].wait(B)
         texts = sinks[i % 2].molblocks(B)[:b - a]
         h = hashlib.blake2b(digest_size=32)
         for t in texts:
@@ -96,7 +96,7 @@ def main():
 
     for i in range(min(2, len(ranges))):               # warm-up (buffers, weight packing)
         enqueue(i)
-        sinks[i % 2].collect(B)
+        sinks[i % 2].wait(B)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
