@@ -70,6 +70,15 @@ def test_no_cpu_fallback():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+    # ... nor do the tools; bench.py only inside its CPU-baseline / reference-arm functions
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
+    gpu_arm = bench.index("def run_train(")
+    assert uses and all(u < gpu_arm for u in uses), "bench.py: the oracle may only appear in cpu_path / calibrate_offsets_cpu"
 
 
 def test_state_dict_matches_reference_inventory():
