@@ -374,6 +374,8 @@ def run_ours(args, rank, world, local_rank):
     dec2 = [dec, abcnet_b200.PeakDecoder(B, atom_cap=args.atom_cap, bond_cap=args.bond_cap, device=dev)]
     obufs = [out_bufs, None]
 
+    mol_threads = max(1, (os.cpu_count() or 1) // world)          # host assembler threads per rank (the ranks share the host cores)
+
     def run_e2e(steps, mol=False, pipes=None):
         """Every step: H2D of its own images (side stream, double-buffered), forward, decode, D2H of the records; the host
         collects the records of step i - 1 (waiting on that step's event only) after it has enqueued step i.
@@ -399,12 +401,12 @@ def run_ours(args, rank, world, local_rank):
             if i > 0:
                 if mol:                                  # records stay in the pinned buffers; the assembler reads them there
                     sink[(i - 1) % 2].wait(n)
-                    sink[(i - 1) % 2].molblocks(n)
+                    sink[(i - 1) % 2].molblocks(n, mol_threads)
                 else:
                     recs = sink[(i - 1) % 2].collect(n)
         if mol:
             sink[(steps - 1) % 2].wait(B)
-            return sink[(steps - 1) % 2].molblocks(B)
+            return sink[(steps - 1) % 2].molblocks(B, mol_threads)
         return sink[(steps - 1) % 2].collect(B)
 
     run_e2e(2)

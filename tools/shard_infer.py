@@ -77,7 +77,7 @@ def main():
         nonlocal n_mol
         a, b = ranges[i]
         sinks[i % 2].wait(B)
-        texts = sinks[i % 2].molblocks(B)[:b - a]
+        texts = sinks[i % 2].molblocks(B, max(1, (os.cpu_count() or 1) // world))[:b - a]
         h = hashlib.blake2b(digest_size=32)
         for t in texts:
             h.update(b"\0" if t is None else t.encode())
