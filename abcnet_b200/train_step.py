@@ -12,7 +12,7 @@ The step is enqueued without any host synchronisation and -- by default -- captu
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Sequence
 
 import torch
 
