@@ -13,28 +13,48 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int device_check() {
+static std::atomic<int> g_dev_ok[kMaxDevices];      // zero-initialised; 1 = sm_100 confirmed
+static std::atomic<int> g_dev_sms[kMaxDevices];
+
+int current_device() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {
     cudaGetLastError();
+    return -1;
+  }
+  return dev;
+}
+
+int device_check() {
+  const int dev = current_device();
+  if (dev < 0) {
     set_error("no CUDA device available (abcnet_b200 has no CPU fallback)");
     return ABC_ERR_NO_DEVICE;
   }
+  if (dev < kMaxDevices && g_dev_ok[dev].load(std::memory_order_relaxed)) return ABC_OK;
   int major = 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) {
     cudaGetLastError();
     set_error("device %d has compute capability major %d; the kernels are built for sm_100a only", dev, major);
     return ABC_ERR_NO_DEVICE;
   }
+  if (dev < kMaxDevices) g_dev_ok[dev].store(1, std::memory_order_relaxed);
   return ABC_OK;
 }
 
 int sm_count() {
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+  const int dev = current_device();
+  if (dev < 0) return 0;
+  if (dev < kMaxDevices) {
+    const int c = g_dev_sms[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
+  if (dev < kMaxDevices) g_dev_sms[dev].store(n, std::memory_order_relaxed);
   return n;
 }
 

@@ -688,6 +688,23 @@ static EncodeTiledFn get_encode_fn() {
 
 static int conv_kc(int cin) { return cin < 64 ? cin : 64; }
 
+// Tuning / experiment knobs from the environment, read ONCE per process (thread-safe static initialisation; the launch
+// path itself never calls getenv).
+struct ConvEnv {
+  int pair_dbg, mt256, mt, nacc;
+  ConvEnv() {
+    auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    pair_dbg = num("ABCNET_PAIR_DBG", 0);
+    mt256 = num("ABCNET_MT256", 0);
+    mt = num("ABCNET_MT", 0);
+    nacc = num("ABCNET_NACC", 0);
+  }
+};
+static const ConvEnv& conv_env() {
+  static const ConvEnv e;
+  return e;
+}
+
 }  // namespace abc
 
 extern "C" int64_t abc_conv_wpack_bytes(int cin, int cout, int ntaps, int n_tile) {
@@ -758,7 +775,8 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.N = d->N; p.H = d->H; p.W = d->W;
   p.tiles_x = (d->W + 7) / 8;
   p.fold = fold;
-  p.dbg = getenv("ABCNET_PAIR_DBG") ? atoi(getenv("ABCNET_PAIR_DBG")) : 0;
+  const ConvEnv& env = conv_env();
+  p.dbg = env.pair_dbg;
   p.tile_rows = swap ? 32 * fold : 16 * fold;
   p.tiles_y = (d->H + p.tile_rows - 1) / p.tile_rows;
   p.in_plane_off = d->in_plane_off;
@@ -808,10 +826,10 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   // n_tile = 256: with one tile per stage every CTA streams the layer's full weight set per 128 pixels (64 B/clk/SM at
   // the MMA rate, above the ~43 B/clk/SM the L2 delivers); two tiles per weight block halve that at the price of a
   // single accumulator stage (512 TMEM columns): the epilogue no longer overlaps the next group's MMAs.
-  if (d->n_tile == 256 && getenv("ABCNET_MT256")) mt_max = atoi(getenv("ABCNET_MT256")) >= 2 ? 2 : 1;
+  if (d->n_tile == 256 && env.mt256 > 0) mt_max = env.mt256 >= 2 ? 2 : 1;
   if (mt_max > 8) mt_max = 8;
   if (mt_max > p.tiles_x) mt_max = p.tiles_x;
-  if (const char* e = getenv("ABCNET_MT")) { int v = atoi(e); if (v >= 1 && v < mt_max) mt_max = v; }
+  if (env.mt >= 1 && env.mt < mt_max) mt_max = env.mt;
   uint32_t smem_bytes = 0;
   p.mt = 0;
   for (int mt = mt_max; mt >= 1 && !p.mt; --mt) {          // prefer resident weights
@@ -843,7 +861,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.acc_cols = swap ? 256 : p.mt * d->n_tile;
   p.nacc = kTmemCols / p.acc_cols;
   if (p.nacc > kMaxAcc) p.nacc = kMaxAcc;
-  if (const char* e = getenv("ABCNET_NACC")) { int v = atoi(e); if (v >= 2 && v < p.nacc) p.nacc = v; }
+  if (env.nacc >= 2 && env.nacc < p.nacc) p.nacc = env.nacc;
   p.groups_x = (p.tiles_x + p.mt - 1) / p.mt;
   const int64_t groups = static_cast<int64_t>(d->N) * p.groups_x * p.tiles_y;
   ABC_REQUIRE(groups < (1ll << 31), "abc_conv_igemm: too many tiles");
@@ -890,16 +908,15 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
                                  {nullptr, conv_igemm_kernel<1, true, false, true>, conv_igemm_kernel<2, true, false, true>,
                                   conv_igemm_kernel<3, true, false, true>, conv_igemm_kernel<4, true, false, true>}};
   KernelFn pair_kernel = conv_igemm_kernel<4, false, true>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  ABC_CUDA(attr_once.run([&]() -> cudaError_t {
     for (int r = 0; r < 2; ++r)
       for (int k = 1; k <= 4; ++k) {
-        ABC_CUDA(cudaFuncSetAttribute(kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        ABC_CUDA(cudaFuncSetAttribute(swap_kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+        if (cudaError_t e = cudaFuncSetAttribute(kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) return e;
+        if (cudaError_t e = cudaFuncSetAttribute(swap_kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) return e;
       }
-    ABC_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    attr_set = true;
-  }
+    return cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  }));
   const int ksteps = p.kp / 2;
   ABC_REQUIRE(ksteps >= 1 && ksteps <= 4, "abc_conv_igemm: internal: ksteps=%d", ksteps);
   const int n_tiles = (d->cout + d->n_tile - 1) / d->n_tile;

@@ -531,11 +531,8 @@ extern "C" int abc_heads_fused(const AbcHeadsFusedDesc* d, void* stream_) {
     set_error("abc_heads_fused: cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(cr));
     return ABC_ERR_CUDA;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ABC_CUDA(cudaFuncSetAttribute(heads_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHfSmem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  ABC_CUDA(attr_once.run([] { return cudaFuncSetAttribute(heads_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHfSmem); }));
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   int gx = sms / pairs;

@@ -293,11 +293,8 @@ extern "C" int abc_conv_wgrad(const AbcWgradDesc* d, void* stream) {
   CUtensorMap map_dz, map_in;
   if (int rc = make_map(&map_dz, d->dz, d->W, d->H, d->dz_planes, d->N, 8, 16, p.m_planes)) return rc;
   if (int rc = make_map(&map_in, d->in, d->W, d->H, d->in_planes, d->N, p.fold ? 8 : cols, p.fold ? 16 : rows, p.n_tile / 8)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ABC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  ABC_CUDA(attr_once.run([] { return cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); }));
   const int gy = p.n_co_tiles * p.n_ci_tiles * p.tap_groups;
   int sms = sm_count();
   if (sms <= 0) sms = 148;

@@ -21,6 +21,7 @@ class GradBuckets:
         if not params:
             raise ValueError("no trainable parameters")
         self.group = group
+        self.comm_enabled = True                         # False: buckets only (measurement of the step without the exchange)
         self.params = list(reversed(params))             # backward produces gradients in reverse registration order
         dev = self.params[0].device
         self.buckets: List[torch.Tensor] = []
@@ -65,7 +66,7 @@ class GradBuckets:
             self._launch(b)
 
     def _launch(self, b: int):
-        if self.world() == 1:
+        if self.world() == 1 or not self.comm_enabled:
             return
         flat = self.buckets[b]
         if self.comm_stream is not None:

@@ -61,6 +61,45 @@ class FusedAdam(torch.optim.Optimizer):
                      table([p.numel() for p in params]), torch.tensor(chunks, dtype=torch.int32, device=dev).contiguous())
         self._n_chunks = len(chunks)
 
+    @torch.no_grad()
+    def reset_state(self, lr=None):
+        """Zero the moments and the step counter IN PLACE (graph-safe: a captured TrainStep keeps its pointers) and
+        optionally set a new learning rate. This is what the reference's LR drop does: ``train.py:84-85`` re-creates
+        ``optim.Adam`` with lr 2.5e-5 at epoch ``epoch_nums / 3``, which discards the moments and restarts the bias correction."""
+        for st in self.state.values():
+            for k in ("exp_avg", "exp_avg_sq"):
+                if k in st:
+                    st[k].zero_()
+        if self._step is not None:
+            self._step.zero_()
+        if lr is not None:
+            g = self.param_groups[0]
+            if torch.is_tensor(g["lr"]):
+                g["lr"].fill_(float(lr))
+            else:
+                g["lr"] = float(lr)
+            self.sync_hyperparams()
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """torch's loader replaces the state tensors; a captured graph (and the device pointer tables) still reference the
+        old ones. The loaded values are therefore copied INTO the existing buffers, which stay the optimiser's state."""
+        old = {p: dict(st) for p, st in self.state.items()}
+        super().load_state_dict(state_dict)
+        for p, st in self.state.items():
+            prev = old.get(p)
+            if not prev:
+                continue
+            for k in ("exp_avg", "exp_avg_sq"):
+                if k in prev and k in st and st[k] is not prev[k]:
+                    prev[k].copy_(st[k])
+                    st[k] = prev[k]
+            new_step = st.get("step")
+            if self._step is not None and new_step is not None and new_step is not self._step:
+                self._step.copy_(torch.as_tensor(new_step, dtype=torch.float32).reshape(()))
+                st["step"] = self._step
+        self._hyper_host = None                                       # lr / betas may have changed: re-push before the next step
+
     def sync_hyperparams(self):
         """Push lr / betas / eps / weight_decay of ``param_groups[0]`` to the device if they changed (call before a CUDA-graph
         replay after editing ``param_groups``; ``step()`` does it itself)."""

@@ -72,11 +72,11 @@ class SparseHeadsPipeline:
             raise ValueError(f"SparseHeadsPipeline was built for batches of {self.batch} images, got {B}")
         st = _lib.current_stream_ptr()
         P_ = m._packed
-        if self._centre_pack is None or self._centre_key != m._packed_key:
+        if self._centre_pack is None or self._centre_key != m._pack_gen:
             wt, bias, _ = m._heads_w1                                    # [9, 1024, 128] BN-folded conv1 of all heads
             sel = torch.cat([torch.arange(0, 128), torch.arange(512, 640)]).to(wt.device)       # heads 0 and 4
             self._centre_pack = _Packed(wt[:, sel].contiguous(), bias[sel].contiguous(), [(dy, dx) for (dy, dx, _, _) in _TAPS3], 256, 256)
-            self._centre_key = m._packed_key
+            self._centre_key = m._pack_gen
         # dense centre heads
         hid2 = self._buf("hid2", (B, 32, H4, W4, 8), torch.bfloat16)
         m._conv(self._centre_pack, k2, 0, hid2, act=2, stream=st)

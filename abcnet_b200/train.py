@@ -21,7 +21,19 @@ from ._lib import AbcBnActBwdDesc, AbcBnActDesc, AbcConvDesc, AbcWgradDesc, chec
 from .unet import fold_rows, fold_rows_swap, pair_pack, row_fold_for, swap_fold_for, use_cta_pair, use_swap
 
 TAPS3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
-_seed_counter = itertools.count(0x5EED)
+_seed_counter = itertools.count(0)
+
+
+def _initial_dropout_seed():
+    """First value of an engine's dropout counter: torch's global seed (so ``torch.manual_seed`` controls the masks, as it
+    does for nn.Dropout in the reference), mixed with the data-parallel rank (every replica must draw its own masks) and
+    an engine ordinal."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+    z = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (rank + 1) + 0xBF58476D1CE4E5B9 * next(_seed_counter)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return (z ^ (z >> 31)) & 0x3FFFFFFFFFFFFFFF                       # positive int64
 
 
 timing = None   # set to a list to collect (label, start event, end event) around every conv / wgrad launch (tools only)
@@ -409,11 +421,12 @@ class TrainEngine:
         x = x.contiguous().view(torch.uint8) if u8 else x.contiguous().float()
         B, _, H, W = x.shape
         plan = self._plan(H, W)
+        m.invalidate_packed()                                        # the eval-mode weight cache is stale after any training pass
         self._sync_arena()
         # dropout stream: a device-resident counter, advanced by a device op so that CUDA-graph replays draw new masks
         seed_t = self.bufs.get("seed")
         if seed_t is None:
-            seed_t = self.bufs["seed"] = torch.full((1,), next(_seed_counter), dtype=torch.int64, device=x.device)
+            seed_t = self.bufs["seed"] = torch.full((1,), _initial_dropout_seed(), dtype=torch.int64, device=x.device)
         seed_t.add_(0x5DEECE66D)
         sv = self.saved = dict(x=x, u8=u8, B=B, H=H, W=W, plan=plan, units={}, seed=seed_t)
         for u in plan:

@@ -78,14 +78,20 @@ class TrainStep:
     def __call__(self, x, targets: Sequence[torch.Tensor]):
         if not self.model.training:
             raise RuntimeError("TrainStep: call model.train() first")
+        self.model.invalidate_packed()        # a graph replay updates weights / running statistics behind torch's version counters
         if not self.use_graph:
             self._enqueue(x, targets, True)
-            return self.loss
+            return self.loss.clone()
+        if self.graph is not None and (x.shape != self._x.shape or x.dtype != self._x.dtype):
+            # e.g. the last, partial batch of a DataLoader without drop_last (the reference's loaders, train.py:43-46): run
+            # it eagerly through the same kernels; the graph of the regular batch shape stays valid (its buffers are keyed
+            # by shape inside the engine and are re-created on the next regular call only if the eager pass replaced them)
+            self._enqueue(x, targets, True)
+            self.graph = None                              # engine buffers were re-shaped: re-capture on the next regular batch
+            return self.loss.clone()
         if self.graph is None:
             self._capture(x, targets)
         else:
-            if x.shape != self._x.shape or x.dtype != self._x.dtype:
-                raise ValueError("TrainStep (graph mode): the batch shape / dtype is fixed at the first call")
             if x.data_ptr() != self._x.data_ptr():
                 self._x.copy_(x, non_blocking=True)
             for dst, src in zip(self._tg, targets):
@@ -96,7 +102,7 @@ class TrainStep:
         self.graph.replay()
         if self.opt is not None and not self._opt_in_graph:
             self.opt.step()
-        return self.loss
+        return self.loss.clone()                           # a fresh tensor per step: callers may collect the returned losses
 
     def _capture(self, x, targets):
         # static input buffers; the first batch is also used for the warm-up iterations (parameters are restored after)

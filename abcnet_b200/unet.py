@@ -269,6 +269,7 @@ class UNet(nn.Module):
         self.out_modules = nn.ModuleList([_head(128, h) for h in self.heads])
         self._packed = None
         self._packed_key = None
+        self._pack_gen = 0
         self._bufs = {}
         self.timing = None        # set to a list to collect (layer name, start event, end event) per launch group
         self.dropout_p = 0.2      # nn.Dropout(0.2) of OutConv (unet.py:69); train mode only
@@ -284,6 +285,18 @@ class UNet(nn.Module):
 
     def _param_key(self):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def invalidate_packed(self):
+        """Drop the eval-mode cache of BN-folded, packed weights. ``_param_key`` only sees updates that bump a tensor's
+        ``_version``; a CUDA-graph replay (``TrainStep`` + ``FusedAdam``) rewrites weights and BatchNorm running statistics
+        through raw pointers without doing so, hence the training entry points and every ``train()`` / ``eval()`` mode
+        change call this explicitly (train.py:89,218 alternates the two every epoch)."""
+        self._packed = None
+        self._packed_key = None
+
+    def train(self, mode=True):
+        self.invalidate_packed()
+        return super().train(mode)
 
     # ------------------------------------------------------------------ weight preparation (cold path)
     def _dc_layers(self, holder):
@@ -356,6 +369,7 @@ class UNet(nn.Module):
         P["heads.fused"] = self._pack_fused_heads(dev)
         self._packed = P
         self._packed_key = self._param_key()
+        self._pack_gen += 1                  # consumers that derive their own packs (SparseHeadsPipeline) key on this
         return self
 
     def _pack_fused_heads(self, dev):

@@ -36,9 +36,9 @@ METRIC = "images_per_sec_unet_fwd_decode"
 UNIT = "images/s"
 FLOPS_PER_IMAGE = 93.98e9          # SURVEY.md section 6 (forward, v2 heads, 512x512)
 HEADS_CONV1_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 1024 * 1152      # fused 8-head 3x3 conv: M=16384, N=1024, K=1152
-# dram__bytes_read.sum + dram__bytes_write.sum of that launch at batch 256, from the committed `ncu --set full` capture
-# profiles/r01_heads_conv1_b256_v16.summary.txt (2.70 GB read + 8.54 GB written; algorithmic: 1.07 GB trunk in + 8.59 GB hidden out)
-HEADS_CONV1_DRAM_BYTES_B256 = 2.703330e9 + 8.539355e9
+# dram__bytes_read.sum + dram__bytes_write.sum of that launch at batch 256 are READ from the newest committed `ncu --set full`
+# summary of the kernel under profiles/ (see ncu_traffic); algorithmic: 1.07 GB trunk in + 8.59 GB hidden out
+HEADS_CONV1_SUMMARY_GLOB = "r*_heads_conv1_b256*.summary.txt"
 HEADS_CONV2_FLOPS_PER_IMAGE = 2.0 * 128 * 128 * 128 * 501        # the eight 1x1 convs, algorithmic (unpadded) channels
 HEADS_FUSED_DRAM_BYTES_B256 = None                                # filled from the ncu capture of heads_fused_kernel
 
@@ -94,6 +94,29 @@ def layer_class_report(layers_ms, B, pk, decode_bytes=None):
             ach, peak, unit = work / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
         out[name] = {"ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
     return out
+
+
+def ncu_traffic(pattern):
+    """(bytes, file) = dram__bytes_read.sum + dram__bytes_write.sum of the FIRST kernel in the newest profiles/ summary matching
+    ``pattern`` (written by tools/ncu_summary.py from an `ncu --set full` capture); (None, None) when there is none."""
+    import glob
+    import re
+    files = glob.glob(os.path.join(ROOT, "profiles", pattern))
+    if not files:
+        return None, None
+
+    def version(f):                                      # r02_..._v12 sorts after r01_..._v25 and after r02_..._v3
+        m = re.search(r"r(\d+)_.*?(?:_v(\d+))?\.summary\.txt$", os.path.basename(f))
+        return (int(m.group(1)), int(m.group(2) or 0)) if m else (0, 0)
+    f = max(files, key=version)
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, set()
+    for line in open(f):
+        parts = line.split()
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[0] not in seen:
+            seen.add(parts[0])
+            total += float(parts[1]) * unit.get(parts[2], 1.0)
+    return (total, os.path.relpath(f, ROOT)) if len(seen) == 2 else (None, None)
 
 
 def peaks():
@@ -207,23 +230,35 @@ def run_reference(args, rank, world):
         return
     sd = make_weights()
     calib = calibrate_offsets_cpu(sd)
-    n = 8                                        # BASELINE.json configs[0]: batch of 8 images
-    for _ in range(min(args.warmup, 1)):
-        cpu_path(sd, make_images(100, n), calib)
+    n = 8                                        # BASELINE.json configs[0]: batch of 8 images = one bounded sample of the 256-image step
     torch.set_num_threads(os.cpu_count() or 1)
     imgs = make_images(100, n)
-    t0 = time.perf_counter()
-    steps = max(1, min(args.steps, 5))
-    for _ in range(steps):
+    # --steps / --warmup are honoured as given (about 1 s per 8-image step on 16 cores); only a wall-clock guard of ~4 minutes
+    # can end the run early, and the line then says how many steps were timed
+    t_guard = time.perf_counter()
+    warm = 0
+    for _ in range(max(args.warmup, 0)):
         cpu_path(sd, imgs, calib)
+        warm += 1
+        if time.perf_counter() - t_guard > 60:
+            break
+    t0 = time.perf_counter()
+    steps = 0
+    for _ in range(max(args.steps, 1)):
+        cpu_path(sd, imgs, calib)
+        steps += 1
+        if time.perf_counter() - t0 > 180:
+            break
     dt = time.perf_counter() - t0
     v = n * steps / dt
     cores = torch.get_num_threads()
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-           "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "ABC-Net v2 U-Net fwd + heat-map decode, 1x512x512 binary images, CPU fp32",
-                      "sample": f"{n} images per step (bounded sample of the 256-image batch)", "images_per_step": n},
+                      "sample": f"{n} images per step (bounded sample of the GPU arm's 256-image batch: the rate is per image, "
+                                "the CPU path has no batch-size dependence beyond thread occupancy)", "images_per_step": n,
+                      "steps_requested": args.steps, "warmup_requested": args.warmup},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{steps} x {n} images, oracle port of src/unet.py + img2smiles.py:62-193"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -275,13 +310,172 @@ def run_train(args, rank, world, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     v = world * B * args.steps / (ms * 1e-3)
-    return {"metric": "images_per_sec_train_step", "value": v, "unit": UNIT, "ms_per_step": ms / args.steps,
+    ddp = ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms / args.steps) if world > 1 else None
+    return {"metric": "images_per_sec_train_step", "value": v, "unit": UNIT, "ms_per_step": ms / args.steps, "ddp": ddp,
             "batch_per_gpu": B, "scaling": "weak", "dtype": "bf16 activations / fp32 master weights, accumulators and gradients",
             "workload": "forward (train-mode BN, dropout) + 8 losses + backward + gradient all-reduce + Adam, 1x512x512 images, "
                         "dense targets resident in HBM (BASELINE configs[3]/[4])",
             "whole_step_tflops": TRAIN_FLOPS_PER_IMAGE * v / 1e12, "loss": float(loss.item()),
             "replay": "one CUDA graph per iteration (kernels counted at capture: %d)" % step.launches_per_step,
             "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
+def ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms_on):
+    """Evidence for the data-parallel exchange (multi_gpu_train2.py:89), measured inside the SCALE run itself:
+      * known_gradients_mean_exact: every rank fills ALL its gradient buckets with rank-dependent known values through the same
+        grad_ready() path the backward uses; the result must be the exact mean over ranks for every parameter element
+        (DistributedDataParallel's averaging) -- exact because the values are small integers;
+      * real step: bucketed + overlapped all-reduce vs ONE plain NCCL all-reduce of the locally computed gradients
+        (relative error), and all replicas bit-identical afterwards;
+      * ms_per_step with the exchange disabled (same graph otherwise) vs enabled = exposed communication time;
+      * the all-reduce alone: time and bus bandwidth 2 (N - 1) / N * bytes / t for the 42.8 MB of gradients in their buckets."""
+    import torch.distributed as dist
+
+    import abcnet_b200
+    rank = dist.get_rank()
+    out = {}
+    # ---- known gradients
+    params = buckets.params
+    buckets.zero()
+    torch.cuda.synchronize()
+    for i, p in enumerate(params):
+        p.grad.copy_(((torch.arange(p.numel(), device=dev) % 7) + 1).view_as(p).float() * (rank + 1) * ((i % 3) + 1))
+        buckets.grad_ready(p)
+    buckets.finish()
+    torch.cuda.synchronize()
+    mean_factor = (world + 1) / 2.0
+    ok = True
+    for i, p in enumerate(params):
+        want = ((torch.arange(p.numel(), device=dev) % 7) + 1).view_as(p).float() * mean_factor * ((i % 3) + 1)
+        ok = ok and bool(torch.equal(p.grad, want))
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out["known_gradients_mean_exact"] = bool(t.item() == 1.0)
+    # ---- real gradients: bucketed / overlapped vs one plain all-reduce of the local gradients
+    step_noopt = abcnet_b200.TrainStep(model, None, class_weights=True, buckets=buckets, use_graph=False)
+    buckets.comm_enabled = False
+    step_noopt(x, tg)
+    torch.cuda.synchronize()
+    local = torch.cat([b.clone() for b in buckets.buckets])
+    dist.all_reduce(local)
+    local /= world
+    buckets.comm_enabled = True
+    step_noopt(x, tg)
+    torch.cuda.synchronize()
+    got = torch.cat(buckets.buckets)
+    # weight gradients use fp32 atomics: two evaluations of the same step differ in the last bits, hence a tolerance
+    rel = ((got - local).norm() / (local.norm() + 1e-30)).item()
+    chk = torch.stack([got.double().sum(), got.double().abs().sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out["bucketed_vs_plain_allreduce_rel_err"] = rel
+    out["replicas_bit_identical"] = bool(torch.equal(lo, hi))
+    out["correct"] = bool(out["known_gradients_mean_exact"] and rel < 1e-3 and out["replicas_bit_identical"])
+    # ---- the exchange alone
+    nbytes = sum(b.numel() for b in buckets.buckets) * 4
+    for _ in range(3):
+        for b in buckets.buckets:
+            dist.all_reduce(b)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        for b in buckets.buckets:
+            dist.all_reduce(b)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ar_ms = t.item()
+    out.update(allreduce_alone_ms=ar_ms, allreduce_bytes=nbytes, n_buckets=len(buckets.buckets),
+               allreduce_bus_gbs=2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9)
+    # ---- the same step with the exchange switched off (new capture)
+    buckets.comm_enabled = False
+    step_off = abcnet_b200.TrainStep(model, opt, class_weights=True, buckets=buckets, use_graph=True)
+    for _ in range(3):
+        step_off(x, tg)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_off(x, tg)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    buckets.comm_enabled = True
+    out.update(ms_per_step_comm_off=t.item(), ms_per_step_comm_on=ms_on, exposed_comm_ms=ms_on - t.item(),
+               nccl={k: os.environ[k] for k in os.environ if k.startswith("NCCL_")})
+    return out
+
+
+def run_small_batches(model, pool, dev, args):
+    """The reference's own inference batch sizes (img2smiles.py:39: 32 images; BASELINE configs[0]: 8): per-batch latency and
+    throughput of forward + decode, (a) eager = ~47 launches enqueued one by one through the C-ABI, (b) the same work replayed
+    as ONE CUDA graph (abcnet_b200.InferGraph), (c) end to end with a pinned uint8 host batch: H2D + graph + D2H of the records
+    + stream sync, i.e. what a caller waits for."""
+    import abcnet_b200
+    res = {}
+    for b in (8, 32):
+        hx = (pool[:b] > 0).to(torch.uint8).contiguous().pin_memory()
+        dx = hx.to(dev)
+        g = abcnet_b200.InferGraph(model, b, hx.shape[2], hx.shape[3], atom_cap=args.atom_cap, bond_cap=args.bond_cap, dtype=torch.uint8)
+        g(dx)                                            # capture
+        outs = None
+        dec = g.decoder
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 50
+
+        def timed(fn):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+
+        def eager():
+            nonlocal outs
+            outs = model.infer(dx, outs, layout="p8f")
+            dec.launch(outs)
+        ms_eager = timed(eager)
+        ms_graph = timed(lambda: g.launch(dx))
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            g(hx)                                        # H2D (pinned, async) + replay + D2H + sync: one caller-visible latency
+        ms_e2e = (time.perf_counter() - t0) / iters * 1e3
+        res[str(b)] = {"eager_ms": ms_eager, "graph_ms": ms_graph, "e2e_latency_ms": ms_e2e, "graph_images_per_s": b / (ms_graph * 1e-3),
+                       "e2e_images_per_s": b / (ms_e2e * 1e-3), "launches_per_replay": g.launches_per_replay}
+        del g
+    return res
+
+
+def run_comparator(args, dev, pool, B):
+    """SURVEY.md section 8d config 2 / 4 comparator: the reference's graph through torch / cuDNN on this same GPU (tools/gpu_comparator.py)
+    -- forward + the dense decode tensor ops at batch B, forward + losses + backward at the training batch size."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gpu_comparator
+
+    import abcnet_b200
+    import synthdata as synth
+    m = abcnet_b200.UNet(1, HEADS).to(dev)
+    m.load_state_dict(make_weights())
+    xi = pool.repeat((B + 63) // 64, 1, 1, 1)[:B].contiguous().to(dev)
+    Bt = args.train_batch
+    xt = xi[:Bt].contiguous()
+    tg = [torch.from_numpy(t).repeat(*([(Bt + 7) // 8] + [1] * (t.ndim - 1)))[:Bt].contiguous().to(dev)
+          for t in synth.dense_targets(0, 8, 128, 128)]
+    res = gpu_comparator.run(m, xi, xt, tg, iters=3, warmup=2)
+    res["what"] = ("src/unet.py's graph executed by stock torch ops (cuDNN convolutions, ATen BatchNorm / pooling / losses, autograd) on "
+                   "the same B200: infer = forward + dense decode tensor ops (img2smiles.py:62-80,115-124) at batch %d; train = forward + "
+                   "8 losses + backward (no optimizer step) at batch %d; CUDA events, cudnn.benchmark on" % (B, Bt))
+    return res
 
 
 # ----------------------------------------------------------------------------------------- GPU arm
@@ -300,8 +494,12 @@ def run_ours(args, rank, world, local_rank):
     model.load_state_dict(sd)
     # synthetic images: a pool of 64 distinct images tiled to the batch (generation of 256 x 512^2 takes a while on the host)
     pool = make_images(1000 + rank, 64)
-    host = pool.repeat((B + 63) // 64, 1, 1, 1)[:B].contiguous().pin_memory()
-    x = host.to(dev)
+    host_f32 = pool.repeat((B + 63) // 64, 1, 1, 1)[:B].contiguous()
+    x = host_f32.to(dev)                                 # `value`: fp32 {0,1} images resident in HBM (the reference DataLoader's format)
+    # e2e transport: the same binary images as uint8 in pinned host memory (utils.py:80-81 binarises before the float cast;
+    # UNet.forward accepts uint8 / bool / fp32 and produces identical bits) -- 4x fewer PCIe bytes than fp32
+    host = (host_f32 > 0).to(torch.uint8).pin_memory()
+    del host_f32
     # calibrate constant offsets of the centre / omega heads for a realistic peak density, folded into the conv2 biases
     outs = model(x[:8].contiguous())
     torch.cuda.synchronize()
@@ -361,7 +559,7 @@ def run_ours(args, rank, world, local_rank):
     # the decoded records back (one D2H + stream sync per step).
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
-    xbuf = [torch.empty_like(x), torch.empty_like(x)]
+    xbuf = [torch.empty(host.shape, dtype=torch.uint8, device=dev), torch.empty(host.shape, dtype=torch.uint8, device=dev)]
     copied = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -469,12 +667,20 @@ def run_ours(args, rank, world, local_rank):
         ms_sp_e2e = None if ms_sp_e2e >= 1e29 else ms_sp_e2e
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    small = None if args.no_small else run_small_batches(model, pool, dev, args)
+    comparator = None
     train = None
     if not args.no_train:
         model._bufs.clear()
         out_bufs = xbuf = x = None
         torch.cuda.empty_cache()
         train = run_train(args, rank, world, dev)
+    if world == 1 and not args.no_comparator:
+        model._bufs.clear()
+        model._packed = None
+        out_bufs = xbuf = x = obufs = dec2 = None
+        torch.cuda.empty_cache()
+        comparator = run_comparator(args, dev, pool, B)
     if rank != 0:
         return
     pk, pk_src = peaks()
@@ -491,13 +697,14 @@ def run_ours(args, rank, world, local_rank):
         flops = (HEADS_CONV1_FLOPS_PER_IMAGE + (HEADS_CONV2_FLOPS_PER_IMAGE if fused else 0.0)) * B
         ach = flops / (dom_ms * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        traffic = (HEADS_FUSED_DRAM_BYTES_B256 if fused else HEADS_CONV1_DRAM_BYTES_B256) if B == 256 else None
+        traffic, traffic_src = (None, None) if (fused or B != 256) else ncu_traffic(HEADS_CONV1_SUMMARY_GLOB)
         roof = {"bound": "tensor",
                 "kernel": "heads_fused_kernel[8 x (128->128 3x3 + LeakyReLU + 128->h 1x1) @128x128]" if fused
                 else "conv_igemm_kernel[heads.conv1 128->1024 3x3 @128x128]", "achieved": ach,
                 "peak": peak, "peak_source": pk_src + " (sustained bf16)", "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": traffic,
                 "traffic_unit": "bytes per launch (ncu dram read + write of the committed --set full capture under profiles/)",
+                "traffic_source": traffic_src,
                 "ms_per_launch": dom_ms, "flops_per_launch": flops}
     total_tflops = FLOPS_PER_IMAGE * B * args.steps / (ms * 1e-3) / 1e12
     cpu = None
@@ -515,8 +722,8 @@ def run_ours(args, rank, world, local_rank):
                       "whole_forward_tflops": total_tflops, "layers_ms": layers,
                       "layer_classes": layer_class_report(layers, B, pk, decode_bytes_per_image(n_atoms, n_bpeaks, n_bonds))},
            "roofline": roof, "cpu_baseline": cpu,
-           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": d2h,
-                   "ms_per_step": ms_e2e / args.steps},
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host.numel() * host.element_size()), "d2h_bytes_per_step": d2h,
+                   "ms_per_step": ms_e2e / args.steps, "input_format": "uint8 {0,1} [B,1,512,512] in pinned host memory"},
            "e2e_molblock": {"value": world * B * args.steps / (ms_mol * 1e-3), "unit": UNIT, "ms_per_step": ms_mol / args.steps,
                             "what": "e2e loop + native multi-threaded host assembly of every image's records into V2000 MOL-block "
                                     "text (abc_assemble_molblocks: img2smiles.py:183-318 + generate_smiles.py:18-105)",
@@ -528,6 +735,7 @@ def run_ours(args, rank, world, local_rank):
                             "what": "opt-in SparseHeadsPipeline, device-resident inputs: trunk + dense centre heads + peak search + "
                                     "class / offset heads at the peaks only (same kernels, same packed weights, same MMA order); "
                                     "NOT the headline `value`, which evaluates all eight heads densely"},
+           "small_batch": small, "gpu_comparator": comparator,
            "gpu_launches": int(launches), "clocks": clocks, "train": train}
     print(json.dumps(out))
 
@@ -543,6 +751,8 @@ def main():
     ap.add_argument("--bond-cap", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (the 'train' object)")
+    ap.add_argument("--no-small", action="store_true", help="skip the batch-8 / batch-32 latency leg ('small_batch')")
+    ap.add_argument("--no-comparator", action="store_true", help="skip the torch / cuDNN comparator leg ('gpu_comparator')")
     ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step (train.py:44)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -118,6 +118,14 @@ def forward(x, sd, heads=V2_HEADS, training=False, crop_first=True, acts=None, d
     sd = _strip(sd)
     rnd = bf16_ste if emulate_bf16 else _id
     t = trunk(x, sd, training, crop_first, acts, rnd)
+    return heads_forward(t, sd, heads, training, acts, dropout_masks, rnd)
+
+
+def heads_forward(t, sd, heads=V2_HEADS, training=False, acts=None, dropout_masks=None, rnd=_id, round_hidden=None):
+    """The eight OutConv heads (unet.py:63-74, :116-118) on a given trunk tensor [B,128,H/4,W/4]. Split out of ``forward``
+    so that tests can feed the heads with the product's own trunk activations (error budget per stage).
+    ``round_hidden``: optional rounding applied to the hidden map only (e.g. ``bf16_ste``)."""
+    sd = _strip(sd)
     outs = []
     for i, _ in enumerate(heads):
         p = f"out_modules.{i}"
@@ -126,6 +134,8 @@ def forward(x, sd, heads=V2_HEADS, training=False, crop_first=True, acts=None, d
         if training and dropout_masks is not None:
             h = h * dropout_masks[i] / 0.8
         h = rnd(h)
+        if round_hidden is not None:
+            h = round_hidden(h)
         if acts is not None:
             acts[p + ".hidden"] = h
         outs.append(F.conv2d(h, rnd(sd[p + ".conv2.weight"]), sd[p + ".conv2.bias"]))

@@ -250,3 +250,30 @@ def test_pack_arena_equals_torch_repack(monkeypatch):
     for n, ga in outs["arena"][1].items():
         gb = outs["torch"][1][n]
         assert _rel(ga, gb) <= 1e-3 or gb.abs().max().item() == 0.0, (n, _rel(ga, gb))
+
+
+@pytest.mark.parametrize("tag,B,H,W,seed", [("small", 2, 64, 96, 3), ("tiny", 2, 32, 32, 4)])
+def test_train_forward_against_reference_minted_golden(tag, B, H, W, seed):
+    """Train-mode forward (batch-statistics BatchNorm, dropout off) of the CUDA path against the logits minted by the
+    reference's own module in train() mode (tests/golden/make_golden.py -> unet_small.npz:*_train_out*).
+
+    With B = 2 and 64 x 96 / 32 x 32 inputs the deepest BatchNorms normalise over 12 / 2 samples, which amplifies any
+    perturbation by orders of magnitude (oracle fp32 vs fp64 already differ by 2e-5 at the trunk), so bf16 storage noise
+    cannot vanish end to end. The yardstick is therefore the fp32 oracle with bf16 rounding injected at the CUDA path's
+    storage points (unet_ref.forward(emulate_bf16=True)) measured against the SAME golden: the CUDA path may not be further
+    from the reference than 3x that emulation + 2 %. The first head (atom centre) error is printed for the record."""
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "unet_small.npz"))
+    m, sd, x = _setup(seed, B, H, W)
+    with torch.no_grad():
+        ours = [o.float().cpu() for o in m(x.cuda())]
+        emu = unet_ref.forward(x, sd, training=True, emulate_bf16=True)
+        exact = unet_ref.forward(x, sd, training=True)
+    rows = []
+    for i in range(8):
+        ref = torch.from_numpy(g[f"{tag}_train_out{i}"])
+        assert _rel(exact[i], ref) < 1e-3, "oracle drifted from its golden"
+        r_ours, r_emu = _rel(ours[i], ref), _rel(emu[i], ref)
+        rows.append((i, round(r_ours, 4), round(r_emu, 4)))
+        assert r_ours <= 3.0 * r_emu + 0.02, f"head {i}: CUDA train forward rel L2 {r_ours} vs bf16-emulated oracle {r_emu}"
+    print(f"train-mode forward vs reference-minted golden ({tag}): (head, ours, bf16-emulated oracle) = {rows}")

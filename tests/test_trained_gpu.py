@@ -1,22 +1,27 @@
 """End-to-end identity on a TRAINED network (north_star: "decoded peak sets ... and the final SMILES must be identical on a
 fixed synthetic test set, with any threshold-boundary ties listed explicitly").
 
-The reference ships no weights, and random-init logits are nearly flat, so the test first trains the network for a few
-hundred iterations on labelled pseudo-molecule drawings (oracle/synth.pseudo_molecules + rasterise_targets, utils.py:83-228)
-with the PRODUCT training step (abcnet_b200.TrainStep: CUDA forward / losses / backward + Adam, one CUDA graph). Then, on the
-fixed image set, the product inference path (bf16 activations, fp32 logits) + CUDA decode is compared with the oracle:
-fp32 CPU forward of src/unet.py's graph (oracle/unet_ref) + the restated decode statements of img2smiles.py:62-193.
+The reference ships no weights, and random-init logits are nearly flat, so the test first trains the network on labelled
+pseudo-molecule drawings (oracle/synth.pseudo_molecules + rasterise_targets, utils.py:83-228) with the PRODUCT training
+step (abcnet_b200.TrainStep: CUDA forward / losses / backward + Adam, one CUDA graph). Then, on the fixed set of N_IMG = 256
+images, the product inference path (bf16 activations, fp32 logits) + CUDA decode is compared with the oracle: fp32 CPU forward
+of src/unet.py's graph (oracle/unet_ref) + the restated decode statements of img2smiles.py:62-193.
 
-Criteria
-  * logits (bf16 activations through 45 layers vs fp32, trained weights with logit ranges of 20..170): per output map
-    max-abs error <= 0.08 * max|ref| + 0.05 and relative L2 error <= 5e-2 (measured: 0.2 .. 2.5 %; the training run is not
-    bitwise reproducible -- fp32 atomics in the weight-gradient kernels -- so the figures move a little from run to run);
-  * records: every image whose atom / bond records are identical must give the identical MOL-block text
-    (generate_smiles.py:18-105 -> identical SMILES);
-  * every differing record is listed, and must be a genuine boundary case: its decision margin in the fp32 reference
-    logits (distance to the -1 threshold, to the 3x3 / 3-bin neighbourhood maximum, to the antipodal omega bins, or between
-    the two best classes) is smaller than twice the measured logit error of that map -- i.e. a tie at bf16 resolution;
-  * at least 2/3 of the images must match exactly, and the set must be non-degenerate (peaks present, most labelled atoms found).
+What is asserted, in this order
+  1. DECODE IS EXACT ON THE PRODUCT'S OWN LOGITS: for every image the CUDA decoder's records equal, bit for bit (positions,
+     classes, omega survivors, order, rho bits), the oracle decode applied to the product's fp32 logits. Hence every difference
+     to the reference below is a consequence of logit error alone, never of the decode kernel.
+  2. logits (bf16 activations through 45 layers vs fp32; trained weights with logit ranges of 20..170): per output map
+     max-abs error <= 0.08 * max|ref| + 0.05 and relative L2 error <= 5e-2.
+  3. every record that differs between decode(reference logits) and decode(product logits) is listed with the comparison that
+     flipped (threshold, 3x3 / 3-bin NMS neighbour, antipodal omega bin, arg-max runner-up), its margin in the fp32 reference
+     logits and the LOCAL error = |ours - ref| summed over exactly the two logits of that comparison. A flip is a boundary tie iff
+     margin <= local error; the old whole-map bound (2 x max|err| of the map) is gone.
+  4. for EVERY image -- differing ones included -- both record sets go through the reference's host assembly (assemble_ref):
+     MOL-block text equality and molecular-graph equality (assemble_ref.molecule_graph: an omega / omega+30 flip of an undirected
+     bond only swaps that bond's two end atoms) are counted and reported; a graph change must come from a listed boundary case.
+  5. error budget per stage: the product's own trunk fed to fp32 heads separates trunk error from head error (hidden-map
+     rounding, bf16 conv1 / conv2 weights), reported per decision head.
 The report is written to gpurun_out/trained_parity_report.json (copied to profiles/ when the run is recorded).
 """
 import json
@@ -31,8 +36,22 @@ from oracle import assemble_ref, decode_ref, synth, unet_ref
 pytestmark = pytest.mark.gpu
 HEADS = list(unet_ref.V2_HEADS)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-N_IMG, BATCH, STEPS, LR, LR_LATE = 32, 16, int(os.environ.get("ABCNET_TRAINED_STEPS", "2400")), 6e-4, 2.5e-4   # late = train.py:55
+N_IMG = int(os.environ.get("ABCNET_TRAINED_IMAGES", "256"))
+BATCH, CHUNK = 16, 32
+STEPS, LR, LR_LATE = int(os.environ.get("ABCNET_TRAINED_STEPS", "4000")), 6e-4, 2.5e-4   # late = train.py:55
 THR = -1.0
+
+
+def _targets_on_gpu(labels):
+    """Dense targets of all images, rasterised chunk-wise on the host (oracle rules) and kept in HBM (41.7 MB per image)."""
+    parts = None
+    for c0 in range(0, len(labels), CHUNK):
+        tg = synth.rasterise_targets(labels[c0:c0 + CHUNK], 128, 128)
+        if parts is None:
+            parts = [torch.empty((len(labels),) + t.shape[1:], dtype=torch.from_numpy(t).dtype, device="cuda") for t in tg]
+        for dst, t in zip(parts, tg):
+            dst[c0:c0 + CHUNK].copy_(torch.from_numpy(t))
+    return parts
 
 
 def _train(imgs, targets):
@@ -45,154 +64,271 @@ def _train(imgs, targets):
     opt = abcnet_b200.make_optimizer(m, lr=lr, capturable=True)
     step = abcnet_b200.TrainStep(m, opt, class_weights=True, use_graph=True)
     x = torch.from_numpy(imgs).cuda()
-    tg = [torch.from_numpy(t).cuda() for t in targets]
-    nb = N_IMG // BATCH
+    nb = len(imgs) // BATCH
     curve = []
     for it in range(STEPS):
         b = it % nb
         if it == (STEPS * 5) // 8:
             lr.fill_(LR_LATE)
         sl = slice(b * BATCH, (b + 1) * BATCH)
-        loss = step(x[sl].contiguous(), [t[sl].contiguous() for t in tg])
-        if it % 100 == 0 or it == STEPS - 1:
+        loss = step(x[sl].contiguous(), [t[sl].contiguous() for t in targets])
+        if it % 200 == 0 or it == STEPS - 1:
             curve.append((it, float(loss.item())))
     torch.cuda.synchronize()
     m.eval()
     return m, curve
 
 
-def _centre_margin(z, x, y):
-    """Decision margin of 'pixel (x, y) is a peak' in map z: > 0 for a peak, < 0 otherwise; |margin| = how far the value is
-    from flipping (threshold and 3x3 neighbourhood, img2smiles.py:62-68)."""
-    H, W = z.shape
-    nb = [z[i, j] for i in range(max(x - 1, 0), min(x + 2, H)) for j in range(max(y - 1, 0), min(y + 2, W)) if (i, j) != (x, y)]
-    return float(min(z[x, y] - THR, z[x, y] - max(nb)))
+# ---------------------------------------------------------------------------- which comparison flipped?
+def _flips(cmps):
+    """cmps: (name, ref_a, ref_b, our_a, our_b, strict) for predicates 'a > b' (strict) or 'a >= b'; b may be a constant
+    (then our_b == ref_b). Returns the flipped predicates as dicts with margin and local error."""
+    out = []
+    for name, ra, rb, oa, ob, strict in cmps:
+        pr = (ra > rb) if strict else (ra >= rb)
+        po = (oa > ob) if strict else (oa >= ob)
+        if pr != po:
+            out.append(dict(cmp=name, margin=float(abs(float(ra) - float(rb))),
+                            local_err=float(abs(float(oa) - float(ra)) + abs(float(ob) - float(rb)))))
+    return out
 
 
-def _top2_gap(v):
-    s = np.sort(np.asarray(v, np.float64))
-    return float(s[-1] - s[-2])
+def _centre_cmps(zr, zo, x, y):
+    H, W = zr.shape
+    c = [("thr", zr[x, y], THR, zo[x, y], THR, True)]
+    for i in range(max(x - 1, 0), min(x + 2, H)):
+        for j in range(max(y - 1, 0), min(y + 2, W)):
+            if (i, j) != (x, y):
+                c.append((f"nms({i - x},{j - y})", zr[x, y], zr[i, j], zo[x, y], zo[i, j], False))
+    return c
 
 
-def _omega_min_gap(col, w):
-    """Smallest gap among the comparisons that decide whether omega bin w is emitted (img2smiles.py:74-80, :143-158)."""
-    n = len(col)
+def _omega_cmps(cr, co, w):
+    """The comparisons that decide whether bin w of an omega column is emitted (img2smiles.py:74-80, :143-158)."""
+    n = len(cr)
     h = n // 2
-    others = [THR, col[(w - 1) % n], col[(w + 1) % n]]
-    if w < h - 1:
-        others += [col[w + h - 1], col[w + h]]
+    c = [("thr", cr[w], THR, co[w], THR, True)]
+    for k in ((w - 1) % n, (w + 1) % n):
+        c.append((f"nms(bin {k})", cr[w], cr[k], co[w], co[k], False))
+    if w <= h - 2:
+        others, strict = (w + h - 1, w + h), False          # dropped if z_w <  max(...): survives on z_w >= each
     elif w == h - 1:
-        others += [col[n - 2], col[0]]
+        others, strict = (n - 2, 0), False
     elif w == h:
-        others += [col[0], col[n - 1]]
+        others, strict = (0, n - 1), True                   # dropped if z_w <= ...: survives on z_w > each
     else:
-        others += [col[w - h - 1], col[w - h]]
-    return float(min(abs(col[w] - o) for o in others))
+        others, strict = (w - h - 1, w - h), True
+    for k in others:
+        c.append((f"antipode(bin {k})", cr[w], cr[k], co[w], co[k], strict))
+    return c
+
+
+def _argmax_cmps(vr, vo, name):
+    a, b = int(np.argmax(vr)), int(np.argmax(vo))
+    # the reference prefers a; ours prefers b: 'v[a] beats v[b]' (first maximum wins ties: strict iff b < a)
+    return [(f"{name} {a} vs {b}", vr[a], vr[b], vo[a], vo[b], b < a)]
+
+
+def _explain(j, R, O, ra, rb, oa, ob):
+    """All record differences of image j between decode(R) and decode(O), each with its flipped comparison(s)."""
+    d = []
+    A_r, A_o = {(a[0], a[1]): a for a in ra.tolist()}, {(a[0], a[1]): a for a in oa.tolist()}
+    for pos in sorted(set(A_r) ^ set(A_o)):
+        d.append(dict(image=j, kind="atom peak", pos=pos, in_ref=pos in A_r, flips=_flips(_centre_cmps(R[0][0], O[0][0], *pos))))
+    for pos in sorted(set(A_r) & set(A_o)):
+        for name, col, head in (("atom type", 2, 1), ("atom charge", 3, 2), ("atom hs", 4, 3)):
+            if A_r[pos][col] != A_o[pos][col]:
+                d.append(dict(image=j, kind=name, pos=pos, ref=A_r[pos][col], ours=A_o[pos][col],
+                              flips=_flips(_argmax_cmps(R[head][:, pos[0], pos[1]], O[head][:, pos[0], pos[1]], name))))
+    B_r = {(b[0], b[1], b[2]): b[3] for b in rb.tolist()}
+    B_o = {(b[0], b[1], b[2]): b[3] for b in ob.tolist()}
+    P_r = decode_ref._peaks2d(R[4][0], THR)
+    P_o = decode_ref._peaks2d(O[4][0], THR)
+    for key in sorted(set(B_r) ^ set(B_o)):
+        x_, y_, w = key
+        if bool(P_r[x_, y_]) != bool(P_o[x_, y_]):
+            d.append(dict(image=j, kind="bond peak", pos=(x_, y_), omega=w, in_ref=key in B_r,
+                          flips=_flips(_centre_cmps(R[4][0], O[4][0], x_, y_))))
+        else:
+            d.append(dict(image=j, kind="bond omega", pos=(x_, y_), omega=w, in_ref=key in B_r,
+                          flips=_flips(_omega_cmps(R[7][:, x_, y_], O[7][:, x_, y_], w))))
+    n_w = R[7].shape[0]
+    for key in sorted(set(B_r) & set(B_o)):
+        if B_r[key] != B_o[key]:
+            x_, y_, w = key
+            vr = R[5].reshape(-1, n_w, *R[5].shape[1:])[:, w, x_, y_]
+            vo = O[5].reshape(-1, n_w, *O[5].shape[1:])[:, w, x_, y_]
+            d.append(dict(image=j, kind="bond type", pos=(x_, y_), omega=w, ref=B_r[key], ours=B_o[key],
+                          flips=_flips(_argmax_cmps(vr, vo, "bond type"))))
+    return d
 
 
 def test_trained_network_end_to_end_identity():
     import abcnet_b200
     imgs, labels = synth.pseudo_molecules(7, N_IMG, 512, 512)
-    targets = synth.rasterise_targets(labels, 128, 128)
+    targets = _targets_on_gpu(labels)
     model, curve = _train(imgs, targets)
+    del targets
+    torch.cuda.empty_cache()
     print("training loss curve:", curve)
     assert curve[-1][1] < 0.2 * curve[0][1], "training did not converge; the decode comparison would be meaningless"
     sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    sd_dev = {k: v.detach().clone() for k, v in model.state_dict().items()}
 
-    # product path: eval forward (fused layout) + CUDA decode, and the reference-format logits for the error measurement
-    x = torch.from_numpy(imgs).cuda()
-    dec = abcnet_b200.PeakDecoder(N_IMG, atom_cap=2048, bond_cap=8192)
-    recs = dec(model.infer(x, layout="p8f"), thr=THR)
-    ours = [o.float().cpu().numpy() for o in model(x)]
-    # oracle: fp32 CPU forward + restated decode
     torch.set_num_threads(os.cpu_count() or 1)
-    with torch.no_grad():
-        ref = [o.numpy() for o in unet_ref.forward(torch.from_numpy(imgs), sd)]
-    err = [float(np.abs(o - r).max()) for o, r in zip(ours, ref)]
-    scale = [float(np.abs(r).max()) for r in ref]
-    rel = [float(np.linalg.norm(o - r) / (np.linalg.norm(r) + 1e-12)) for o, r in zip(ours, ref)]
-    print("logit max-abs error per map:", [round(e, 4) for e in err], "scale:", [round(s, 2) for s in scale],
-          "rel L2:", [round(r, 4) for r in rel])
-    for i in range(8):
-        assert err[i] <= 0.08 * scale[i] + 0.05, f"map {i}: max abs err {err[i]} (scale {scale[i]})"
-        assert rel[i] <= 0.05, f"map {i}: rel L2 {rel[i]}"
-
-    # the opt-in sparse-heads path on the same trained network and images: identical records to the dense product path
-    pipe = abcnet_b200.SparseHeadsPipeline(model, N_IMG, peak_cap=256, bond_cap=8192)
-    sparse = pipe.fetch(pipe.launch(x, thr=THR))
-    for j, ((da, db, dn), (sa, sb, sn)) in enumerate(zip(recs, sparse)):
-        assert dn == sn and np.array_equal(da, sa) and np.array_equal(db, sb), f"image {j}: sparse-heads records differ"
-    assert pipe.molblocks(N_IMG) == dec.molblocks(N_IMG)
-    del pipe
-
-    report = dict(images=N_IMG, train_steps=STEPS, loss_curve=curve, logit_max_abs_err=err, logit_scale=scale, logit_rel_l2=rel,
-                  differences=[], identical_images=0, molblocks_compared=0, labelled_atoms=0, found_atoms=0, ref_atom_peaks=0,
-                  ref_bond_records=0)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False       # fp32 hybrid heads below: true fp32
+    dec = abcnet_b200.PeakDecoder(CHUNK, atom_cap=2048, bond_cap=8192)
+    pipe = abcnet_b200.SparseHeadsPipeline(model, CHUNK, peak_cap=256, bond_cap=8192)
+    report = dict(images=N_IMG, train_steps=STEPS, loss_curve=curve, differences=[], identical_record_images=0,
+                  identical_molblock_images=0, identical_graph_images=0, molecules_compared=0, labelled_atoms=0, found_atoms=0,
+                  ref_atom_peaks=0, ref_bond_records=0, images_with_differences=[], graph_changes=[])
+    err = np.zeros(8)
+    scale = np.zeros(8)
+    num = np.zeros(8)
+    den = np.zeros(8)
+    budget = {k: dict(trunk=0.0, heads=0.0, total=0.0) for k in (0, 4, 7)}
     unexplained = []
-    for j in range(N_IMG):
-        maps = [r[j] for r in ref]
-        ra, (rb, rrho) = decode_ref.decode_records(maps, THR, "nms")
-        atoms, bonds, nbp = recs[j]
-        ga = np.stack([atoms["x"], atoms["y"], atoms["type"], atoms["charge"], atoms["hs"]], -1).astype(np.int32).reshape(-1, 5)
-        gb = np.stack([bonds["x"], bonds["y"], bonds["omega"], bonds["type"]], -1).astype(np.int32).reshape(-1, 4)
-        report["ref_atom_peaks"] += len(ra)
-        report["ref_bond_records"] += len(rb)
-        lab = {(a[0] // 4, a[1] // 4) for a in labels[j]["atoms"]}
-        report["labelled_atoms"] += len(lab)
-        report["found_atoms"] += sum(1 for (px, py) in lab if any(abs(px - q[0]) <= 1 and abs(py - q[1]) <= 1 for q in ra))
-        if np.array_equal(ga, ra) and np.array_equal(gb, rb):
-            report["identical_images"] += 1
-            # rho is a float: the records carry the product's fp32 value; bond assignment / MOL text must not depend on it
-            L_ours = abcnet_b200.records_to_lists(atoms, bonds, nbp)
+    for c0 in range(0, N_IMG, CHUNK):
+        xs = torch.from_numpy(imgs[c0:c0 + CHUNK]).cuda()
+        n = xs.shape[0]
+        # product: dense maps in the fused layout -> CUDA decode; reference-format logits for the comparison
+        recs = dec(model.infer(xs, layout="p8f"), thr=THR)
+        blocks = dec.molblocks(n)
+        ours_t = model(xs)
+        ours = [o.float().cpu().numpy() for o in ours_t]
+        # the opt-in sparse-heads path on the same trained network and images: identical records and MOL blocks
+        sparse = pipe.fetch(pipe.launch(xs, thr=THR)) if n == CHUNK else None
+        if sparse is not None:
+            for j, ((da, db, dn), (sa, sb, sn)) in enumerate(zip(recs, sparse)):
+                assert dn == sn and np.array_equal(da, sa) and np.array_equal(db, sb), f"image {c0 + j}: sparse-heads records differ"
+            assert pipe.molblocks(n) == blocks
+        # oracle: fp32 CPU forward
+        with torch.no_grad():
+            ref = [o.numpy() for o in unet_ref.forward(torch.from_numpy(imgs[c0:c0 + CHUNK]), sd)]
+        for i in range(8):
+            err[i] = max(err[i], float(np.abs(ours[i] - ref[i]).max()))
+            scale[i] = max(scale[i], float(np.abs(ref[i]).max()))
+            num[i] += float(((ours[i] - ref[i]).astype(np.float64) ** 2).sum())
+            den[i] += float((ref[i].astype(np.float64) ** 2).sum())
+        # error budget: the product's trunk (bf16) through fp32 heads (cuDNN fp32, TF32 off) isolates the trunk's share
+        with torch.no_grad():
+            hyb = unet_ref.heads_forward(model.activation("k2").float(), sd_dev)
+        for k in budget:
+            h = hyb[k].cpu().numpy()
+            budget[k]["trunk"] = max(budget[k]["trunk"], float(np.abs(h - ref[k]).max()))
+            budget[k]["heads"] = max(budget[k]["heads"], float(np.abs(ours[k] - h).max()))
+            budget[k]["total"] = max(budget[k]["total"], float(np.abs(ours[k] - ref[k]).max()))
+        for jj in range(n):
+            j = c0 + jj
+            R = [r[jj] for r in ref]
+            O = [o[jj] for o in ours]
+            ra, (rb, rrho) = decode_ref.decode_records(R, THR, "nms")
+            oa, (ob, orho) = decode_ref.decode_records(O, THR, "nms")
+            atoms, bonds, nbp = recs[jj]
+            ga = np.stack([atoms["x"], atoms["y"], atoms["type"], atoms["charge"], atoms["hs"]], -1).astype(np.int32).reshape(-1, 5)
+            gb = np.stack([bonds["x"], bonds["y"], bonds["omega"], bonds["type"]], -1).astype(np.int32).reshape(-1, 4)
+            # 1. the CUDA decoder is exact on the product's own logits
+            assert np.array_equal(ga, oa) and np.array_equal(gb, ob), f"image {j}: CUDA decode != oracle decode on the SAME logits"
+            assert np.array_equal(bonds["rho"].view(np.uint32), orho.view(np.uint32)), f"image {j}: rho bits"
+            report["ref_atom_peaks"] += len(ra)
+            report["ref_bond_records"] += len(rb)
+            lab = {(a[0] // 4, a[1] // 4) for a in labels[j]["atoms"]}
+            report["labelled_atoms"] += len(lab)
+            report["found_atoms"] += sum(1 for (px, py) in lab if any(abs(px - q[0]) <= 1 and abs(py - q[1]) <= 1 for q in ra))
+            # 4. molecule level, for every image
             L_ref = decode_ref.records_to_lists(ra, (rb, rrho)) if (len(ra) and len(rb)) else None
-            if L_ours is not None and L_ref is not None:
-                assert assemble_ref.records_to_molblock(L_ours) == assemble_ref.records_to_molblock(L_ref), f"image {j}: MOL block"
-                report["molblocks_compared"] += 1
-            if len(rb):
-                assert np.abs(bonds["rho"] - rrho).max() <= 0.08 * scale[6] + 0.05
-            continue
-        # ---- list and explain every difference
-        za, zb, zw = maps[0][0], maps[4][0], maps[7]
-        d = []
-        A_o, A_r = {(a[0], a[1]): a for a in ga.tolist()}, {(a[0], a[1]): a for a in ra.tolist()}
-        for pos in sorted(set(A_o) ^ set(A_r)):
-            d.append(dict(image=j, kind="atom peak", pos=pos, in_ref=pos in A_r, margin=_centre_margin(za, *pos), tol=2 * err[0]))
-        for pos in sorted(set(A_o) & set(A_r)):
-            for name, col, head in (("atom type", 2, 1), ("atom charge", 3, 2), ("atom hs", 4, 3)):
-                if A_o[pos][col] != A_r[pos][col]:
-                    d.append(dict(image=j, kind=name, pos=pos, ours=A_o[pos][col], ref=A_r[pos][col],
-                                  margin=_top2_gap(maps[head][:, pos[0], pos[1]]), tol=2 * err[head]))
-        B_o = {(b[0], b[1], b[2]): b[3] for b in gb.tolist()}
-        B_r = {(b[0], b[1], b[2]): b[3] for b in rb.tolist()}
-        P_o, P_r = {(b[0], b[1]) for b in gb.tolist()}, {(b[0], b[1]) for b in rb.tolist()}
-        for key in sorted(set(B_o) ^ set(B_r)):
-            x_, y_, w = key
-            m_c = _centre_margin(zb, x_, y_)
-            if ((x_, y_) in P_o) != ((x_, y_) in P_r) and abs(m_c) <= 2 * err[4]:
-                d.append(dict(image=j, kind="bond peak", pos=(x_, y_), omega=w, in_ref=key in B_r, margin=m_c, tol=2 * err[4]))
-            else:
-                d.append(dict(image=j, kind="bond omega", pos=(x_, y_), omega=w, in_ref=key in B_r,
-                              margin=_omega_min_gap(zw[:, x_, y_], w), tol=2 * err[7]))
-        for key in sorted(set(B_o) & set(B_r)):
-            if B_o[key] != B_r[key]:
-                x_, y_, w = key
-                d.append(dict(image=j, kind="bond type", pos=(x_, y_), omega=w, ours=B_o[key], ref=B_r[key],
-                              margin=_top2_gap(maps[5].reshape(6, 60, 128, 128)[:, w, x_, y_]), tol=2 * err[5]))
-        assert d, f"image {j}: records differ only in order"
-        for item in d:
-            item["explained"] = bool(abs(item["margin"]) <= item["tol"])
-            if not item["explained"]:
-                unexplained.append(item)
-        report["differences"] += d
+            L_our = abcnet_b200.records_to_lists(atoms, bonds, nbp)
+            mol_r = assemble_ref.records_to_molblock(L_ref) if L_ref is not None else None
+            mol_o = assemble_ref.records_to_molblock(L_our) if L_our is not None else None
+            g_r = assemble_ref.molecule_graph(L_ref) if L_ref is not None else None
+            g_o = assemble_ref.molecule_graph(L_our) if L_our is not None else None
+            assert mol_o == blocks[jj], f"image {j}: native assembler text != reference assembly of the same records"
+            report["molecules_compared"] += int(mol_r is not None)
+            same_rec = np.array_equal(ga, ra) and np.array_equal(gb, rb)
+            report["identical_record_images"] += int(same_rec)
+            report["identical_molblock_images"] += int(mol_r == mol_o)
+            report["identical_graph_images"] += int(g_r == g_o)
+            if same_rec:
+                assert mol_r == mol_o, f"image {j}: identical records but different MOL block (rho dependence)"
+                if len(rb):
+                    assert np.abs(bonds["rho"] - rrho).max() <= 0.08 * scale[6] + 0.05
+                continue
+            # 3. list and explain every difference
+            d = _explain(j, R, O, ra, rb, oa, ob)
+            assert d, f"image {j}: records differ only in order"
+            for item in d:
+                item["explained"] = bool(item["flips"]) and all(f["margin"] <= f["local_err"] for f in item["flips"])
+                if not item["explained"]:
+                    unexplained.append(item)
+            report["differences"] += d
+            report["images_with_differences"].append(dict(image=j, n=len(d), molblock_identical=bool(mol_r == mol_o),
+                                                          graph_identical=bool(g_r == g_o), kinds=sorted({i["kind"] for i in d})))
+            if g_r != g_o:
+                report["graph_changes"].append(dict(image=j, kinds=sorted({i["kind"] for i in d})))
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    rel = np.sqrt(num / np.maximum(den, 1e-30))
+    report.update(logit_max_abs_err=err.tolist(), logit_scale=scale.tolist(), logit_rel_l2=rel.tolist(),
+                  error_budget_max_abs={str(k): v for k, v in budget.items()})
+    margins = [f["margin"] for it in report["differences"] for f in it["flips"]]
+    report["flip_margin_max"] = max(margins) if margins else 0.0
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "trained_parity_report.json"), "w") as f:
         json.dump(report, f, indent=1, default=lambda o: o.item() if hasattr(o, "item") else str(o))
-    print(f"identical images: {report['identical_images']}/{N_IMG}; MOL blocks compared: {report['molblocks_compared']}; "
-          f"reference atom peaks {report['ref_atom_peaks']} (labelled {report['labelled_atoms']}, found {report['found_atoms']}), "
-          f"bond records {report['ref_bond_records']}; listed boundary cases: {len(report['differences'])}")
-    for item in report["differences"]:
+    print("logit max-abs error per map:", [round(e, 4) for e in err], "scale:", [round(s, 2) for s in scale],
+          "rel L2:", [round(r, 4) for r in rel])
+    print("error budget (max-abs, decision heads): ", budget)
+    print(f"images {N_IMG}: identical records {report['identical_record_images']}, identical MOL text {report['identical_molblock_images']}, "
+          f"identical molecular graph {report['identical_graph_images']}; molecules {report['molecules_compared']}; reference atom peaks "
+          f"{report['ref_atom_peaks']} (labelled {report['labelled_atoms']}, found {report['found_atoms']}), bond records "
+          f"{report['ref_bond_records']}; listed boundary cases: {len(report['differences'])}, largest flipped margin {report['flip_margin_max']:.4f}")
+    for item in report["differences"][:40]:
         print("  boundary case:", item)
-    assert not unexplained, f"differences that are NOT threshold / tie boundary cases: {unexplained}"
+    for i in range(8):
+        assert err[i] <= 0.08 * scale[i] + 0.05, f"map {i}: max abs err {err[i]} (scale {scale[i]})"
+        assert rel[i] <= 0.05, f"map {i}: rel L2 {rel[i]}"
+    assert not unexplained, f"differences that are NOT threshold / tie boundary cases: {unexplained[:5]}"
     assert report["ref_atom_peaks"] >= 4 * N_IMG and report["found_atoms"] >= 0.7 * report["labelled_atoms"], "degenerate network"
-    assert report["identical_images"] >= (2 * N_IMG) // 3
-    assert report["molblocks_compared"] >= N_IMG // 2
+    assert report["identical_record_images"] >= (2 * N_IMG) // 3
+    assert report["identical_graph_images"] >= (9 * N_IMG) // 10
+
+
+def test_eval_cache_follows_graph_training():
+    """a CUDA-graph replay updates weights and BatchNorm running statistics behind torch's version
+    counters; eval -> train (replays) -> eval must run on the NEW weights (train.py:89,218 alternates per epoch)."""
+    import abcnet_b200
+    imgs, labels = synth.pseudo_molecules(3, 8, 256, 256)
+    tg = [torch.from_numpy(t).cuda() for t in synth.rasterise_targets(labels, 64, 64)]
+    x = torch.from_numpy(imgs).cuda()
+    torch.manual_seed(0)
+    m = abcnet_b200.UNet(1, HEADS).cuda()
+    m.load_state_dict(unet_ref.make_state_dict(seed=5, variant="W1"))
+    opt = abcnet_b200.make_optimizer(m, lr=1e-3)
+    step = abcnet_b200.TrainStep(m, opt, use_graph=True)
+    pipe = abcnet_b200.SparseHeadsPipeline(m, 8, peak_cap=1024, bond_cap=8192)
+    m.train()
+    for _ in range(2):
+        step(x, tg)
+    m.eval()
+    first = [o.clone() for o in m(x)]
+    pipe.launch(x)                                          # caches a pack derived from the current weights
+    m.train()
+    for _ in range(5):
+        step(x, tg)                                         # pure graph replays: no _version bump anywhere
+    m.eval()
+    second = m(x)
+    fresh = abcnet_b200.UNet(1, HEADS).cuda().eval()
+    fresh.load_state_dict(m.state_dict())
+    want = fresh(x)
+    assert any((a - b).abs().max().item() > 1e-3 for a, b in zip(first, second)), "training did not change the outputs"
+    for i, (a, b) in enumerate(zip(second, want)):
+        assert torch.equal(a, b), f"head {i}: eval after graph training used stale packed weights"
+    # the sparse pipeline re-derives its centre pack as well
+    dec = abcnet_b200.PeakDecoder(8, atom_cap=4096, bond_cap=16384)
+    dense = dec(fresh.infer(x, layout="p8f"))
+    try:
+        sp = pipe.fetch(pipe.launch(x))
+    except RuntimeError:
+        return                                              # more peaks than peak_cap on this barely trained net: nothing to compare
+    for (da, db, dn), (sa, sb, sn) in zip(dense, sp):
+        assert dn == sn and np.array_equal(da, sa) and np.array_equal(db, sb)
