@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libabcnet_b200.so")
 
 EXPORTS = (
     "abc_last_error", "abc_version", "abc_device_ok", "abc_sm_count", "abc_launch_count",
-    "abc_conv3x3_c1", "abc_conv3x3_c1_u8", "abc_conv_igemm", "abc_conv_wpack_bytes", "abc_decode_peaks",
+    "abc_conv3x3_c1", "abc_conv3x3_c1_u8", "abc_conv3x3_cn", "abc_conv3x3_cn_wgrad", "abc_conv_igemm", "abc_conv_wpack_bytes", "abc_decode_peaks",
     "abc_loss_partials", "abc_loss_backward",
     "abc_bn_stats", "abc_bn_finalize", "abc_bn_act", "abc_bn_act_backward", "abc_nchw_to_p8", "abc_channel_sum",
     "abc_nchw_to_p8_ex", "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
@@ -141,6 +141,10 @@ def _load():
     lib.abc_conv3x3_c1.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_void_p]
     lib.abc_conv3x3_c1_u8.argtypes = lib.abc_conv3x3_c1.argtypes
+    lib.abc_conv3x3_cn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.abc_conv3x3_cn_wgrad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p]
     lib.abc_conv_igemm.argtypes = [C.POINTER(AbcConvDesc), C.c_void_p]
     lib.abc_decode_peaks.argtypes = [C.POINTER(AbcDecodeDesc), C.c_void_p]
     lib.abc_loss_partials.argtypes = [C.POINTER(AbcLossDesc), C.c_void_p]

@@ -210,7 +210,77 @@ __global__ void __launch_bounds__(256, 4) conv3x3_c1_rows_kernel(const T* __rest
   }
 }
 
+// General stem: Cin (1..8) real-valued fp32 input channels -> 16 channels. UNet(in_channels=3) of the reference's own
+// self-check (/root/reference/src/unet.py:122-134) and any non-binarised input take this path; bandwidth class like the
+// binary kernel (4 * Cin B read + 32 B written per pixel). One thread per pixel, weights [16][Cin][9] in shared memory,
+// fp32 fmaf accumulation in (ci, ky, kx) order.
+__global__ void __launch_bounds__(256) conv3x3_cn_kernel(const float* __restrict__ img, int cin, const float* __restrict__ w,
+                                                         const float* __restrict__ b, uint4* __restrict__ out, int H, int W,
+                                                         int out_planes, int out_plane_off, int relu) {
+  __shared__ float ws[16 * 8 * 9 + 16];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < 16 * cin * 9; i += 256) ws[i] = w[i];
+  if (tid < 16) ws[16 * 8 * 9 + tid] = b[tid];
+  __syncthreads();
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int n = blockIdx.z;
+  if (x >= W || y >= H) return;
+  float v[16];
+#pragma unroll
+  for (int co = 0; co < 16; ++co) v[co] = ws[16 * 8 * 9 + co];
+  for (int ci = 0; ci < cin; ++ci) {
+    const float* im = img + (static_cast<size_t>(n) * cin + ci) * H * W;
+    float t[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int yy = y + dy - 1, xx = x + dx - 1;
+        t[dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + static_cast<size_t>(yy) * W + xx) : 0.f;
+      }
+#pragma unroll
+    for (int co = 0; co < 16; ++co) {
+      float a = v[co];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(t[k], ws[(co * cin + ci) * 9 + k], a);
+      v[co] = a;
+    }
+  }
+#pragma unroll
+  for (int pl = 0; pl < 2; ++pl) {
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = v[pl * 8 + 2 * i], c = v[pl * 8 + 2 * i + 1];
+      if (relu) {
+        a = fmaxf(a, 0.f);
+        c = fmaxf(c, 0.f);
+      }
+      __nv_bfloat162 pk = __floats2bfloat162_rn(a, c);
+      ow[i] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    out[((static_cast<size_t>(n) * out_planes + out_plane_off + pl) * H + y) * W + x] = o;
+  }
+}
+
 }  // namespace abc
+
+extern "C" int abc_conv3x3_cn(const float* img, int cin, const float* w, const float* b, void* out, int N, int H, int W,
+                              int out_planes, int out_plane_off, int relu, void* stream) {
+  using namespace abc;
+  if (int rc = device_check()) return rc;
+  ABC_REQUIRE(img && w && b && out, "abc_conv3x3_cn: null pointer");
+  ABC_REQUIRE(cin >= 1 && cin <= 8, "abc_conv3x3_cn: cin=%d must be in 1..8", cin);
+  ABC_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535, "abc_conv3x3_cn: bad geometry N=%d H=%d W=%d", N, H, W);
+  ABC_REQUIRE(out_plane_off >= 0 && out_plane_off + 2 <= out_planes, "abc_conv3x3_cn: output plane range");
+  ABC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "abc_conv3x3_cn: output must be 16-byte aligned");
+  dim3 grid((W + 31) / 32, (H + 7) / 8, N);
+  conv3x3_cn_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(img, cin, w, b, static_cast<uint4*>(out), H, W,
+                                                                                  out_planes, out_plane_off, relu);
+  return launch_check("conv3x3_cn_kernel");
+}
 
 template <typename T>
 static int conv3x3_c1_launch(const T* img, const float* w, const float* b, void* out, int N, int H, int W, int out_planes,

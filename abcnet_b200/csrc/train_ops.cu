@@ -471,9 +471,11 @@ __global__ void __launch_bounds__(256) nchw_to_p8_ex_kernel(const float* __restr
 }
 
 // dW[16][9], db-free: gradient of the first 1 -> 16 convolution (no dgrad: the image needs no gradient)
+// img_cstride: channels of the image tensor (1 for the binary stem); img points at the channel to differentiate.
+// dw_costride: floats between consecutive output channels in dw ([16][cin][9]: cin * 9).
 template <typename T>
 __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const T* __restrict__ img, P8View dz, int N, int H, int W,
-                                                            float* __restrict__ dw) {
+                                                            float* __restrict__ dw, int img_cstride, int dw_costride) {
   __shared__ float acc[144];
   if (threadIdx.x < 144) acc[threadIdx.x] = 0.f;
   __syncthreads();
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const T* __restrict_
       for (int dx = 0; dx < 3; ++dx) {
         const int yy = y + dy - 1, xx = x + dx - 1;
         t[dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                             ? static_cast<float>(img[static_cast<size_t>(n) * H * W + static_cast<size_t>(yy) * W + xx]) : 0.f;
+                             ? static_cast<float>(img[static_cast<size_t>(n) * img_cstride * H * W + static_cast<size_t>(yy) * W + xx]) : 0.f;
       }
     float g[16];
     unpack8(dz.ptr[(static_cast<size_t>(n) * dz.planes + dz.plane_off) * H * W + pix], g);
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const T* __restrict_
     if ((threadIdx.x & 31) == 0) atomicAdd(&acc[i], v);
   }
   __syncthreads();
-  if (threadIdx.x < 144) atomicAdd(dw + threadIdx.x, acc[threadIdx.x]);
+  if (threadIdx.x < 144) atomicAdd(dw + (threadIdx.x / 9) * dw_costride + threadIdx.x % 9, acc[threadIdx.x]);
 }
 
 // P8 [N][planes][2H][2W][8] -> 4 phase tensors stacked on the plane axis: dst[N][4*cp][H][W][8], phase = 2*py + px
@@ -687,10 +689,26 @@ extern "C" int abc_conv3x3_c1_wgrad(const void* img, int img_is_u8, const void* 
   P8View v{static_cast<const uint4*>(dz), dz_planes, dz_plane_off};
   const int blocks = 148 * 4;
   if (img_is_u8)
-    conv_c1_wgrad_kernel<uint8_t><<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(img), v, N, H, W, dw);
+    conv_c1_wgrad_kernel<uint8_t><<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(img), v, N, H, W, dw, 1, 9);
   else
-    conv_c1_wgrad_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(img), v, N, H, W, dw);
+    conv_c1_wgrad_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(img), v, N, H, W, dw, 1, 9);
   return launch_check("conv_c1_wgrad_kernel");
+}
+
+// Weight gradient of the general stem (abc_conv3x3_cn): dw fp32 [16][cin][9], one pass over dz per input channel.
+extern "C" int abc_conv3x3_cn_wgrad(const float* img, int cin, const void* dz, int dz_planes, int dz_plane_off, int N, int H, int W,
+                                    float* dw, void* stream) {
+  if (int rc = device_check()) return rc;
+  ABC_REQUIRE(img && dw && N > 0 && H > 0 && W > 0 && cin >= 1 && cin <= 8, "abc_conv3x3_cn_wgrad: bad arguments");
+  if (int rc = p8_check(dz, dz_planes, dz_plane_off, 2, "abc_conv3x3_cn_wgrad(dz)")) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ABC_CUDA(cudaMemsetAsync(dw, 0, static_cast<size_t>(144) * cin * sizeof(float), st));
+  P8View v{static_cast<const uint4*>(dz), dz_planes, dz_plane_off};
+  for (int ci = 0; ci < cin; ++ci) {
+    conv_c1_wgrad_kernel<float><<<148 * 4, 256, 0, st>>>(img + static_cast<size_t>(ci) * H * W, v, N, H, W, dw + ci * 9, cin, cin * 9);
+    if (int rc = launch_check("conv_c1_wgrad_kernel")) return rc;
+  }
+  return ABC_OK;
 }
 
 extern "C" int abc_deinterleave2(const void* src, int src_planes, int src_plane_off, int C, void* dst, int N, int H, int W, void* stream) {

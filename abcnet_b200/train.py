@@ -368,7 +368,7 @@ class TrainEngine:
         L = []
         # first conv handled separately (direct kernel): unit 0
         seq = m.inc1.double_conv
-        L.append(dict(name="inc1.0", conv=seq[0], bn=seq[1], act=1, src=("img", None), src_off=0, cin=1, cout=16, hw=(H, W),
+        L.append(dict(name="inc1.0", conv=seq[0], bn=seq[1], act=1, src=("img", None), src_off=0, cin=m.n_channels, cout=16, hw=(H, W),
                       dst=("a", "inc1.0"), dst_off=0, pool=None, keep=True, first=True))
         L.append(dict(name="inc1.3", conv=seq[3], bn=seq[4], act=1, src=("a", "inc1.0"), src_off=0, cin=16, cout=16, hw=(H, W),
                       dst=("a", "inc1.3"), dst_off=0, pool=None, keep=True))
@@ -415,9 +415,9 @@ class TrainEngine:
         if not x.is_cuda:
             raise RuntimeError("abcnet_b200 training forward needs a CUDA tensor (no CPU fallback)")
         _lib.require_device()
-        if x.dim() != 4 or x.shape[1] != 1 or x.shape[2] % 32 or x.shape[3] % 32:
-            raise ValueError(f"expected [B,1,H,W] with H, W multiples of 32, got {tuple(x.shape)}")
-        u8 = x.dtype in (torch.uint8, torch.bool)
+        if x.dim() != 4 or x.shape[1] != m.n_channels or x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError(f"expected [B,{m.n_channels},H,W] with H, W multiples of 32, got {tuple(x.shape)}")
+        u8 = x.dtype in (torch.uint8, torch.bool) and m.n_channels == 1
         x = x.contiguous().view(torch.uint8) if u8 else x.contiguous().float()
         B, _, H, W = x.shape
         plan = self._plan(H, W)
@@ -448,10 +448,14 @@ class TrainEngine:
             cout = u["cout"]
             z = self.buf("z:" + u["name"], (B, cout // 8, h, w, 8))
             if u.get("first"):                                       # direct kernel, raw conv + bias (BN / ReLU follow)
-                w9 = u["conv"].weight.detach().float().reshape(16, 9).contiguous()
+                w9 = u["conv"].weight.detach().float().reshape(16, m.n_channels * 9).contiguous()
                 bias = u["conv"].bias.detach().float()
-                check(lib.abc_conv3x3_c1_raw(x.data_ptr(), 1 if u8 else 0, w9.data_ptr(), bias.data_ptr(), z.data_ptr(), B, h, w, 2, 0,
-                                             _st()), "abc_conv3x3_c1_raw")
+                if m.n_channels == 1:
+                    check(lib.abc_conv3x3_c1_raw(x.data_ptr(), 1 if u8 else 0, w9.data_ptr(), bias.data_ptr(), z.data_ptr(), B, h, w, 2, 0,
+                                                 _st()), "abc_conv3x3_c1_raw")
+                else:
+                    check(lib.abc_conv3x3_cn(x.data_ptr(), m.n_channels, w9.data_ptr(), bias.data_ptr(), z.data_ptr(), B, h, w, 2, 0, 0,
+                                             _st()), "abc_conv3x3_cn")
             else:
                 src = self._tensor(u["src"], B, H, W, (B, u["cin"] // 8, h, w, 8))
 
@@ -582,10 +586,14 @@ class TrainEngine:
             sink(u["bn"].bias, s1.float())
             sink(u["conv"].bias, torch.zeros(cout, device=dev))
             if u.get("first"):
-                dwf = torch.zeros(144, dtype=torch.float32, device=dev)
-                check(lib.abc_conv3x3_c1_wgrad(sv["x"].data_ptr(), 1 if sv["u8"] else 0, dz.data_ptr(), 2, 0, B, h, w, dwf.data_ptr(), _st()),
-                      "abc_conv3x3_c1_wgrad")
-                sink(u["conv"].weight, dwf.reshape(16, 1, 3, 3))
+                dwf = torch.zeros(144 * m.n_channels, dtype=torch.float32, device=dev)
+                if m.n_channels == 1:
+                    check(lib.abc_conv3x3_c1_wgrad(sv["x"].data_ptr(), 1 if sv["u8"] else 0, dz.data_ptr(), 2, 0, B, h, w, dwf.data_ptr(), _st()),
+                          "abc_conv3x3_c1_wgrad")
+                else:
+                    check(lib.abc_conv3x3_cn_wgrad(sv["x"].data_ptr(), m.n_channels, dz.data_ptr(), 2, 0, B, h, w, dwf.data_ptr(), _st()),
+                          "abc_conv3x3_cn_wgrad")
+                sink(u["conv"].weight, dwf.reshape(16, m.n_channels, 3, 3))
                 continue
             src = self._tensor(u["src"], B, H, W, (B, cin // 8, h, w, 8))
             dwt = wgrad(dz, 0, cout, src, u["src_off"], cin, TAPS3)               # [9][cout][cin]

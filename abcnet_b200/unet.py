@@ -246,9 +246,11 @@ class _LaunchTimer:
 class UNet(nn.Module):
     def __init__(self, in_channels, heads=[1, 21, 5, 1, 4, 2], crop_first=True):
         super().__init__()
-        if in_channels != 1:
-            raise NotImplementedError("abcnet_b200.UNet: only in_channels=1 (binarised images, utils.py:80-81) is built")
-        self.n_channels = in_channels
+        # in_channels = 1: the binarised drawings of the reference's datasets (utils.py:80-81), table-driven stem kernel;
+        # 2..8 real-valued channels (unet.py:127 self-checks in_channels=3): general fp32 stem kernel (abc_conv3x3_cn)
+        if not (1 <= int(in_channels) <= 8):
+            raise ValueError("abcnet_b200.UNet: in_channels must be in 1..8")
+        self.n_channels = int(in_channels)
         self.heads = list(heads)
         # torch >= 1.13 floor-divides the negative crop in unet.py:54-55 -> the FIRST row / column is dropped
         self.crop_first = bool(crop_first)
@@ -324,7 +326,7 @@ class UNet(nn.Module):
         # first conv (1 -> 16): direct kernel, fp32 folded weights [16][9]
         c0, b0 = self.inc1.double_conv[0], self.inc1.double_conv[1]
         w, b = _fold(c0.weight, c0.bias, b0)
-        P["inc1.0"] = (w.reshape(16, 9).contiguous(), b.contiguous())
+        P["inc1.0"] = (w.reshape(16, self.n_channels * 9).contiguous(), b.contiguous())        # [16][cin][9]
         pack3("inc1.3", self.inc1.double_conv[3], self.inc1.double_conv[4])
         for name, holder in (("inc2", self.inc2), ("down1", self.down1.maxpool_conv[1]), ("down2", self.down2.maxpool_conv[1]),
                              ("inc3", self.inc3), ("down3", self.down3.maxpool_conv[1]), ("down4", self.down4.maxpool_conv[1]),
@@ -479,13 +481,18 @@ class UNet(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("abcnet_b200.UNet.forward needs a CUDA tensor (no CPU fallback)")
         _lib.require_device()
-        if x.dim() != 4 or x.shape[1] != 1 or x.shape[2] % 32 or x.shape[3] % 32:
-            raise ValueError(f"expected [B,1,H,W] with H, W multiples of 32, got {tuple(x.shape)}")
+        if x.dim() != 4 or x.shape[1] != self.n_channels or x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError(f"expected [B,{self.n_channels},H,W] with H, W multiples of 32, got {tuple(x.shape)}")
         if self._packed is None or self._packed_key != self._param_key():
             self.prepare()
         P = self._packed
         # fp32 {0,1} images as the reference's DataLoader delivers them, or the same bits as uint8 / bool
-        if x.dtype in (torch.uint8, torch.bool):
+        if self.n_channels != 1:
+            x = x.contiguous().float()
+
+            def first(xp, wp, bp, op, B_, H_, W_, planes, off, st_):
+                return lib.abc_conv3x3_cn(xp, self.n_channels, wp, bp, op, B_, H_, W_, planes, off, 1, st_)
+        elif x.dtype in (torch.uint8, torch.bool):
             x = x.contiguous().view(torch.uint8)
             first = lib.abc_conv3x3_c1_u8
         else:

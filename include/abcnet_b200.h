@@ -58,6 +58,11 @@ ABC_API int abc_conv3x3_c1(const float* img, const float* w, const float* b, voi
  * 4x fewer bytes over PCIe and HBM. */
 ABC_API int abc_conv3x3_c1_u8(const uint8_t* img, const float* w, const float* b, void* out, int N, int H, int W,
                               int out_planes, int out_plane_off, void* stream);
+/* General stem for in_channels = cin in 1..8 real-valued fp32 channels (src/unet.py:77,83 with in_channels != 1; the reference's
+ * self-check builds UNet(in_channels=3), unet.py:127): img fp32 NCHW [N][cin][H][W], w fp32 [16][cin][9], b fp32 [16];
+ * relu = 1: (BatchNorm-folded) conv + ReLU for eval, relu = 0: raw conv + bias for the training pass. Output as above. */
+ABC_API int abc_conv3x3_cn(const float* img, int cin, const float* w, const float* b, void* out, int N, int H, int W,
+                           int out_planes, int out_plane_off, int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 x bf16 -> fp32 in TMEM).
@@ -384,6 +389,9 @@ ABC_API int abc_conv3x3_c1_raw(const void* img, int img_is_u8, const float* w, c
                                int out_planes, int out_plane_off, void* stream);
 /* dw[16][9] of the first 1 -> 16 convolution (img fp32 or uint8). */
 ABC_API int abc_conv3x3_c1_wgrad(const void* img, int img_is_u8, const void* dz, int dz_planes, int dz_plane_off, int N, int H, int W,
+                                 float* dw, void* stream);
+/* Same for the general stem: dw fp32 [16][cin][9] (zeroed by the call). */
+ABC_API int abc_conv3x3_cn_wgrad(const float* img, int cin, const void* dz, int dz_planes, int dz_plane_off, int N, int H, int W,
                                  float* dw, void* stream);
 
 #ifdef __cplusplus

@@ -149,7 +149,7 @@ def records_to_molblock(lists):
 
 
 
-def molecule_graph(lists):
+def molecule_graph(lists, with_positions=True):
     """Canonical, order-free description of the molecule that ``assemble`` builds from one image's lists, or None.
 
     Two record sets with the same graph give the same molecule to RDKit (``generate_smiles.py:115-118`` parses the MOL
@@ -157,12 +157,14 @@ def molecule_graph(lists):
     implicit-H atom set, and the bonds -- as UNORDERED atom pairs for the plain orders 1..4 (a V2000 bond line ``a b o``
     and ``b a o`` describe the same bond) and as ORDERED (begin, end) pairs for the two wedge orders 5 / 6, whose
     direction carries the stereo information. Used to decide whether an omega / omega + 30 flip of an undirected bond
-    (which swaps the two end atoms of that bond, ``img2smiles.py:160-164, 195-212``) changes the molecule: it does not."""
+    (which swaps the two end atoms of that bond, ``img2smiles.py:160-164, 195-212``) changes the molecule: it does not.
+    ``with_positions=False`` drops the drawing coordinates (stride-4 pixel positions / 60 - 1 in the MOL block): the
+    topology alone, which is all a SMILES string encodes for molecules without wedge bonds."""
     r = assemble(lists)
     if r is None:
         return None
     f_types, f_pairs, f_charges, orders, f_pos, implicit = r
-    atoms = tuple((t, int(c), int(p[0]), int(p[1])) for t, c, p in zip(f_types, f_charges, f_pos))
+    atoms = tuple((t, int(c)) + ((int(p[0]), int(p[1])) if with_positions else ()) for t, c, p in zip(f_types, f_charges, f_pos))
     bonds = []
     for (a, b), o in zip(f_pairs, orders):
         o = int(o)

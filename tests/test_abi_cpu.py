@@ -62,8 +62,10 @@ def test_no_cpu_fallback():
     m = abcnet_b200.UNet(1, [1, 14, 3, 2, 1, 360, 60, 60]).eval()
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 32, 32))
-    with pytest.raises(NotImplementedError):
-        abcnet_b200.UNet(3)                                             # only the binarised 1-channel input is built
+    m3 = abcnet_b200.UNet(3, [1, 14]).eval()                               # unet.py:127: the reference's self-check model
+    assert m3.inc1.double_conv[0].weight.shape == (16, 3, 3, 3)
+    with pytest.raises(RuntimeError):
+        m3(torch.zeros(1, 3, 32, 32))
     # product code never imports the oracle
     for root, _, files in os.walk(os.path.join(ROOT, "abcnet_b200")):
         for f in files:

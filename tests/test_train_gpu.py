@@ -277,3 +277,40 @@ def test_train_forward_against_reference_minted_golden(tag, B, H, W, seed):
         rows.append((i, round(r_ours, 4), round(r_emu, 4)))
         assert r_ours <= 3.0 * r_emu + 0.02, f"head {i}: CUDA train forward rel L2 {r_ours} vs bf16-emulated oracle {r_emu}"
     print(f"train-mode forward vs reference-minted golden ({tag}): (head, ours, bf16-emulated oracle) = {rows}")
+
+
+def test_three_channel_stem_forward_and_weight_gradient():
+    """UNet(in_channels=3) (the reference's own self-check, unet.py:122-134) on real-valued input: eval logits against the
+    oracle, and in train mode the stem's activation / weight gradient / BN gradients in situ against fp64 autograd."""
+    import torch.nn.functional as F
+    import abcnet_b200
+    B, H, W, seed = 2, 64, 64, 9
+    sd = unet_ref.make_state_dict(seed=seed, in_channels=3, variant="W1")
+    m = abcnet_b200.UNet(3, HEADS).cuda()
+    m.load_state_dict(sd)
+    x = torch.from_numpy(synth.detrand.uniform(77, (B, 3, H, W), -1.0, 1.0).astype(np.float32))
+    m.eval()
+    outs = [o.float().cpu() for o in m(x.cuda())]
+    with torch.no_grad():
+        ref = unet_ref.forward(x, sd)
+    for i, (o, r) in enumerate(zip(outs, ref)):
+        err, scale = (o - r).abs().max().item(), r.abs().max().item()
+        assert err <= 0.04 * scale + 0.03, f"head {i}: max abs err {err} vs scale {scale}"
+    m.train()
+    m.dropout_p = 0.0
+    outs = m(x.cuda())
+    R = [torch.from_numpy(synth.detrand.uniform(200 + i, tuple(o.shape), -1, 1)) for i, o in enumerate(outs)]
+    sum((o * r.cuda()).sum() for o, r in zip(outs, R)).backward()
+    torch.cuda.synchronize()
+    bufs = m._engine.bufs
+    conv, bn = m.inc1.double_conv[0], m.inc1.double_conv[1]
+    wt = conv.weight.detach().cpu().double().requires_grad_(True)
+    gam = bn.weight.detach().cpu().double().requires_grad_(True)
+    bet = bn.bias.detach().cpu().double().requires_grad_(True)
+    z = _ste(F.conv2d(x.double(), wt, conv.bias.detach().cpu().double(), padding=1))
+    a = _ste(F.relu(F.batch_norm(z, None, None, gam, bet, True, 0.1, 1e-5)))
+    assert _rel(_p8_to_nchw(bufs["a:inc1.0"]), a.detach()) <= 5e-3
+    (a * _p8_to_nchw(bufs["g:a:inc1.0"]).double()).sum().backward()
+    assert conv.weight.grad.shape == (16, 3, 3, 3)
+    assert _rel(conv.weight.grad.cpu(), wt.grad) <= 3e-2
+    assert _rel(bn.weight.grad.cpu(), gam.grad) <= 3e-2 and _rel(bn.bias.grad.cpu(), bet.grad) <= 3e-2
