@@ -25,6 +25,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "p8_device.cuh"
 #include "ptx_sm100.cuh"
 
 namespace abc {
@@ -60,6 +61,10 @@ struct ConvKParams {
   int out_planes, out_plane_off, out_H, out_W, out_sy, out_oy, out_sx, out_ox;
   void* pool_out;
   int pool_planes, pool_plane_off;
+  // fused train-mode BatchNorm statistics (AbcConvDesc.stat_sum / stat_sq): per output channel sum / sum of squares of the
+  // bf16-rounded outputs, accumulated per thread over the CTA's whole tile loop, one fp64 atomic per thread at the end
+  double* stat_sum;
+  double* stat_sq;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -125,11 +130,14 @@ __device__ __forceinline__ uint4 pool_max_bf16x8(uint4 q) {
 // M = 256 instructions for both, and each CTA's epilogue drains its own 128 TMEM lanes. See ptx_sm100.cuh.
 // SWAP: operand-swap mode (AbcConvDesc.swap_mn): M = the 128 output channels of the n-tile (the weight block is the A
 // operand), N = 256 pixels (one 32 x 8 tile per pipeline stage is the B operand); accumulator = [channel][pixel].
-template <int KSTEPS, bool RESIDENT, bool CG2, bool SWAP = false>
+// STATS: the non-swap epilogue of the row-folded 16-channel layers also accumulates the fused BatchNorm statistics (32 extra
+// registers per epilogue thread, hence its own instantiation); the operand-swap epilogue does so behind a runtime flag.
+template <int KSTEPS, bool RESIDENT, bool CG2, bool SWAP = false, bool STATS = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p) {
   static_assert(!(CG2 && RESIDENT), "the CTA-pair variant streams its weights");
   static_assert(!(CG2 && SWAP), "operand swap is a single-CTA mode");
+  static_assert(!(STATS && (SWAP || CG2)), "STATS is the non-swap, single-CTA variant");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = static_cast<int>(warp_id_uniform());   // provably warp-uniform
@@ -449,6 +457,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const uint4* st_r = reinterpret_cast<const uint4*>(stage + i8 * kSwapRowBytes + g8 * 16);  // + row * 8 * kSwapRowBytes / 16
     const bool plane_ok = (n0 + ch0) < p.cout;
     const size_t out_plane_px = static_cast<size_t>(p.out_H) * p.out_W;
+    // fused statistics: this thread's own GEMM row (before the transposition) = (folded row fj_own, channel)
+    const bool do_stats = p.stat_sum != nullptr;
+    const int m_own = q * 32 + lane;
+    const int fj_own = m_own / cpj;
+    float st_s = 0.f, st_q = 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int g = g_first; g < p.num_groups; g += gridDim.x) {
@@ -463,13 +476,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
                      static_cast<size_t>(p.out_oy) * p.out_W + (x * p.out_sx + p.out_ox);
       const bool col_ok = plane_ok && x < p.W;
       const uint32_t tbase = tmem_base + acc * p.acc_cols + (static_cast<uint32_t>(q * 32) << 16) + eh * 128;
+      // statistics: validity of the 8 pixel columns of this tile (bit c: column tx * 8 + c is inside the image)
+      const int x_left = p.W - tx * 8;
+      const uint32_t xmask8 = x_left >= 8 ? 0xffu : ((1u << (x_left > 0 ? x_left : 0)) - 1u);
+      const int yo0 = (ty * 32 + eh * 16) * J + fj_own;
       mbar_wait(bar_acc_full + 8 * acc, acc_phase);
       tc_fence_after();
       auto process = [&](uint32_t (&raw)[16], int it) {
+        uint32_t vmask = 0;
+        if (do_stats)
+          vmask = ((yo0 + (it * 2) * J) < p.H ? xmask8 : 0u) | ((yo0 + (it * 2 + 1) * J) < p.H ? (xmask8 << 8) : 0u);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float t = __uint_as_float(raw[i]) + bias;
-          st_w[i * (kSwapRowBytes / 2)] = __float2bfloat16_rn(fmaxf(t, t * slope));
+          const __nv_bfloat16 hv = __float2bfloat16_rn(fmaxf(t, t * slope));
+          st_w[i * (kSwapRowBytes / 2)] = hv;
+          if (do_stats && ((vmask >> i) & 1u)) {
+            const float r = __bfloat162float(hv);
+            st_s += r;
+            st_q = fmaf(r, r, st_q);
+          }
         }
         __syncwarp();
 #pragma unroll
@@ -499,6 +525,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
         acc_phase ^= 1;
       }
     }
+    if (do_stats) {
+      const int ch = n0 + (m_own - fj_own * cpj);
+      if (ch < p.cout) {
+        atomicAdd(p.stat_sum + ch, static_cast<double>(st_s));
+        atomicAdd(p.stat_sq + ch, static_cast<double>(st_q));
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (8 warps: two per TMEM lane quarter)
     // The accumulators of one group are mt * n_tile contiguous TMEM columns. They are drained in 16-column units, two
@@ -520,6 +553,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const size_t pool_plane_px = static_cast<size_t>(ph) * pw;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float sacc[STATS ? 16 : 1], qacc[STATS ? 16 : 1];       // fused statistics of the 16 channels (cout == 16, row-folded)
+#pragma unroll
+    for (int i = 0; i < (STATS ? 16 : 1); ++i) sacc[i] = qacc[i] = 0.f;
     const uint32_t acc_empty_base = CG2 ? mapa_cluster(bar_acc_empty, 0) : bar_acc_empty;   // the leader's barriers
     for (int gp = g_first; gp < p.num_groups; gp += gridDim.x) {
       const int g = CG2 ? min(gp + static_cast<int>(cta_rank), p.num_groups - 1) : gp;
@@ -571,6 +607,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
           }
           if (p.out_mode == 0) {
             uint4 q0 = pack8_bf16(v), q1 = pack8_bf16(v + 8);
+            if constexpr (STATS) {
+              if (valid) {
+                float r[16];
+                unpack8u(q0, r);
+                unpack8u(q1, r + 8);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  sacc[i] += r[i];
+                  qacc[i] = fmaf(r[i], r[i], qacc[i]);
+                }
+              }
+            }
             if (p.out != nullptr && valid) {
               uint4* o = reinterpret_cast<uint4*>(p.out) + (out_pl0 + 2 * b16) * out_plane_px + out_px0 +
                          static_cast<size_t>(j * p.out_sy) * p.out_W + ti * 8 * p.out_sx;
@@ -651,6 +699,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
       if (++acc == p.nacc) {
         acc = 0;
         acc_phase ^= 1;
+      }
+    }
+    if constexpr (STATS) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = sacc[i], b = qacc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0 && n0 + i < p.cout) {
+          atomicAdd(p.stat_sum + n0 + i, static_cast<double>(a));
+          atomicAdd(p.stat_sq + n0 + i, static_cast<double>(b));
+        }
       }
     }
   }
@@ -875,6 +938,21 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.out_H = d->out_H; p.out_W = d->out_W;
   p.out_sy = d->out_sy; p.out_oy = d->out_oy; p.out_sx = d->out_sx; p.out_ox = d->out_ox;
   p.pool_out = d->pool_out; p.pool_planes = d->pool_planes; p.pool_plane_off = d->pool_plane_off;
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream_);
+  // fused BatchNorm statistics (training forward)
+  const bool stats = d->stat_sum != nullptr || d->stat_sq != nullptr;
+  if (stats) {
+    ABC_REQUIRE(d->stat_sum && d->stat_sq, "abc_conv_igemm: stat_sum and stat_sq go together");
+    ABC_REQUIRE(d->out_mode == 0 && d->out != nullptr && d->pool_out == nullptr && !want_pair,
+                "abc_conv_igemm: fused statistics need a plain P8 output");
+    ABC_REQUIRE(swap || (fold == 4 && d->cout == 16 && d->n_tile == 64 && d->cin == 16),
+                "abc_conv_igemm: fused statistics are built for operand-swap launches and the row-folded 16 -> 16 layers "
+                "(use abc_bn_stats otherwise)");
+    ABC_CUDA(cudaMemsetAsync(d->stat_sum, 0, d->cout * sizeof(double), st_));
+    ABC_CUDA(cudaMemsetAsync(d->stat_sq, 0, d->cout * sizeof(double), st_));
+    p.stat_sum = d->stat_sum;
+    p.stat_sq = d->stat_sq;
+  }
 
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) {
@@ -908,6 +986,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
                                  {nullptr, conv_igemm_kernel<1, true, false, true>, conv_igemm_kernel<2, true, false, true>,
                                   conv_igemm_kernel<3, true, false, true>, conv_igemm_kernel<4, true, false, true>}};
   KernelFn pair_kernel = conv_igemm_kernel<4, false, true>;
+  KernelFn stats_kernel = conv_igemm_kernel<1, true, false, false, true>;      // row-folded 16 -> 16 with fused statistics
   static PerDeviceOnce attr_once;
   ABC_CUDA(attr_once.run([&]() -> cudaError_t {
     for (int r = 0; r < 2; ++r)
@@ -915,6 +994,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
         if (cudaError_t e = cudaFuncSetAttribute(kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) return e;
         if (cudaError_t e = cudaFuncSetAttribute(swap_kernels[r][k], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) return e;
       }
+    if (cudaError_t e = cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget)) return e;
     return cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   }));
   const int ksteps = p.kp / 2;
@@ -948,6 +1028,11 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   }
   if (gx > p.num_groups) gx = p.num_groups;
   dim3 grid(gx, n_tiles, 1);
-  (swap ? swap_kernels : kernels)[p.resident_b ? 1 : 0][ksteps]<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream_)>>>(tmap, p);
+  KernelFn fn = (swap ? swap_kernels : kernels)[p.resident_b ? 1 : 0][ksteps];
+  if (stats && !swap) {
+    ABC_REQUIRE(p.resident_b && ksteps == 1, "abc_conv_igemm: internal: fused statistics variant");
+    fn = stats_kernel;
+  }
+  fn<<<grid, kThreads, smem_bytes, st_>>>(tmap, p);
   return launch_check(swap ? "conv_igemm_kernel<swap>" : "conv_igemm_kernel");
 }

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import itertools
+import os
 
 import torch
 
@@ -159,7 +160,14 @@ class PackArena:
                 self._gather(kind, 0, self.used[kind])
 
 
-def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_scale=(1, 0, 1, 0), pool=None, pool_plane_off=0):
+def can_fuse_stats(pk, dst):
+    """Fused BatchNorm statistics exist in the operand-swap epilogue and in the row-folded 16 -> 16 epilogue (AbcConvDesc.stat_sum)."""
+    return use_swap(pk, 0, dst, None) or (pk.fold == 4 and not pk.fold_swap and pk.cout == 16 and pk.cin == 16 and not pk.pair)
+
+
+def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_scale=(1, 0, 1, 0), pool=None, pool_plane_off=0,
+         stats=None):
+    """stats: (sum, sumsq) fp64 [cout] tensors -> fused BatchNorm statistics of the output (AbcConvDesc.stat_sum / stat_sq)."""
     d = AbcConvDesc()
     N, in_planes, H, W, _ = src.shape
     d.in_, d.N, d.H, d.W = src.data_ptr(), N, H, W
@@ -185,6 +193,8 @@ def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_sca
         d.out_H, d.out_W = H, W
     if pool is not None:
         d.pool_out, d.pool_planes, d.pool_plane_off = pool.data_ptr(), pool.shape[1], pool_plane_off
+    if stats is not None:
+        d.stat_sum, d.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
     with _timed(f"conv {pk.cin}->{pk.cout} t{len(pk.taps)} @{H}x{W} nt{pk.n_tile}"):
         check(lib.abc_conv_igemm(C.byref(d), _st()), "abc_conv_igemm")
 
@@ -291,7 +301,6 @@ class TrainEngine:
 
     def _sync_arena(self):
         """Called at the start of every forward: (re)build the arena when the parameter storage changed, else refresh it."""
-        import os
         if os.environ.get("ABCNET_NO_ARENA"):
             self.arena, self._packs = None, {}
             return
@@ -311,13 +320,17 @@ class TrainEngine:
         return t
 
     # ------------------------------------------------------------------ layer helpers
-    def _bn_forward(self, key, z, z_off, Cc, bn_params, act, out, out_off, pool, drop_p, seed):
+    def _stat_bufs(self, key, Cc):
+        return self.buf(key + ".sum", (Cc,), torch.float64), self.buf(key + ".sq", (Cc,), torch.float64)
+
+    def _bn_forward(self, key, z, z_off, Cc, bn_params, act, out, out_off, pool, drop_p, seed, have_stats=False):
+        """have_stats: the producing convolution already accumulated the batch statistics into ``_stat_bufs(key)``."""
         N, _, H, W, _ = z.shape
         dev = z.device
         gamma, beta, rmean, rvar = bn_params
-        s = self.buf(key + ".sum", (Cc,), torch.float64)
-        q = self.buf(key + ".sq", (Cc,), torch.float64)
-        check(lib.abc_bn_stats(z.data_ptr(), N, H, W, z.shape[1], z_off, Cc, s.data_ptr(), q.data_ptr(), _st()), "abc_bn_stats")
+        s, q = self._stat_bufs(key, Cc)
+        if not have_stats:
+            check(lib.abc_bn_stats(z.data_ptr(), N, H, W, z.shape[1], z_off, Cc, s.data_ptr(), q.data_ptr(), _st()), "abc_bn_stats")
         st = [self.buf(key + f".st{i}", (Cc,), torch.float32) for i in range(4)]
         check(lib.abc_bn_finalize(s.data_ptr(), q.data_ptr(), Cc, float(N * H * W), gamma.data_ptr(), beta.data_ptr(), 1e-5, 0.1,
                                   rmean.data_ptr(), rvar.data_ptr(), *[t.data_ptr() for t in st], _st()), "abc_bn_finalize")
@@ -334,10 +347,12 @@ class TrainEngine:
         check(lib.abc_bn_act(C.byref(d), _st()), "abc_bn_act")
         return st
 
+    def _bwd_sum_bufs(self, key, Cc):
+        return self.buf(key + ".s1", (Cc,), torch.float64), self.buf(key + ".s2", (Cc,), torch.float64)
+
     def _bn_backward(self, key, z, Cc, st, act, dA, dA_off, dP, dz, drop_p, seed):
         N, _, H, W, _ = z.shape
-        s1 = self.buf(key + ".s1", (Cc,), torch.float64)
-        s2 = self.buf(key + ".s2", (Cc,), torch.float64)
+        s1, s2 = self._bwd_sum_bufs(key, Cc)
         d = AbcBnActBwdDesc()
         d.z, d.z_planes, d.z_plane_off = z.data_ptr(), z.shape[1], 0
         if dA is not None:
@@ -428,7 +443,8 @@ class TrainEngine:
         if seed_t is None:
             seed_t = self.bufs["seed"] = torch.full((1,), _initial_dropout_seed(), dtype=torch.int64, device=x.device)
         seed_t.add_(0x5DEECE66D)
-        sv = self.saved = dict(x=x, u8=u8, B=B, H=H, W=W, plan=plan, units={}, seed=seed_t)
+        fuse = bool(getattr(m, "fuse_bn", True)) and not os.environ.get("ABCNET_NO_BN_FUSE")
+        sv = self.saved = dict(x=x, u8=u8, B=B, H=H, W=W, plan=plan, units={}, seed=seed_t, fuse=fuse)
         for u in plan:
             h, w = u["hw"]
             if "up" in u:                                            # up-sampling conv: 4 sub-pixel phases, bias, no BN
@@ -447,6 +463,7 @@ class TrainEngine:
                 continue
             cout = u["cout"]
             z = self.buf("z:" + u["name"], (B, cout // 8, h, w, 8))
+            fused_stats = False
             if u.get("first"):                                       # direct kernel, raw conv + bias (BN / ReLU follow)
                 w9 = u["conv"].weight.detach().float().reshape(16, m.n_channels * 9).contiguous()
                 bias = u["conv"].bias.detach().float()
@@ -464,12 +481,14 @@ class TrainEngine:
                     mats = torch.stack([wt[:, :, dy + 1, dx + 1] for dy, dx in TAPS3])
                     js = swap_fold_for(cin, cout)                      # train-mode convolutions write plain maps (pooling is in bn_act)
                     return Packed(mats, self._w(cv.bias), TAPS3, fold=js or row_fold_for(cin, cout), fold_swap=bool(js))
-                conv(self._pk(u["name"], make), src, u["src_off"], z)
+                pk = self._pk(u["name"], make)
+                fused_stats = fuse and can_fuse_stats(pk, z)
+                conv(pk, src, u["src_off"], z, stats=self._stat_bufs("bn:" + u["name"], cout) if fused_stats else None)
             dst = self._tensor(u["dst"], B, H, W, (B, cout // 8, h, w, 8)) if u["keep"] or u["dst"][0] == "cat" else None
             pool = self._tensor(u["pool"], B, H, W) if u["pool"] else None
             bn = u["bn"]
             st = self._bn_forward("bn:" + u["name"], z, 0, cout, (bn.weight, bn.bias, bn.running_mean, bn.running_var), 1,
-                                  dst, u["dst_off"], pool, 0.0, None)
+                                  dst, u["dst_off"], pool, 0.0, None, have_stats=fused_stats)
             bn.num_batches_tracked += 1
             sv["units"][u["name"]] = dict(z=z, st=st)
         # heads: fused conv1 (N = 128 * heads) -> BN -> LeakyReLU -> Dropout -> per-head 1x1
@@ -481,15 +500,17 @@ class TrainEngine:
             w1 = torch.cat([self._w(om.conv1.weight) for om in m.out_modules], 0)
             b1 = torch.cat([self._w(om.conv1.bias) for om in m.out_modules])
             return Packed(torch.stack([w1[:, :, dy + 1, dx + 1] for dy, dx in TAPS3]), b1, TAPS3,
-                          n_tile=256 if (128 * nh) % 256 == 0 else 128)
-        conv(self._pk("heads.conv1", make_h1), trunk, 0, zh)
+                          n_tile=256 if ((128 * nh) % 256 == 0 and not os.environ.get("ABCNET_TRAIN_HEADS_SWAP")) else 128)
+        pk_h1 = self._pk("heads.conv1", make_h1)
+        h1_stats = fuse and can_fuse_stats(pk_h1, zh)
+        conv(pk_h1, trunk, 0, zh, stats=self._stat_bufs("bn:heads", 128 * nh) if h1_stats else None)
         gam = torch.cat([om.bn.weight.detach() for om in m.out_modules]).float().contiguous()
         bet = torch.cat([om.bn.bias.detach() for om in m.out_modules]).float().contiguous()
         rme = torch.cat([om.bn.running_mean for om in m.out_modules]).float().contiguous()
         rva = torch.cat([om.bn.running_var for om in m.out_modules]).float().contiguous()
         hid = self.buf("a:hid", (B, 16 * nh, H // 4, W // 4, 8))
         p_drop = float(m.dropout_p)
-        st = self._bn_forward("bn:heads", zh, 0, 128 * nh, (gam, bet, rme, rva), 2, hid, 0, None, p_drop, sv["seed"])
+        st = self._bn_forward("bn:heads", zh, 0, 128 * nh, (gam, bet, rme, rva), 2, hid, 0, None, p_drop, sv["seed"], have_stats=h1_stats)
         for i, om in enumerate(m.out_modules):                       # write the updated running statistics back
             om.bn.running_mean.copy_(rme[128 * i:128 * (i + 1)])
             om.bn.running_var.copy_(rva[128 * i:128 * (i + 1)])

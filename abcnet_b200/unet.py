@@ -276,6 +276,7 @@ class UNet(nn.Module):
         self.timing = None        # set to a list to collect (layer name, start event, end event) per launch group
         self.dropout_p = 0.2      # nn.Dropout(0.2) of OutConv (unet.py:69); train mode only
         self.grad_buckets = None  # optional abcnet_b200.ddp.GradBuckets: gradients are accumulated into its buckets
+        self.fuse_bn = True       # training pass: BatchNorm statistics / backward reductions fused into the conv epilogues
         self._engine = None
 
     # ------------------------------------------------------------------ checkpoints

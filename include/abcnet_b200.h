@@ -135,6 +135,11 @@ typedef struct AbcConvDesc {
    * are then (folded row j, channel) -- weight pack rows ordered j * cout + co instead of row_fold's (16-channel block, j,
    * channel) order, bias[j * cout + co] = bias of channel co -- and a pixel column stands for J vertically adjacent pixels. */
   int swap_mn;
+  /* Optional fused train-mode BatchNorm statistics (src/unet.py:13,16,67 in train() mode): per output channel the sum and sum
+   * of squares of the bf16-rounded outputs, fp64 [cout], zeroed by the call. Built for swap_mn launches and for the row-folded
+   * 16 -> 16 layers (row_fold = 4, cin = cout = 16); other layers use abc_bn_stats. Replaces one full read of the conv output. */
+  double* stat_sum;
+  double* stat_sq;
 } AbcConvDesc;
 
 ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);

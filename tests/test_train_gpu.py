@@ -55,6 +55,7 @@ def test_train_step_in_situ_layer_parity():
     import torch.nn.functional as F
     B, H, W, seed = 2, 64, 64, 5
     m, sd, x = _setup(seed, B, H, W)
+    m.fuse_bn = False          # this test reads the dA buffers; with the fused reduction they hold dA * act' (checked separately below)
     outs = m(x.cuda())
     R = [torch.from_numpy(synth.detrand.uniform(100 + i, tuple(o.shape), -1, 1)) for i, o in enumerate(outs)]
     sum((o * r.cuda()).sum() for o, r in zip(outs, R)).backward()
@@ -314,3 +315,40 @@ def test_three_channel_stem_forward_and_weight_gradient():
     assert conv.weight.grad.shape == (16, 3, 3, 3)
     assert _rel(conv.weight.grad.cpu(), wt.grad) <= 3e-2
     assert _rel(bn.weight.grad.cpu(), gam.grad) <= 3e-2 and _rel(bn.bias.grad.cpu(), bet.grad) <= 3e-2
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (3, 96, 160)])
+def test_fused_batchnorm_statistics_match_separate_pass(B, H, W):
+    """The BatchNorm batch statistics accumulated in the conv epilogues (AbcConvDesc.stat_sum / stat_sq: operand-swap launches
+    and the row-folded 16 -> 16 layers) against abc_bn_stats run on the SAME stored conv output: per channel sum and sum of
+    squares equal up to fp32 summation order. Partial tiles included (96 x 160 is not a multiple of the 32 / 64 / 128-row swap
+    tiles at every level; the deepest maps are narrower than one 8-pixel tile). An end-to-end comparison of the two modes would
+    only measure train-mode BatchNorm's amplification of last-bit differences (see test_train_step_in_situ_layer_parity)."""
+    import ctypes as C
+    from abcnet_b200 import _lib
+    m, sd, x = _setup(7, B, H, W)
+    assert m.fuse_bn
+    m(x.cuda())
+    torch.cuda.synchronize()
+    eng = m._engine
+    st = torch.cuda.current_stream().cuda_stream
+    fused, checked = 0, 0
+    for u in eng.saved["plan"]:
+        if "up" in u or u.get("first"):
+            continue
+        z = eng.saved["units"][u["name"]]["z"]
+        got_s, got_q = [t.clone() for t in eng._stat_bufs("bn:" + u["name"], u["cout"])]
+        want_s, want_q = torch.zeros_like(got_s), torch.zeros_like(got_q)
+        N, planes, h, w, _ = z.shape
+        _lib.check(_lib.lib.abc_bn_stats(z.data_ptr(), N, h, w, planes, 0, u["cout"], want_s.data_ptr(), want_q.data_ptr(), st))
+        torch.cuda.synchronize()
+        checked += 1
+        tol_s = 1e-5 * float(want_q.sqrt().max() * (N * h * w) ** 0.5) + 1e-6
+        assert (got_s - want_s).abs().max().item() <= tol_s, (u["name"], (got_s - want_s).abs().max().item(), tol_s)
+        assert _rel(got_q.cpu(), want_q.cpu()) <= 1e-5, (u["name"], _rel(got_q.cpu(), want_q.cpu()))
+    # which launches carried the statistics: every cout <= 128 layer except the three 16 -> 16 ... all of them here
+    from abcnet_b200.train import can_fuse_stats
+    fused = sum(1 for k, pk in eng._packs.items() if not k.endswith(".dgrad") and "heads" not in k and ".up." not in k
+                and can_fuse_stats(pk, object()))
+    print(f"fused BatchNorm statistics verified on {checked} conv units ({fused} of them accumulated in the conv epilogue)")
+    assert checked >= 20 and fused >= 14

@@ -8,9 +8,16 @@
 Every rank takes a contiguous range of the global image list (abcnet_b200.shard.shard_bounds), runs U-Net forward + decode
 on it in batches, assembles each image's records into MOL-block text with the native host assembler while the GPU works on
 the next batch, and hashes the texts. There is NO data-path collective: only one 32-byte digest per batch and a molecule
-count are gathered at the end (shard.gather_results). Image g of the global set is deterministic -- image g % 64 of a seeded
-pool, rolled by (g // 64) % W pixels -- so the combined digest must not depend on the number of GPUs: run with N = 1 and
+count are gathered at the end (shard.gather_results). Image g of the global set is deterministic -- image g % P of a seeded
+pool, rolled by (g // P) % W pixels -- so the combined digest must not depend on the number of GPUs: run with N = 1 and
 N = 2 and compare "digest". Rank 0 prints one JSON line.
+
+--train-steps K (K > 0): instead of random-init weights, rank 0 first trains the network for K iterations on labelled
+pseudo-molecule drawings (synthdata.molecules; labels -> abcnet_b200.parse_labels -> TargetRasteriser, i.e. the product's own
+target path) and broadcasts the weights once (setup, not data path); the image pool is then 1024 pseudo-molecule drawings.
+--dump-subset M: rank 0 writes gpurun_out/shard_subset.pt = {state_dict, MOL-block texts of global images [0, M)}; the CPU
+oracle check of that subset (exact match vs the fp32 reference path, BASELINE configs[2]) is tests/shard_subset_check.py,
+which needs no GPU and is run in the build container.
 """
 import argparse
 import hashlib
@@ -28,11 +35,34 @@ from abcnet_b200 import shard  # noqa: E402
 import synthdata  # noqa: E402  (deterministic synthetic weights / images; the oracle is not used here)
 
 
+def train_on_pool(model, pool, labels, steps, dev, batch=16, n_train=256):
+    """A short training run with the product path only: labels -> label strings -> parse_labels -> TargetRasteriser (GPU) ->
+    TrainStep (forward + 8 losses + backward + fused Adam as one CUDA graph). Schedule as in tests/test_trained_gpu.py."""
+    from synthdata import molecules
+    model.train()
+    lr = torch.tensor(6e-4, device=dev)
+    opt = abcnet_b200.make_optimizer(model, lr=lr, capturable=True)
+    step = abcnet_b200.TrainStep(model, opt, class_weights=True, use_graph=True)
+    rast = abcnet_b200.TargetRasteriser(batch, 128, 128, device=dev)
+    parsed = [abcnet_b200.parse_labels(*molecules.label_strings(labels[i])) for i in range(n_train)]
+    nb = n_train // batch
+    for it in range(steps):
+        b = it % nb
+        if it == (steps * 5) // 8:
+            lr.fill_(2.5e-4)
+        tg = rast(parsed[b * batch:(b + 1) * batch])
+        step(pool[b * batch:(b + 1) * batch].contiguous(), tg)
+    torch.cuda.synchronize()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=102400)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--sparse", action="store_true", help="SparseHeadsPipeline instead of dense heads + PeakDecoder")
+    ap.add_argument("--train-steps", type=int, default=0, help="train on pseudo-molecules first (rank 0) and broadcast the weights")
+    ap.add_argument("--dump-subset", type=int, default=0, help="write weights + MOL blocks of the first M images to gpurun_out/")
+    ap.add_argument("--weights", default="", help="load this state_dict (.pt) instead of training / random init")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -44,21 +74,40 @@ def main():
     B = args.batch
     total = args.images // (B * world) * (B * world)   # whole batches per rank: the batch ranges (hence the digest) do not depend on N
     heads = list(synthdata.V2_HEADS)
-    model = abcnet_b200.UNet(1, heads).to(dev).eval()
-    model.load_state_dict(synthdata.make_state_dict(seed=0, variant="W1"))
-    pool = torch.from_numpy(synthdata.binary_images(1000, 64, 512, 512, 0.05)).to(dev)
+    model = abcnet_b200.UNet(1, heads).to(dev)
+    trained = args.train_steps > 0 or bool(args.weights)
+    if trained:
+        from synthdata import molecules
+        P = 1024
+        imgs, labels = molecules.pseudo_molecules(7, P, 512, 512)
+        pool = torch.from_numpy(imgs).to(dev)
+        if args.weights:
+            model.load_state_dict(torch.load(args.weights, map_location=dev))
+        else:
+            model.load_state_dict(synthdata.make_state_dict(seed=11, variant="W0"))
+            if rank == 0:
+                train_on_pool(model, pool, labels, args.train_steps, dev)
+            if world > 1:                              # one broadcast of the weights (multi_gpu_train2.py:89 does the same at start-up)
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, 0)
+        model.eval()
+    else:
+        P = 64
+        model.eval()
+        model.load_state_dict(synthdata.make_state_dict(seed=0, variant="W1"))
+        pool = torch.from_numpy(synthdata.binary_images(1000, P, 512, 512, 0.05)).to(dev)
+        with torch.no_grad():                          # same calibration of the centre / omega biases as bench.py
+            outs = model(pool[:8].contiguous())
+            for k in (0, 4, 7):
+                model.out_modules[k].conv2.bias += -1.0 - torch.quantile(outs[k].flatten()[:4_000_000].float(), 0.997)
     W = pool.shape[-1]
-    with torch.no_grad():                              # same calibration of the centre / omega biases as bench.py
-        outs = model(pool[:8].contiguous())
-        for k in (0, 4, 7):
-            model.out_modules[k].conv2.bias += -1.0 - torch.quantile(outs[k].flatten()[:4_000_000].float(), 0.997)
     cols = torch.arange(W, device=dev)
 
     def make_batch(a, b):
         g = torch.arange(a, b, device=dev)
-        shift = (g // 64) % W
+        shift = (g // P) % W
         idx = (cols[None, :] - shift[:, None]) % W                                   # [n, W] source column of every output column
-        x = pool[g % 64]                                                             # [n, 1, H, W]
+        x = pool[g % P]                                                              # [n, 1, H, W]
         x = torch.take_along_dim(x, idx[:, None, None, :].expand(-1, 1, x.shape[2], -1), dim=3)
         if b - a < B:                                                                # pad the last batch of the shard
             x = torch.cat([x, x.new_zeros((B - (b - a),) + tuple(x.shape[1:]))])
@@ -72,12 +121,16 @@ def main():
     lo, hi = shard.shard_bounds(total, rank, world)
     ranges = list(shard.batches(lo, hi, B))
     digests, n_mol = [], 0
+    subset = {}
 
     def finish(i):
         nonlocal n_mol
         a, b = ranges[i]
         sinks[i % 2].wait(B)
         texts = sinks[i % 2].molblocks(B, max(1, (os.cpu_count() or 1) // world))[:b - a]
+        for g_, t_ in zip(range(a, b), texts):
+            if g_ < args.dump_subset:
+                subset[g_] = t_
         h = hashlib.blake2b(digest_size=32)
         for t in texts:
             h.update(b"\0" if t is None else t.encode())
@@ -117,6 +170,12 @@ def main():
         dist.all_gather_object(parts, (digests, n_mol))
     else:
         parts = [(digests, n_mol)]
+    if rank == 0 and args.dump_subset:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        torch.save({"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+                    "molblocks": [subset.get(g_) for g_ in range(min(args.dump_subset, total // world))],
+                    "pool": P, "seed": 7, "trained": trained, "sparse": bool(args.sparse)},
+                   os.path.join(ROOT, "gpurun_out", "shard_subset.pt"))
     if rank == 0:
         allb = sorted(d for p, _ in parts for d in p)
         h = hashlib.blake2b(digest_size=16)
@@ -126,7 +185,8 @@ def main():
             h.update(f"{a}:{d};".encode())
         print(json.dumps({"tool": "shard_infer", "images": total, "n_gpus": world, "batch": B, "sparse_heads": bool(args.sparse),
                           "seconds": dt, "images_per_s": total / dt, "molecules": int(sum(n for _, n in parts)),
-                          "batches": len(allb), "digest": h.hexdigest(),
+                          "batches": len(allb), "digest": h.hexdigest(), "weights": "trained on pseudo-molecules" if trained else "random init, calibrated",
+                          "subset_dumped": int(args.dump_subset),
                           "what": "forward + decode + native MOL-block assembly per image, sharded by contiguous image ranges, "
                                   "no data-path collective; digest over all MOL-block texts in global image order"}))
     if world > 1:
