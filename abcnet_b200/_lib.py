@@ -19,6 +19,7 @@ EXPORTS = (
     "abc_bn_stats", "abc_bn_finalize", "abc_bn_act", "abc_bn_act_backward", "abc_nchw_to_p8", "abc_channel_sum",
     "abc_nchw_to_p8_ex", "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
     "abc_heads_fused", "abc_heads_fused_pack_sizes", "abc_gather_pack", "abc_adam_step", "abc_adam_chunk_elems", "abc_assemble_molblocks", "abc_gather_patches", "abc_rasterise_targets",
+    "abc_unet_wpack_bytes", "abc_unet_workspace_bytes", "abc_unet_create", "abc_unet_forward_infer", "abc_unet_destroy",
 )
 
 
@@ -36,8 +37,16 @@ class AbcConvDesc(C.Structure):
         ("pool_out", C.c_void_p), ("pool_planes", C.c_int), ("pool_plane_off", C.c_int),
         ("k_segments", C.c_int), ("seg_tap0", C.c_int * 4), ("seg_ntaps", C.c_int * 4),
         ("row_fold", C.c_int), ("cta_pair", C.c_int), ("swap_mn", C.c_int),
-        ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p),
+        ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p), ("subpixel", C.c_int),
     ]
+
+
+class AbcUNetConfig(C.Structure):
+    _fields_ = [("in_channels", C.c_int), ("n_heads", C.c_int), ("heads", C.c_int * 16), ("crop_first", C.c_int)]
+
+
+class AbcNamedTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_int64)]
 
 
 class AbcAtomRec(C.Structure):
@@ -168,6 +177,13 @@ def _load():
     lib.abc_adam_step.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp, vp, vp]
     lib.abc_rasterise_targets.argtypes = [C.POINTER(AbcTargetsDesc), vp]
     lib.abc_gather_patches.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci, vp, vp]
+    lib.abc_unet_wpack_bytes.restype = C.c_int64
+    lib.abc_unet_wpack_bytes.argtypes = [C.POINTER(AbcUNetConfig)]
+    lib.abc_unet_workspace_bytes.restype = C.c_int64
+    lib.abc_unet_workspace_bytes.argtypes = [C.POINTER(AbcUNetConfig), ci, ci, ci]
+    lib.abc_unet_create.argtypes = [C.POINTER(AbcUNetConfig), C.POINTER(AbcNamedTensor), ci, vp, C.c_int64, vp, C.POINTER(vp)]
+    lib.abc_unet_forward_infer.argtypes = [vp, vp, ci, ci, ci, ci, vp, C.c_int64, C.POINTER(vp), ci, vp]
+    lib.abc_unet_destroy.argtypes = [vp]
     lib.abc_assemble_molblocks.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, ci, ci, vp, C.c_int64, vp]
     return lib
 

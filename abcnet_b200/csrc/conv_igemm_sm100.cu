@@ -61,6 +61,7 @@ struct ConvKParams {
   int out_planes, out_plane_off, out_H, out_W, out_sy, out_oy, out_sx, out_ox;
   void* pool_out;
   int pool_planes, pool_plane_off;
+  int subpixel;                              // channels per sub-pixel phase (AbcConvDesc.subpixel), 0 = off
   // fused train-mode BatchNorm statistics (AbcConvDesc.stat_sum / stat_sq): per output channel sum / sum of squares of the
   // bf16-rounded outputs, accumulated per thread over the CTA's whole tile loop, one fp64 atomic per thread at the end
   double* stat_sum;
@@ -182,12 +183,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
   }
   for (int i = threadIdx.x; i < p.n_tile; i += kThreads) bias_s[i] = p.bias[blockIdx.y * p.n_tile + i];
   uint32_t* utab = reinterpret_cast<uint32_t*>(smem + 800);   // [<= 32] per-unit constants of the epilogue
+  uint32_t* utab2 = reinterpret_cast<uint32_t*>(smem + 928);  // [<= 16] sub-pixel mode: (output plane of the unit) << 16 | pixel offset
   if (threadIdx.x < ((p.mt * p.n_tile) >> 4)) {
     const int col = threadIdx.x << 4;
     const int ti = col / p.n_tile;
     const int ul = (col - ti * p.n_tile) >> 4;               // 16-column unit within the tile = bias unit
     const int b16 = ul / p.fold;
     utab[threadIdx.x] = static_cast<uint32_t>(ti) | (ul << 8) | (b16 << 16) | ((ul - b16 * p.fold) << 24);
+    if (p.subpixel > 0 && threadIdx.x < 16) {
+      // GEMM column c = phase * subpixel + channel: the unit goes to output pixel (2y + py, 2x + px), plane channel / 8
+      const int c0 = blockIdx.y * p.n_tile + (b16 << 4);
+      const int ph = c0 / p.subpixel, chn = c0 - ph * p.subpixel;
+      utab2[threadIdx.x] = (static_cast<uint32_t>(chn >> 3) << 16) | static_cast<uint32_t>((ph >> 1) * p.out_W + (ph & 1));
+    }
   }
   tc_fence_before();
   if (CG2) cluster_sync_all();
@@ -620,8 +628,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
               }
             }
             if (p.out != nullptr && valid) {
-              uint4* o = reinterpret_cast<uint4*>(p.out) + (out_pl0 + 2 * b16) * out_plane_px + out_px0 +
-                         static_cast<size_t>(j * p.out_sy) * p.out_W + ti * 8 * p.out_sx;
+              uint4* o;
+              if (p.subpixel > 0) {
+                const uint32_t t2 = utab2[u];
+                o = reinterpret_cast<uint4*>(p.out) +
+                    (static_cast<size_t>(n) * p.out_planes + p.out_plane_off + (t2 >> 16)) * out_plane_px + out_px0 + (t2 & 0xffffu) +
+                    ti * 8 * p.out_sx;
+              } else {
+                o = reinterpret_cast<uint4*>(p.out) + (out_pl0 + 2 * b16) * out_plane_px + out_px0 +
+                    static_cast<size_t>(j * p.out_sy) * p.out_W + ti * 8 * p.out_sx;
+              }
               o[0] = q0;
               if (two) o[out_plane_px] = q1;
             }
@@ -824,6 +840,18 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
       ABC_REQUIRE(d->out_plane_off >= 0 && d->out_plane_off + (d->cout + 7) / 8 <= d->out_planes,
                   "abc_conv_igemm: planar fp32 output plane range");
   }
+  const int subpixel = d->subpixel > 0 ? d->subpixel : 0;
+  if (subpixel) {
+    // four sub-pixel phases of a stride-2 transposed convolution as blocks of the GEMM N axis (see the header)
+    ABC_REQUIRE(d->out_mode == 0 && d->out != nullptr && d->pool_out == nullptr && !swap && fold == 1 && !d->cta_pair,
+                "abc_conv_igemm: subpixel needs a plain P8 output without pool / swap / fold / pair");
+    ABC_REQUIRE(subpixel % 16 == 0 && d->cout == 4 * subpixel && d->out_sy == 2 && d->out_sx == 2,
+                "abc_conv_igemm: subpixel needs cout == 4 * subpixel (multiple of 16) and out_sy == out_sx == 2");
+    ABC_REQUIRE(d->n_tile / 16 <= 16 && d->out_W < 32768 && d->out_plane_off + subpixel / 8 <= d->out_planes,
+                "abc_conv_igemm: subpixel: n_tile <= 256, out_W < 32768, plane range");
+    ABC_REQUIRE((d->H - 1) * 2 + d->out_oy + 1 < d->out_H && (d->W - 1) * 2 + d->out_ox + 1 < d->out_W,
+                "abc_conv_igemm: subpixel output mapping exceeds out_H x out_W");
+  }
   if (d->out) {
     ABC_REQUIRE(d->out_sy >= 1 && d->out_sx >= 1 && d->out_oy >= 0 && d->out_ox >= 0 &&
                     (d->H - 1) * d->out_sy + d->out_oy < d->out_H && (d->W - 1) * d->out_sx + d->out_ox < d->out_W,
@@ -938,6 +966,7 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.out_H = d->out_H; p.out_W = d->out_W;
   p.out_sy = d->out_sy; p.out_oy = d->out_oy; p.out_sx = d->out_sx; p.out_ox = d->out_ox;
   p.pool_out = d->pool_out; p.pool_planes = d->pool_planes; p.pool_plane_off = d->pool_plane_off;
+  p.subpixel = subpixel;
   cudaStream_t st_ = static_cast<cudaStream_t>(stream_);
   // fused BatchNorm statistics (training forward)
   const bool stats = d->stat_sum != nullptr || d->stat_sq != nullptr;

@@ -27,15 +27,25 @@ __device__ __forceinline__ float act_grad(float pre, int act) {
   return 1.f;
 }
 
-// counter-based dropout mask: keep iff hash(seed, element) >= p * 2^32 (same function in forward and backward)
-__device__ __forceinline__ float drop_scale(unsigned long long seed, unsigned long long idx, float p) {
-  if (p <= 0.f) return 1.f;
-  unsigned long long z = idx * 0x9E3779B97F4A7C15ull + seed;
+// Counter-based dropout masks for the 8 channels of one P8 vector (same function in forward and backward): two 64-bit
+// hashes of (seed, vector index) give eight 16-bit uniforms; channel i is kept iff its uniform >= p * 65536 (p is thereby
+// quantised to 2^-16; nn.Dropout's scale 1 / (1 - p) is kept). One hash per FOUR channels instead of one per channel: the
+// dropout passes of the 1024-channel head BatchNorm were ALU-bound on the 64-bit multiplies of the per-element hash.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = static_cast<float>(static_cast<unsigned>(z >> 40)) * (1.f / 16777216.f);
-  return u >= p ? 1.f / (1.f - p) : 0.f;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ void drop_scale8(unsigned long long seed, unsigned long long vec_idx, float p, float* m) {
+  const unsigned thr = static_cast<unsigned>(p * 65536.f);
+  const float keep = 1.f / (1.f - p);
+  const unsigned long long h0 = mix64((2 * vec_idx) * 0x9E3779B97F4A7C15ull + seed);
+  const unsigned long long h1 = mix64((2 * vec_idx + 1) * 0x9E3779B97F4A7C15ull + seed);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = (static_cast<unsigned>(h0 >> (16 * i)) & 0xffffu) >= thr ? keep : 0.f;
+    m[4 + i] = (static_cast<unsigned>(h1 >> (16 * i)) & 0xffffu) >= thr ? keep : 0.f;
+  }
 }
 
 }  // namespace abc

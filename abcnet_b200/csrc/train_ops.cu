@@ -152,14 +152,15 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
   const int stride = gridDim.x * 256;
   if (!POOL) {
     const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
-    const unsigned long long ebase = (static_cast<unsigned long long>(n) * p.planes + plane) * 8;
+    const unsigned long long vbase = (static_cast<unsigned long long>(n) * p.planes + plane) * HW;   // index of the plane's first vector
     for (int e = blockIdx.x * 256 + threadIdx.x; e < HW; e += stride) {
-      float v[8];
+      float v[8], dm[8];
       unpack8u(zb[e], v);
+      if (p.drop_p > 0.f) drop_scale8(seed, vbase + e, p.drop_p, dm);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float a = act_fwd(fmaf(v[i], sc[i], sh[i]), p.act);
-        if (p.drop_p > 0.f) a *= drop_scale(seed, (ebase + i) * HW + e, p.drop_p);
+        if (p.drop_p > 0.f) a *= dm[i];
         v[i] = a;
       }
       ob[e] = pack8(v);
@@ -213,12 +214,14 @@ struct BnActBwdParams {
 
 // Gradient g wrt the BatchNorm output for one pixel (8 channels): g = dA * act'(pre) * dropout scale.
 __device__ __forceinline__ void bwd_pixel(const BnActBwdParams& p, const float* v, const float* d, const float* sc, const float* sh,
-                                          unsigned long long seed, unsigned long long ebase, int HW, int e, float* g) {
+                                          unsigned long long seed, unsigned long long vbase, int e, float* g) {
+  float dm[8];
+  if (p.drop_p > 0.f) drop_scale8(seed, vbase + e, p.drop_p, dm);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float pre = fmaf(v[i], sc[i], sh[i]);
     float m = act_grad(pre, p.act);
-    if (p.drop_p > 0.f) m *= drop_scale(seed, (ebase + i) * HW + e, p.drop_p);
+    if (p.drop_p > 0.f) m *= dm[i];
     g[i] = d[i] * m;
   }
 }
@@ -262,13 +265,29 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwdPa
   const int stride = gridDim.x * 256;
   if (!POOL) {
     const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
-    const unsigned long long ebase = (static_cast<unsigned long long>(n) * p.planes + plane) * 8;
-    for (int e = blockIdx.x * 256 + threadIdx.x; e < HW; e += stride) {
+    const unsigned long long vbase = (static_cast<unsigned long long>(n) * p.planes + plane) * HW;
+    int e = blockIdx.x * 256 + threadIdx.x;
+    for (; e + stride < HW; e += 2 * stride) {            // four independent 16-byte loads in flight per thread
+      const uint4 zu0 = zb[e], du0 = db[e], zu1 = zb[e + stride], du1 = db[e + stride];
+      float v[8], d[8], g[8], w[8], f[8], h[8];
+      unpack8u(zu0, v);
+      unpack8u(du0, d);
+      unpack8u(zu1, w);
+      unpack8u(du1, f);
+      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
+      bwd_pixel(p, w, f, sc, sh, seed, vbase, e + stride, h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += g[i] + h[i];
+        t2[i] = fmaf(g[i], v[i], fmaf(h[i], w[i], t2[i]));
+      }
+    }
+    if (e < HW) {
       float v[8], d[8], g[8];
       const uint4 zu = zb[e], du = db[e];
       unpack8u(zu, v);
       unpack8u(du, d);
-      bwd_pixel(p, v, d, sc, sh, seed, ebase, HW, e, g);
+      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s1[i] += g[i];
@@ -342,13 +361,31 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnActBwdPar
   const int stride = gridDim.x * 256;
   if (!POOL) {
     const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
-    const unsigned long long ebase = (static_cast<unsigned long long>(n) * p.planes + plane) * 8;
-    for (int e = blockIdx.x * 256 + threadIdx.x; e < HW; e += stride) {
+    const unsigned long long vbase = (static_cast<unsigned long long>(n) * p.planes + plane) * HW;
+    int e = blockIdx.x * 256 + threadIdx.x;
+    for (; e + stride < HW; e += 2 * stride) {            // four independent 16-byte loads in flight per thread
+      const uint4 zu0 = zb[e], du0 = db[e], zu1 = zb[e + stride], du1 = db[e + stride];
+      float v[8], d[8], g[8], w[8], f[8], h[8];
+      unpack8u(zu0, v);
+      unpack8u(du0, d);
+      unpack8u(zu1, w);
+      unpack8u(du1, f);
+      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
+      bwd_pixel(p, w, f, sc, sh, seed, vbase, e + stride, h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[i] = fmaf(g[i], sc[i], fmaf(v[i], cb[i], ca[i]));
+        h[i] = fmaf(h[i], sc[i], fmaf(w[i], cb[i], ca[i]));
+      }
+      ob[e] = pack8(g);
+      ob[e + stride] = pack8(h);
+    }
+    if (e < HW) {
       float v[8], d[8], g[8];
       const uint4 zu = zb[e], du = db[e];
       unpack8u(zu, v);
       unpack8u(du, d);
-      bwd_pixel(p, v, d, sc, sh, seed, ebase, HW, e, g);
+      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], sc[i], fmaf(v[i], cb[i], ca[i]));
       ob[e] = pack8(g);

@@ -336,11 +336,13 @@ class UNet(nn.Module):
             (ca, ba), (cb, bb) = self._dc_layers(holder)
             pack3(name + ".0", ca, ba)
             pack3(name + ".3", cb, bb)
-        # up-sampling convolutions: 4 sub-pixel phases each
+        # up-sampling convolutions: 4 sub-pixel phases each -- as ONE launch with the phases as blocks of the
+        # GEMM N axis (AbcConvDesc.subpixel), and as four separate launches (kept for comparison: ABCNET_UP_PHASES=1)
         for name, holder in (("up1", self.up1), ("up2", self.up2), ("up3", self.up3)):
             w = holder.up.weight.detach().float()          # [Cin, Cout, 3, 3]
             b = holder.up.bias.detach().float()
             cin, cout = w.shape[:2]
+            P[f"{name}.up"] = self._pack_subpixel(w, b)
             for py in (0, 1):
                 for px in (0, 1):
                     ys = self._phase_taps(py)
@@ -407,6 +409,22 @@ class UNet(nn.Module):
         assert w2pack.numel() * 2 == nb.value and bias2.numel() == nl.value
         return w2pack, bias2
 
+    def _pack_subpixel(self, w, b):
+        """All four sub-pixel phases of ConvTranspose2d(k3, s2) + crop as one N = 4 * cout GEMM over the union of the phases'
+        input offsets: w [Cin, Cout, 3, 3] -> taps [(dy, dx)], weights [ntaps, 4 * cout, cin] with zero blocks."""
+        cin, cout = w.shape[:2]
+        offs = sorted({(dy, dx) for py in (0, 1) for px in (0, 1) for (_, dy) in self._phase_taps(py) for (_, dx) in self._phase_taps(px)})
+        wt = w.new_zeros(len(offs), 4 * cout, cin)
+        for py in (0, 1):
+            for px in (0, 1):
+                ph = 2 * py + px
+                for (ky, dy) in self._phase_taps(py):
+                    for (kx, dx) in self._phase_taps(px):
+                        wt[offs.index((dy, dx)), ph * cout:(ph + 1) * cout] = w[:, :, ky, kx].t()
+        pk = _Packed(wt, b.repeat(4), offs, 256 if cout % 64 == 0 else 128, 4 * cout, pair=False)
+        pk.subpixel = cout
+        return pk
+
     def _phase_taps(self, parity):
         """(kernel index, input offset) pairs of one output parity of ConvTranspose2d(k=3, s=2) + crop."""
         if self.crop_first:      # kept[y] = U[y + 1]
@@ -433,7 +451,8 @@ class UNet(nn.Module):
         for i, (dy, dx) in enumerate(pk.taps):
             d.tap_dy[i], d.tap_dx[i] = dy, dx
         d.row_fold, d.cta_pair = pk.fold, int(pk.pair)
-        d.swap_mn = int(use_swap(pk, out_mode, dst, pool))
+        d.subpixel = getattr(pk, "subpixel", 0)
+        d.swap_mn = int(use_swap(pk, out_mode, dst, pool)) if not d.subpixel else 0
         d.act, d.out_mode = act, out_mode
         sy, oy, sx, ox = out_scale
         d.out_sy, d.out_oy, d.out_sx, d.out_ox = sy, oy, sx, ox
@@ -542,8 +561,13 @@ class UNet(nn.Module):
         cv("down5.0", p5, 0, h1)
         cv("down5.3", h1, 0, h2)                                            # x6
 
+        merged_up = not os.environ.get("ABCNET_UP_PHASES")
+
         def up(name, src, cat, half_planes):
             with self._timed(name + ".up"):
+                if merged_up:
+                    self._conv(P[f"{name}.up"], src, 0, cat, out_plane_off=half_planes, act=0, out_scale=(2, 0, 2, 0), stream=st)
+                    return
                 for py in (0, 1):
                     for px in (0, 1):
                         self._conv(P[f"{name}.up.{py}{px}"], src, 0, cat, out_plane_off=half_planes, act=0,

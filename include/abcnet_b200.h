@@ -140,6 +140,14 @@ typedef struct AbcConvDesc {
    * 16 -> 16 layers (row_fold = 4, cin = cout = 16); other layers use abc_bn_stats. Replaces one full read of the conv output. */
   double* stat_sum;
   double* stat_sq;
+  /* Optional sub-pixel output blocks (0 = off; else the channel count of ONE phase, multiple of 16): the stride-2 transposed
+   * convolution + crop of Up.forward (src/unet.py:44,49-55) as ONE launch instead of four. cout must be 4 * subpixel; GEMM
+   * column c = phase * subpixel + channel with phase = 2 * py + px is stored at output pixel
+   * (y * 2 + out_oy + py, x * 2 + out_ox + px), plane out_plane_off + channel / 8 (out_sy = out_sx = 2). The tap list is the
+   * union of the input offsets any phase uses (<= 4); the weight pack holds zero blocks where a phase does not use a tap
+   * (9 of the 16 (tap, phase) blocks are non-zero). The input tile is read once instead of four times and
+   * a thread writes both px phases of a pixel = one full 32-byte sector. */
+  int subpixel;
 } AbcConvDesc;
 
 ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);
@@ -398,6 +406,44 @@ ABC_API int abc_conv3x3_c1_wgrad(const void* img, int img_is_u8, const void* dz,
 /* Same for the general stem: dw fp32 [16][cin][9] (zeroed by the call). */
 ABC_API int abc_conv3x3_cn_wgrad(const float* img, int cin, const void* dz, int dz_planes, int dz_plane_off, int N, int H, int W,
                                  float* dw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Whole-network inference (abc_unet_forward_infer) -- UNet.forward of src/unet.py:100-119 in eval mode
+ * behind one call, for hosts without the Python layer.
+ *
+ *   AbcUNetConfig cfg = {1, 8, {1, 14, 3, 2, 1, 360, 60, 60}, 1};
+ *   wpack = device_alloc(abc_unet_wpack_bytes(&cfg));                       caller-owned, lives as long as the handle
+ *   abc_unet_create(&cfg, tensors, n, wpack, bytes, stream, &net);          tensors: the checkpoint's fp32 state_dict entries
+ *   ws = device_alloc(abc_unet_workspace_bytes(&cfg, N, H, W));             caller-owned activations (bf16 P8), 256-byte aligned
+ *   abc_unet_forward_infer(net, img, 0, N, H, W, ws, ws_bytes, outs, 1, stream);   outs[i]: fp32 [N][heads[i]][H/4][W/4]
+ *   abc_decode_peaks(...) on the same stream; abc_unet_destroy(net);
+ *
+ * abc_unet_create reads HOST pointers: for every key of the reference's state_dict ("inc1.double_conv.0.weight", ...,
+ * "up1.up.weight" [Cin][Cout][3][3], "out_modules.5.conv2.weight", BatchNorm "running_mean" / "running_var"; an optional
+ * "module." prefix is ignored, "s" and "num_batches_tracked" are not needed) the fp32 data in the checkpoint's own layout. It
+ * folds BatchNorm (running statistics) into the convolutions, packs them for the kernels and uploads the result into wpack
+ * (one synchronising copy; nothing else in this library allocates or synchronises). logits_layout 1 = the reference's NCHW fp32
+ * tensors, 2 = planar-8 fp32 for heads with more than one channel (what abc_decode_peaks reads fastest, p8f_mask).
+ * img: [N][in_channels][H][W] fp32, or uint8 {0,1} (img_is_u8, in_channels = 1). H, W multiples of 32. */
+typedef struct AbcUNetConfig {
+  int in_channels;     /* 1..8 */
+  int n_heads;         /* 1..16 */
+  int heads[16];       /* output channels per head (v2: 1, 14, 3, 2, 1, 360, 60, 60) */
+  int crop_first;      /* 1: torch >= 1.13 semantics of unet.py:54-55 (drop the FIRST row / column of the up-sampled map) */
+} AbcUNetConfig;
+typedef struct AbcNamedTensor {
+  const char* name;
+  const float* data;   /* host pointer */
+  int64_t numel;
+} AbcNamedTensor;
+typedef struct AbcUNet AbcUNet;   /* opaque */
+ABC_API int64_t abc_unet_wpack_bytes(const AbcUNetConfig* cfg);
+ABC_API int64_t abc_unet_workspace_bytes(const AbcUNetConfig* cfg, int N, int H, int W);
+ABC_API int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* tensors, int n_tensors, void* wpack_dev, int64_t wpack_bytes,
+                            void* stream, AbcUNet** out);
+ABC_API int abc_unet_forward_infer(AbcUNet* net, const void* img, int img_is_u8, int N, int H, int W, void* workspace,
+                                   int64_t workspace_bytes, void* const* out_ptrs, int logits_layout, void* stream);
+ABC_API int abc_unet_destroy(AbcUNet* net);
 
 #ifdef __cplusplus
 }

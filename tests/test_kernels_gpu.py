@@ -373,3 +373,27 @@ def test_upsampling_conv_phases(crop_first):
             got, _ = run_conv(x, wt, b, taps, 64, act=0, out_scale=(2, py, 2, px), out_hw=(2 * H, 2 * W))
             out[:, :, py::2, px::2] = got[:, :, py::2, px::2]
     assert_close(out, ref, 2 ** -7, 2e-3, "up-sampling conv")
+
+
+@pytest.mark.parametrize("crop_first", [True, False])
+@pytest.mark.parametrize("cin,cout,H,W", [(128, 64, 16, 8), (256, 128, 8, 24), (512, 256, 2, 2)])
+def test_upsampling_conv_single_launch(crop_first, cin, cout, H, W):
+    """The same operator as ONE launch: the four sub-pixel phases as blocks of the GEMM N axis (AbcConvDesc.subpixel), written
+    into the upper half of a concat buffer whose lower half (the skip) must stay untouched. Against fp64 conv_transpose2d."""
+    import abcnet_b200
+    N = 2
+    x = bf16_round(rnd(191, (N, cin, H, W)))
+    w = bf16_round(rnd(192, (cin, cout, 3, 3)) * 0.05)
+    b = rnd(193, (cout,))
+    U = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2).float()
+    ref = U[:, :, 1:, 1:] if crop_first else U[:, :, :-1, :-1]
+    m = abcnet_b200.UNet(1, [1], crop_first=crop_first)
+    dev = torch.device("cuda")
+    pk = m._pack_subpixel(w.to(dev), b.to(dev))
+    src = to_p8(x).to(dev)
+    cat = torch.full((N, 2 * cout // 8, 2 * H, 2 * W, 8), -5.0, dtype=torch.bfloat16, device=dev)
+    m._conv(pk, src, 0, cat, out_plane_off=cout // 8, act=0, out_scale=(2, 0, 2, 0), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = from_p8(cat).cpu()
+    assert (got[:, :cout] == -5.0).all(), "the skip half of the concat buffer was overwritten"
+    assert_close(got[:, cout:], ref, 2 ** -7, 2e-3, "single-launch up-sampling conv")

@@ -1,0 +1,53 @@
+"""The whole-network C entry points (abc_unet_create / abc_unet_forward_infer: BatchNorm fold, weight packing and the launch
+plan in C++) against abcnet_b200.UNet (the same in Python): bit-identical logits, and both against the fp32 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, unet_ref
+
+pytestmark = pytest.mark.gpu
+HEADS = list(unet_ref.V2_HEADS)
+
+
+@pytest.mark.parametrize("cin,B,H,W,crop_first", [(1, 2, 64, 96, True), (1, 3, 128, 64, False), (3, 2, 64, 64, True)])
+def test_native_forward_matches_python_plan_and_oracle(cin, B, H, W, crop_first):
+    import abcnet_b200
+    from abcnet_b200.native import NativeUNet
+    sd = unet_ref.make_state_dict(seed=21, in_channels=cin, variant="W1")
+    m = abcnet_b200.UNet(cin, HEADS, crop_first=crop_first).cuda().eval()
+    m.load_state_dict(sd)
+    net = NativeUNet({"module." + k: v for k, v in sd.items()}, in_channels=cin, heads=HEADS, crop_first=crop_first)
+    if cin == 1:
+        x = torch.from_numpy(synth.binary_images(21, B, H, W, 0.08))
+    else:
+        x = torch.from_numpy(synth.detrand.uniform(21, (B, cin, H, W), -1.0, 1.0).astype(np.float32))
+    want = m(x.cuda())
+    got = net(x.cuda())
+    torch.cuda.synchronize()
+    for i, (g, w_) in enumerate(zip(got, want)):
+        assert torch.equal(g, w_), f"head {i}: C++ plan differs from the Python plan (max {float((g - w_).abs().max())})"
+    with torch.no_grad():
+        ref = unet_ref.forward(x, sd, crop_first=crop_first)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        err, scale = (g.cpu() - r).abs().max().item(), r.abs().max().item()
+        assert err <= 0.04 * scale + 0.03, f"head {i}: max abs err {err} vs scale {scale}"
+    # planar-8 logits + uint8 transport + decode through the C-ABI only
+    if cin == 1:
+        p8 = net((x > 0).to(torch.uint8).cuda(), layout="p8f")
+        ref8 = m.infer(x.cuda(), layout="p8f")
+        for g, w_ in zip(p8.to_nchw(), ref8.to_nchw()):
+            assert torch.equal(g, w_)
+        dec = abcnet_b200.PeakDecoder(B, atom_cap=4096, bond_cap=16384)
+        a = dec(p8)
+        b = dec(ref8)
+        for (aa, ab, an), (ba, bb, bn) in zip(a, b):
+            assert an == bn and np.array_equal(aa, ba) and np.array_equal(ab, bb)
+
+
+def test_native_create_reports_missing_tensors():
+    from abcnet_b200.native import NativeUNet
+    sd = unet_ref.make_state_dict(seed=1, variant="W1")
+    del sd["up2.up.weight"]
+    with pytest.raises(RuntimeError, match="up2.up.weight"):
+        NativeUNet(sd)
