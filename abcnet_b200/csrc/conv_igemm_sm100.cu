@@ -833,7 +833,9 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   }
   if (d->out_mode == 0) {
     ABC_REQUIRE(d->cout % 8 == 0, "abc_conv_igemm: P8 output needs cout %% 8 == 0 (got %d)", d->cout);
-    if (d->out) ABC_REQUIRE(d->out_plane_off >= 0 && d->out_plane_off + d->cout / 8 <= d->out_planes, "abc_conv_igemm: output plane range");
+    // sub-pixel mode: the four phases share the plane range of ONE phase
+    const int out_ch = d->subpixel > 0 ? d->subpixel : d->cout;
+    if (d->out) ABC_REQUIRE(d->out_plane_off >= 0 && d->out_plane_off + out_ch / 8 <= d->out_planes, "abc_conv_igemm: output plane range");
   } else {
     ABC_REQUIRE(d->out != nullptr && d->pool_out == nullptr, "abc_conv_igemm: fp32 output modes need out and no pool_out");
     if (d->out_mode == 2)

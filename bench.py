@@ -668,6 +668,21 @@ def run_ours(args, rank, world, local_rank):
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
     small = None if args.no_small else run_small_batches(model, pool, dev, args)
+    # the same 256-image step replayed as ONE CUDA graph ("graph-captured and eager both reported")
+    graph_ms = None
+    if not args.no_small:
+        g = abcnet_b200.InferGraph(model, B, x.shape[2], x.shape[3], atom_cap=args.atom_cap, bond_cap=args.bond_cap, dtype=x.dtype)
+        for _ in range(3):
+            g.launch(x)
+        barrier()
+        t0.record()
+        for _ in range(args.steps):
+            g.launch(x)
+        t1.record()
+        barrier()
+        graph_ms = t0.elapsed_time(t1) / args.steps
+        del g
+        torch.cuda.empty_cache()
     comparator = None
     train = None
     if not args.no_train:
@@ -736,6 +751,8 @@ def run_ours(args, rank, world, local_rank):
                                     "class / offset heads at the peaks only (same kernels, same packed weights, same MMA order); "
                                     "NOT the headline `value`, which evaluates all eight heads densely"},
            "small_batch": small, "gpu_comparator": comparator,
+           "graph_replay": None if graph_ms is None else {"ms_per_step": graph_ms, "value": world * B / (graph_ms * 1e-3), "unit": UNIT,
+                                                           "what": "the device-resident step (`value` = eager launches) as one CUDA-graph replay"},
            "gpu_launches": int(launches), "clocks": clocks, "train": train}
     print(json.dumps(out))
 
