@@ -770,7 +770,8 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (the 'train' object)")
     ap.add_argument("--no-small", action="store_true", help="skip the batch-8 / batch-32 latency leg ('small_batch')")
     ap.add_argument("--no-comparator", action="store_true", help="skip the torch / cuDNN comparator leg ('gpu_comparator')")
-    ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step (train.py:44)")
+    ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per training step (train.py:44; multi_gpu_train2.py:20 uses 60)")
+    ap.add_argument("--train-only", action="store_true", help="only the training-step leg: prints its object as the JSON line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -789,7 +790,14 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.train_only:
+            torch.cuda.set_device(local_rank)
+            out = run_train(args, rank, world, torch.device("cuda", local_rank))
+            if rank == 0:
+                out.update(n_gpus=world, steps=args.steps, higher_is_better=True)
+                print(json.dumps(out))
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
