@@ -38,6 +38,7 @@ class GradBuckets:
         self.bucket_of = {id(p): b for b, ms in enumerate(self.members) for p in ms}
         self._pending = [len(ms) for ms in self.members]
         self._works = []
+        self._launched = False
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
 
     def _close(self, ps, n, dev):
@@ -54,6 +55,7 @@ class GradBuckets:
             b.zero_()
         self._pending = [len(ms) for ms in self.members]
         self._works = []
+        self._launched = False
 
     def world(self):
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -69,6 +71,7 @@ class GradBuckets:
         if self.world() == 1 or not self.comm_enabled:
             return
         flat = self.buckets[b]
+        self._launched = True
         if self.comm_stream is not None:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
@@ -88,6 +91,8 @@ class GradBuckets:
                 self._launch(b)
         for w in self._works:
             w.wait()
-        if self.comm_stream is not None:
+        # join the communication stream only if something was forked to it since zero(): inside a CUDA-graph capture a wait on a
+        # stream that is not part of the capture is an error
+        if self.comm_stream is not None and self._launched:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         self._works = []

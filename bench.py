@@ -309,6 +309,8 @@ def run_train(args, rank, world, dev):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
+    if os.environ.get("ABCNET_BENCH_WATCHDOG"):
+        print(f"[rank {rank}] run_train: timed {args.steps} steps, {ms / args.steps:.2f} ms each", file=sys.stderr, flush=True)
     v = world * B * args.steps / (ms * 1e-3)
     ddp = ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms / args.steps) if world > 1 else None
     return {"metric": "images_per_sec_train_step", "value": v, "unit": UNIT, "ms_per_step": ms / args.steps, "ddp": ddp,
@@ -334,6 +336,11 @@ def ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms_on):
     import abcnet_b200
     rank = dist.get_rank()
     out = {}
+
+    def mark(msg):
+        if os.environ.get("ABCNET_BENCH_WATCHDOG"):
+            print(f"[rank {rank}] ddp_evidence: {msg}", file=sys.stderr, flush=True)
+    mark("start")
     # ---- known gradients
     params = buckets.params
     buckets.zero()
@@ -351,6 +358,7 @@ def ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms_on):
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     out["known_gradients_mean_exact"] = bool(t.item() == 1.0)
+    mark("known gradients done")
     # ---- real gradients: bucketed / overlapped vs one plain all-reduce of the local gradients
     step_noopt = abcnet_b200.TrainStep(model, None, class_weights=True, buckets=buckets, use_graph=False)
     buckets.comm_enabled = False
@@ -372,6 +380,7 @@ def ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms_on):
     out["bucketed_vs_plain_allreduce_rel_err"] = rel
     out["replicas_bit_identical"] = bool(torch.equal(lo, hi))
     out["correct"] = bool(out["known_gradients_mean_exact"] and rel < 1e-3 and out["replicas_bit_identical"])
+    mark("real gradients done")
     # ---- the exchange alone
     nbytes = sum(b.numel() for b in buckets.buckets) * 4
     for _ in range(3):
@@ -392,6 +401,7 @@ def ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms_on):
     ar_ms = t.item()
     out.update(allreduce_alone_ms=ar_ms, allreduce_bytes=nbytes, n_buckets=len(buckets.buckets),
                allreduce_bus_gbs=2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9)
+    mark("exchange alone done")
     # ---- the same step with the exchange switched off (new capture)
     buckets.comm_enabled = False
     step_off = abcnet_b200.TrainStep(model, opt, class_weights=True, buckets=buckets, use_graph=True)
@@ -776,6 +786,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("ABCNET_BENCH_WATCHDOG"):          # debugging aid: dump every thread's stack and exit if the run takes too long
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["ABCNET_BENCH_WATCHDOG"]), exit=True)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
