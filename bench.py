@@ -361,6 +361,7 @@ def ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms_on):
     mark("known gradients done")
     # ---- real gradients: bucketed / overlapped vs one plain all-reduce of the local gradients
     step_noopt = abcnet_b200.TrainStep(model, None, class_weights=True, buckets=buckets, use_graph=False)
+    p_drop, model.dropout_p = model.dropout_p, 0.0      # the two evaluations below must see the same function (new masks every step)
     buckets.comm_enabled = False
     step_noopt(x, tg)
     torch.cuda.synchronize()
@@ -370,6 +371,7 @@ def ddp_evidence(args, world, dev, model, opt, buckets, x, tg, ms_on):
     buckets.comm_enabled = True
     step_noopt(x, tg)
     torch.cuda.synchronize()
+    model.dropout_p = p_drop
     got = torch.cat(buckets.buckets)
     # weight gradients use fp32 atomics: two evaluations of the same step differ in the last bits, hence a tolerance
     rel = ((got - local).norm() / (local.norm() + 1e-30)).item()
