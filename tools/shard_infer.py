@@ -128,9 +128,12 @@ def main():
         a, b = ranges[i]
         sinks[i % 2].wait(B)
         texts = sinks[i % 2].molblocks(B, max(1, (os.cpu_count() or 1) // world))[:b - a]
-        for g_, t_ in zip(range(a, b), texts):
-            if g_ < args.dump_subset:
-                subset[g_] = t_
+        if a < args.dump_subset:                       # compact records of the subset, for the record-level oracle comparison
+            dec = sinks[i % 2].dec if args.sparse else sinks[i % 2]
+            recs = dec._parse(B)
+            for g_, t_, r_ in zip(range(a, b), texts, recs):
+                if g_ < args.dump_subset:
+                    subset[g_] = (t_, r_[0].copy(), r_[1].copy(), r_[2])
         h = hashlib.blake2b(digest_size=32)
         for t in texts:
             h.update(b"\0" if t is None else t.encode())
@@ -173,7 +176,9 @@ def main():
     if rank == 0 and args.dump_subset:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         torch.save({"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
-                    "molblocks": [subset.get(g_) for g_ in range(min(args.dump_subset, total // world))],
+                    "molblocks": [subset[g_][0] for g_ in range(min(args.dump_subset, total // world))],
+                    "atoms": [subset[g_][1] for g_ in range(min(args.dump_subset, total // world))],
+                    "bonds": [subset[g_][2] for g_ in range(min(args.dump_subset, total // world))],
                     "pool": P, "seed": 7, "trained": trained, "sparse": bool(args.sparse)},
                    os.path.join(ROOT, "gpurun_out", "shard_subset.pt"))
     if rank == 0:
