@@ -279,6 +279,7 @@ def run_train(args, rank, world, dev):
     from abcnet_b200.ddp import GradBuckets
     import synthdata as synth
     B = args.train_batch
+    torch.cuda.reset_peak_memory_stats()                 # `mem_gb` = the training leg's own peak, not the inference legs before it
     model = abcnet_b200.UNet(1, HEADS).to(dev)
     model.load_state_dict(make_weights())
     model.train()

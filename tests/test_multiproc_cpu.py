@@ -77,3 +77,25 @@ def test_sharded_inference_gather_world2():
 def test_bucketed_allreduce_world2():
     ok, views, nb = _run(_worker_buckets, 29612)
     assert ok and views and nb >= 2
+
+
+def test_grad_buckets_tail_bucket_holds_the_last_gradients():
+    """The parameters whose gradients appear last in the backward pass (first registered) get a small bucket of their own, so
+    that the last large bucket can be reduced while they are still being computed (abcnet_b200/ddp.py, tail_bytes)."""
+    from abcnet_b200.ddp import GradBuckets
+    shapes = [(10,), (16, 1, 3, 3), (16,), (16, 16, 3, 3), (256, 256, 3, 3), (512, 256, 3, 3), (128, 128, 3, 3), (360, 128, 1, 1)]
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    gb = GradBuckets(params, bucket_bytes=4 << 20, tail_bytes=16 << 10)
+    tail = gb.members[-1]
+    assert [tuple(p.shape) for p in tail] == [(16, 16, 3, 3), (16,), (16, 1, 3, 3), (10,)]      # reverse registration order, <= 16 KB
+    assert sum(p.numel() for p in tail) * 4 <= 16 << 10
+    assert all(id(p) in gb.bucket_of for p in params) and sum(len(m) for m in gb.members) == len(params)
+    # every .grad is a view into its bucket, contiguous and in order
+    for b, ms in zip(gb.buckets, gb.members):
+        off = 0
+        for p in ms:
+            assert p.grad.data_ptr() == b.data_ptr() + 4 * off
+            off += p.numel()
+    # a model without small trailing parameters: no empty / degenerate tail bucket
+    gb2 = GradBuckets([torch.nn.Parameter(torch.zeros(1 << 20)) for _ in range(3)], bucket_bytes=4 << 20, tail_bytes=16 << 10)
+    assert all(len(m) >= 1 for m in gb2.members) and sum(len(m) for m in gb2.members) == 3

@@ -55,9 +55,13 @@ def main():
         a["ms"] += t
         a["rd"] += num(r[col["dram__bytes_read.sum"]]) * UNIT.get(units[col["dram__bytes_read.sum"]], 1.0)
         a["wr"] += num(r[col["dram__bytes_write.sum"]]) * UNIT.get(units[col["dram__bytes_write.sum"]], 1.0)
-        a["dram_pct"] += t * num(r[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]])
-        a["tensor_pct"] += t * num(r[col["sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"]])
-        a["regs"] = max(a["regs"], int(num(r[col["launch__registers_per_thread"]])))
+        def get(key):                       # a metric that was not collected (or is n/a for this kernel) counts as 0
+            i = col[key]
+            v = num(r[i]) if i is not None else 0.0
+            return 0.0 if v != v else v
+        a["dram_pct"] += t * get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+        a["tensor_pct"] += t * get("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed")
+        a["regs"] = max(a["regs"], int(get("launch__registers_per_thread")))
     print(f"# {args[0]}: per kernel name -- launches, total gpu__time_duration (ms, cold-cache replays), DRAM read / written (GB),")
     print("# achieved DRAM GB/s over those launches, time-weighted gpu__dram_throughput % and tensor-pipe active %, registers")
     print(f"# {'n':>4s} {'ms':>9s} {'rd GB':>8s} {'wr GB':>8s} {'GB/s':>8s} {'dram%':>6s} {'tens%':>6s} {'regs':>5s}  kernel")
