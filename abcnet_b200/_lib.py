@@ -37,7 +37,7 @@ class AbcConvDesc(C.Structure):
         ("pool_out", C.c_void_p), ("pool_planes", C.c_int), ("pool_plane_off", C.c_int),
         ("k_segments", C.c_int), ("seg_tap0", C.c_int * 4), ("seg_ntaps", C.c_int * 4),
         ("row_fold", C.c_int), ("cta_pair", C.c_int), ("swap_mn", C.c_int),
-        ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p), ("subpixel", C.c_int),
+        ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p), ("subpixel", C.c_int), ("k_chunk", C.c_int),
     ]
 
 

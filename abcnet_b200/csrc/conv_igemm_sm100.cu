@@ -873,7 +873,11 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.tile_rows = swap ? 32 * fold : 16 * fold;
   p.tiles_y = (d->H + p.tile_rows - 1) / p.tile_rows;
   p.in_plane_off = d->in_plane_off;
-  const int kc = conv_kc(d->cin);
+  // K chunk = channels per pipeline stage; 0 = the default min(cin, 64). A smaller chunk halves the activation stage and the
+  // weight blocks, i.e. deepens both rings (AbcConvDesc.k_chunk)
+  const int kc = d->k_chunk > 0 ? d->k_chunk : conv_kc(d->cin);
+  ABC_REQUIRE((kc == 16 || kc == 32 || kc == 48 || kc == 64) && kc <= d->cin && d->cin % kc == 0 && !(d->cta_pair && kc != 64),
+              "abc_conv_igemm: k_chunk=%d must be 16, 32 or 64 and divide cin=%d", kc, d->cin);
   p.kp = kc / 8;
   p.nkc = d->cin / kc;
   p.ntaps = fold > 1 ? 3 * (fold + 2) : d->ntaps;

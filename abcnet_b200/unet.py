@@ -76,6 +76,14 @@ def row_fold_for(cin, cout):
     return 1
 
 
+def k_chunk_for(cin):
+    """Channels per pipeline stage (AbcConvDesc.k_chunk). Default min(cin, 64); ABCNET_KC64=32 selects 32 for the cin = 64
+    layers (experiment: deeper rings for the pipeline-depth-bound 64-channel layers at 128 x 128)."""
+    if cin == 64 and os.environ.get("ABCNET_KC64"):
+        return int(os.environ["ABCNET_KC64"])
+    return min(cin, 64)
+
+
 def use_cta_pair(cin, ntaps, n_tile):
     """CTA-pair (cta_group::2) mode for the layers whose weights of one n-tile do not fit in shared memory and are streamed
     (Cin >= 128 3x3 layers, the 8-head conv1, the large up-sampling phases): see AbcConvDesc.cta_pair.
@@ -161,7 +169,7 @@ def fold_rows(w_taps, bias, taps, J):
 class _Packed:
     """Device-resident, kernel-ready form of one convolution: packed bf16 weights + fp32 bias + tap list."""
 
-    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1, pair=None, fold_swap=False):
+    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1, pair=None, fold_swap=False, kc=None):
         # w_taps: fp32 [ntaps, cout, cin] (already BN-folded); taps: list of (dy, dx)
         # pair: CTA-pair mode (AbcConvDesc.cta_pair); None = decide from the layer size (weights too large to stay resident)
         # fold_swap: row folding in the row order of the operand-swap kernel (the launch must then use swap_mn)
@@ -170,7 +178,8 @@ class _Packed:
             w_taps, bias = (fold_rows_swap if fold_swap else fold_rows)(w_taps, bias, taps, fold)
             n_tile = fold * cout
         ntaps, co, cin = w_taps.shape
-        kc = min(cin, 64)
+        kc = kc or k_chunk_for(cin)
+        self.kc = kc
         n_tiles = (cout + n_tile - 1) // n_tile
         pad = n_tiles * n_tile - co
         if pad:
@@ -451,6 +460,7 @@ class UNet(nn.Module):
         for i, (dy, dx) in enumerate(pk.taps):
             d.tap_dy[i], d.tap_dx[i] = dy, dx
         d.row_fold, d.cta_pair = pk.fold, int(pk.pair)
+        d.k_chunk = getattr(pk, "kc", 0) if getattr(pk, "kc", 0) != min(pk.cin, 64) else 0
         d.subpixel = getattr(pk, "subpixel", 0)
         d.swap_mn = int(use_swap(pk, out_mode, dst, pool)) if not d.subpixel else 0
         d.act, d.out_mode = act, out_mode

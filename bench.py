@@ -680,21 +680,29 @@ def run_ours(args, rank, world, local_rank):
         ms_sp_e2e = None if ms_sp_e2e >= 1e29 else ms_sp_e2e
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
-    small = None if args.no_small else run_small_batches(model, pool, dev, args)
+    small = None
+    if not args.no_small:
+        try:                                             # auxiliary legs never cost the headline line
+            small = run_small_batches(model, pool, dev, args)
+        except Exception as e:                           # noqa: BLE001
+            small = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     # the same 256-image step replayed as ONE CUDA graph ("graph-captured and eager both reported")
     graph_ms = None
-    if not args.no_small:
-        g = abcnet_b200.InferGraph(model, B, x.shape[2], x.shape[3], atom_cap=args.atom_cap, bond_cap=args.bond_cap, dtype=x.dtype)
-        for _ in range(3):
-            g.launch(x)
-        barrier()
-        t0.record()
-        for _ in range(args.steps):
-            g.launch(x)
-        t1.record()
-        barrier()
-        graph_ms = t0.elapsed_time(t1) / args.steps
-        del g
+    if not args.no_small and world == 1:                 # single-GPU configuration (configs[1]); no collective-style barriers inside the try
+        try:
+            g = abcnet_b200.InferGraph(model, B, x.shape[2], x.shape[3], atom_cap=args.atom_cap, bond_cap=args.bond_cap, dtype=x.dtype)
+            for _ in range(3):
+                g.launch(x)
+            barrier()
+            t0.record()
+            for _ in range(args.steps):
+                g.launch(x)
+            t1.record()
+            barrier()
+            graph_ms = t0.elapsed_time(t1) / args.steps
+            del g
+        except Exception:                                # noqa: BLE001
+            graph_ms = None
         torch.cuda.empty_cache()
     comparator = None
     train = None
@@ -708,7 +716,10 @@ def run_ours(args, rank, world, local_rank):
         model._packed = None
         out_bufs = xbuf = x = obufs = dec2 = None
         torch.cuda.empty_cache()
-        comparator = run_comparator(args, dev, pool, B)
+        try:
+            comparator = run_comparator(args, dev, pool, B)
+        except Exception as e:                           # noqa: BLE001
+            comparator = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if rank != 0:
         return
     pk, pk_src = peaks()

@@ -148,6 +148,11 @@ typedef struct AbcConvDesc {
    * (9 of the 16 (tap, phase) blocks are non-zero). The input tile is read once instead of four times and
    * a thread writes both px phases of a pixel = one full 32-byte sector. */
   int subpixel;
+  /* Optional K chunk (0 = min(cin, 64)): channels per pipeline stage, 16 / 32 / 64, dividing cin. The weight pack is laid out
+   * with the same kc ([n_tiles][cin/kc][ntaps][kc/8][n_tile][8]). Halving it halves the activation stage and the weight blocks and
+   * so deepens both shared-memory rings: for the 64-channel layers at 128 x 128, which are bound by pipeline depth rather than
+   * by the tensor pipe or HBM (profiles/r01_down2_3_swapfold_v33.summary.txt). The K order of the accumulation changes with it. */
+  int k_chunk;
 } AbcConvDesc;
 
 ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);
