@@ -708,7 +708,8 @@ def run_ours(args, rank, world, local_rank):
     train = None
     if not args.no_train:
         model._bufs.clear()
-        out_bufs = xbuf = x = None
+        model._packed = None
+        out_bufs = xbuf = x = obufs = dec2 = dec = None      # the inference legs' buffers (2 x 8.4 GB of logits among them)
         torch.cuda.empty_cache()
         train = run_train(args, rank, world, dev)
     if world == 1 and not args.no_comparator:
