@@ -63,6 +63,32 @@ def dense_decode_ops(outs):
             zbt.view(B, -1, nw, H, W).argmax(1), zr.abs())
 
 
+def record_level_maps(outs, thr=-1.0):
+    """Everything the decoded records depend on, as dense tensors (img2smiles.py:62-80, :115-124 and the per-peak rules of :134-182
+    vectorised): atom peaks + their three classes, and for every bond-centre peak the EMITTED omega bins (3-bin circular NMS, the
+    > thr test and the asymmetric half-circle rule of :143-158) + their bond types. Two logit sets give identical records (up to
+    the float rho) iff these maps agree -- used by tools/shard_infer.py --ref-check to compare the product with the fp32 torch
+    forward on every image of the 100 k-image run. outs: 8 NCHW fp32 tensors."""
+    za, zt, zc, zh, zb, zbt, zr, zw = [o.float() for o in outs]
+    B, nw, H, W = zw.shape
+    h = nw // 2
+    atom_pk = (F.max_pool2d(za, 3, 1, 1) == za) & (za > thr)
+    bond_pk = (F.max_pool2d(zb, 3, 1, 1) == zb) & (zb > thr)
+    left, right = torch.roll(zw, 1, 1), torch.roll(zw, -1, 1)
+    cand = (zw >= left) & (zw >= right) & (zw > thr)
+    surv = torch.zeros_like(cand)
+    lo = zw[:, :h - 1]                                                     # omega <= h - 2: dropped if z < max(z[w + h - 1], z[w + h])
+    surv[:, :h - 1] = (lo >= zw[:, h - 1:2 * h - 2]) & (lo >= zw[:, h:2 * h - 1])
+    surv[:, h - 1] = (zw[:, h - 1] >= zw[:, nw - 2]) & (zw[:, h - 1] >= zw[:, 0])      # sic: bins n - 2 and 0
+    surv[:, h] = (zw[:, h] > zw[:, 0]) & (zw[:, h] > zw[:, nw - 1])
+    hi = zw[:, h + 1:]                                                     # omega >= h + 1: dropped if z <= max(z[w - h - 1], z[w - h])
+    surv[:, h + 1:] = (hi > zw[:, :h - 1]) & (hi > zw[:, 1:h])
+    emitted = cand & surv & bond_pk
+    a_cls = torch.stack([zt.argmax(1), zc.argmax(1), zh.argmax(1)], 1) * atom_pk
+    b_type = zbt.view(B, -1, nw, H, W).argmax(1) * emitted
+    return atom_pk, a_cls, bond_pk, emitted, b_type
+
+
 def reference_loss(outs, targets, s, type_w):
     """train.py:95-137 as torch statements (same formulas as SURVEY App. C); rho / omega targets may be float64 (utils.py:91-92)."""
     za, zt, zc, zh, zb, zbt, zr, zw = [o.float() for o in outs]

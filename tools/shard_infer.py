@@ -55,6 +55,40 @@ def train_on_pool(model, pool, labels, steps, dev, batch=16, n_train=256):
     torch.cuda.synchronize()
 
 
+def ref_check(model, make_batch, ranges, B, dev):
+    """Every image of this rank's shard against the reference's graph executed by torch / cuDNN in fp32 with TF32 off (SURVEY D5:
+    the arithmetic of the CPU oracle) on the same GPU and weights, at RECORD level: two logit sets decode to the same records iff
+    gpu_comparator.record_level_maps agree (validated against the oracle decode on planted and dense random maps). Untimed second
+    pass; per-rank counts are summed on rank 0."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gpu_comparator as gc
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    c = dict(images=0, identical_records=0, identical_atom_peak_set=0, identical_bond_peak_set=0, identical_omega_set=0,
+             identical_classes=0, ref_atom_peaks=0, ref_bond_records=0, differing_atom_peaks=0, differing_bond_records=0)
+    outs = None
+    with torch.no_grad():
+        for (a, b) in ranges:
+            x = make_batch(a, b)
+            n = b - a
+            outs = model.infer(x, outs, layout="nchw")
+            mo = gc.record_level_maps([o[:n] for o in outs])
+            mr = gc.record_level_maps([o[:n] for o in gc.torch_forward(model, x)])
+            eq = [(p == q).flatten(1).all(1) for p, q in zip(mo, mr)]            # per image: atom_pk, a_cls, bond_pk, emitted, b_type
+            c["images"] += n
+            c["identical_atom_peak_set"] += int(eq[0].sum())
+            c["identical_bond_peak_set"] += int(eq[2].sum())
+            c["identical_omega_set"] += int(eq[3].sum())
+            c["identical_classes"] += int((eq[1] & eq[4]).sum())
+            c["identical_records"] += int((eq[0] & eq[1] & eq[3] & eq[4]).sum())
+            c["ref_atom_peaks"] += int(mr[0].sum())
+            c["ref_bond_records"] += int(mr[3].sum())
+            c["differing_atom_peaks"] += int((mo[0] != mr[0]).sum())
+            c["differing_bond_records"] += int((mo[3] != mr[3]).sum())
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return c
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=102400)
@@ -63,6 +97,8 @@ def main():
     ap.add_argument("--train-steps", type=int, default=0, help="train on pseudo-molecules first (rank 0) and broadcast the weights")
     ap.add_argument("--dump-subset", type=int, default=0, help="write weights + MOL blocks of the first M images to gpurun_out/")
     ap.add_argument("--weights", default="", help="load this state_dict (.pt) instead of training / random init")
+    ap.add_argument("--ref-check", action="store_true",
+                    help="second pass: compare every image with the fp32 torch / cuDNN forward (TF32 off) of the same weights at record level")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -165,12 +201,19 @@ def main():
         finish(len(ranges) - 1)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    ref = None
+    if args.ref_check:
+        ref = ref_check(model, make_batch, ranges, B, dev)
     if world > 1:
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = t.item()
         parts = [None] * world
         dist.all_gather_object(parts, (digests, n_mol))
+        if ref is not None:
+            refs = [None] * world
+            dist.all_gather_object(refs, ref)
+            ref = {k: sum(r[k] for r in refs) for k in ref}
     else:
         parts = [(digests, n_mol)]
     if rank == 0 and args.dump_subset:
@@ -191,7 +234,7 @@ def main():
         print(json.dumps({"tool": "shard_infer", "images": total, "n_gpus": world, "batch": B, "sparse_heads": bool(args.sparse),
                           "seconds": dt, "images_per_s": total / dt, "molecules": int(sum(n for _, n in parts)),
                           "batches": len(allb), "digest": h.hexdigest(), "weights": "trained on pseudo-molecules" if trained else "random init, calibrated",
-                          "subset_dumped": int(args.dump_subset),
+                          "subset_dumped": int(args.dump_subset), "ref_check_fp32_torch": ref,
                           "what": "forward + decode + native MOL-block assembly per image, sharded by contiguous image ranges, "
                                   "no data-path collective; digest over all MOL-block texts in global image order"}))
     if world > 1:
