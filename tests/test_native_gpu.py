@@ -51,3 +51,49 @@ def test_native_create_reports_missing_tensors():
     del sd["up2.up.weight"]
     with pytest.raises(RuntimeError, match="up2.up.weight"):
         NativeUNet(sd)
+
+
+def test_native_host_program(tmp_path):
+    """examples/native_host.cpp -- a host with neither Python nor torch -- compiled against include/abcnet_b200.h alone: same
+    peak / record counts per image and the same atom-centre logits as abcnet_b200.UNet + PeakDecoder."""
+    import os
+    import struct
+    import subprocess
+    import abcnet_b200
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "native_host"
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.run(["g++", "-std=c++17", "-O2", os.path.join(root, "examples", "native_host.cpp"), "-I", os.path.join(root, "include"),
+                    "-I", os.path.join(cuda, "include"), "-L", os.path.join(root, "abcnet_b200"), "-labcnet_b200",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", f"-Wl,-rpath,{os.path.join(root, 'abcnet_b200')}", "-o", str(exe)],
+                   check=True)
+    sd = unet_ref.make_state_dict(seed=31, variant="W1")
+    N, H, W = 3, 96, 64
+    x = torch.from_numpy(synth.binary_images(31, N, H, W, 0.08))
+    m = abcnet_b200.UNet(1, HEADS).cuda().eval()
+    m.load_state_dict(sd)
+    with torch.no_grad():                                   # move the centre / omega heads so that peaks exist, in the checkpoint itself
+        outs = m(x.cuda())
+        for k in (0, 4, 7):
+            sd[f"out_modules.{k}.conv2.bias"] = sd[f"out_modules.{k}.conv2.bias"] + float(-1.0 - torch.quantile(outs[k].flatten().float(), 0.99))
+    m.load_state_dict(sd)
+    with open(tmp_path / "weights.bin", "wb") as f:
+        for k, v in sd.items():
+            if not torch.is_floating_point(v):
+                continue
+            name = k.encode()
+            f.write(struct.pack("<i", len(name)) + name + struct.pack("<q", v.numel()) + v.detach().float().contiguous().numpy().tobytes())
+    (tmp_path / "images.u8").write_bytes((x > 0).to(torch.uint8).numpy().tobytes())
+    r = subprocess.run([str(exe), str(tmp_path / "weights.bin"), str(tmp_path / "images.u8"), str(N), str(H), str(W)],
+                       capture_output=True, text=True, env=dict(os.environ, LD_LIBRARY_PATH=os.path.join(cuda, "lib64") + ":" +
+                                                                os.environ.get("LD_LIBRARY_PATH", "")))
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    got = [tuple(int(v) for v in ln.split(":")[1].split()) for ln in lines[:N]]
+    logit_sum = float(lines[N].split()[-1])
+    p8 = m.infer(x.cuda(), layout="p8f")
+    recs = abcnet_b200.PeakDecoder(N, atom_cap=4096, bond_cap=16384)(p8)
+    want = [(len(a), len(b)) for a, b, _ in recs]
+    assert sum(a for a, _ in want) > 0
+    assert got == want, (got, want)
+    assert abs(logit_sum - float(p8[0].double().sum())) <= 1e-3 * float(p8[0].double().abs().sum())

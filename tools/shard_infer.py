@@ -65,7 +65,8 @@ def ref_check(model, make_batch, ranges, B, dev):
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     c = dict(images=0, identical_records=0, identical_atom_peak_set=0, identical_bond_peak_set=0, identical_omega_set=0,
-             identical_classes=0, ref_atom_peaks=0, ref_bond_records=0, differing_atom_peaks=0, differing_bond_records=0)
+             identical_classes=0, ref_atom_peaks=0, ref_bond_records=0, differing_atom_peaks=0, differing_bond_records=0,
+             tf32_identical_records=0, tf32_differing_atom_peaks=0, tf32_differing_bond_records=0)
     outs = None
     with torch.no_grad():
         for (a, b) in ranges:
@@ -85,6 +86,15 @@ def ref_check(model, make_batch, ranges, B, dev):
             c["ref_bond_records"] += int(mr[3].sum())
             c["differing_atom_peaks"] += int((mo[0] != mr[0]).sum())
             c["differing_bond_records"] += int((mo[3] != mr[3]).sum())
+            # yardstick: the reference's OWN default GPU arithmetic (cuDNN TF32 convolutions) against its fp32 arithmetic,
+            # same weights, same images, same metric -- how stable are the decode decisions of this network at all?
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+            mt = gc.record_level_maps([o[:n] for o in gc.torch_forward(model, x)])
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            eqt = [(p == q).flatten(1).all(1) for p, q in zip(mt, mr)]
+            c["tf32_identical_records"] += int((eqt[0] & eqt[1] & eqt[3] & eqt[4]).sum())
+            c["tf32_differing_atom_peaks"] += int((mt[0] != mr[0]).sum())
+            c["tf32_differing_bond_records"] += int((mt[3] != mr[3]).sum())
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     return c
 
