@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libabcnet_b200.so")
 
 EXPORTS = (
     "abc_last_error", "abc_version", "abc_device_ok", "abc_sm_count", "abc_launch_count",
-    "abc_conv3x3_c1", "abc_conv3x3_c1_u8", "abc_conv3x3_cn", "abc_conv3x3_cn_wgrad", "abc_conv_igemm", "abc_conv_wpack_bytes", "abc_decode_peaks",
+    "abc_conv3x3_c1", "abc_conv3x3_c1_u8", "abc_conv3x3_cn", "abc_conv3x3_cn_wgrad", "abc_conv3x3_stem", "abc_conv_igemm", "abc_conv_wpack_bytes", "abc_decode_peaks",
     "abc_loss_partials", "abc_loss_backward",
     "abc_bn_stats", "abc_bn_finalize", "abc_bn_act", "abc_bn_act_backward", "abc_nchw_to_p8", "abc_channel_sum",
     "abc_nchw_to_p8_ex", "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
@@ -37,12 +37,12 @@ class AbcConvDesc(C.Structure):
         ("pool_out", C.c_void_p), ("pool_planes", C.c_int), ("pool_plane_off", C.c_int),
         ("k_segments", C.c_int), ("seg_tap0", C.c_int * 4), ("seg_ntaps", C.c_int * 4),
         ("row_fold", C.c_int), ("cta_pair", C.c_int), ("swap_mn", C.c_int),
-        ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p), ("subpixel", C.c_int), ("k_chunk", C.c_int),
+        ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p), ("subpixel", C.c_int), ("k_chunk", C.c_int), ("act_fp16", C.c_int),
     ]
 
 
 class AbcUNetConfig(C.Structure):
-    _fields_ = [("in_channels", C.c_int), ("n_heads", C.c_int), ("heads", C.c_int * 16), ("crop_first", C.c_int)]
+    _fields_ = [("in_channels", C.c_int), ("n_heads", C.c_int), ("heads", C.c_int * 16), ("crop_first", C.c_int), ("act_fp16", C.c_int)]
 
 
 class AbcNamedTensor(C.Structure):
@@ -153,6 +153,8 @@ def _load():
     lib.abc_conv3x3_c1_u8.argtypes = lib.abc_conv3x3_c1.argtypes
     lib.abc_conv3x3_cn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.abc_conv3x3_stem.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.abc_conv3x3_cn_wgrad.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p]
     lib.abc_conv_igemm.argtypes = [C.POINTER(AbcConvDesc), C.c_void_p]

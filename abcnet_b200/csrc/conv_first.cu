@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "p8_device.cuh"
 
 namespace abc {
 
@@ -38,21 +39,11 @@ __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const T* __restrict__ i
     float a = ws[144 + co];
 #pragma unroll
     for (int k = 0; k < 9; ++k) a = fmaf(t[k], ws[co * 9 + k], a);
-    v[co] = relu ? fmaxf(a, 0.f) : a;
+    v[co] = (relu & 1) ? fmaxf(a, 0.f) : a;
   }
 #pragma unroll
-  for (int pl = 0; pl < 2; ++pl) {
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[pl * 8 + 0], v[pl * 8 + 1]);
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[pl * 8 + 2], v[pl * 8 + 3]);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[pl * 8 + 4], v[pl * 8 + 5]);
-    __nv_bfloat162 p3 = __floats2bfloat162_rn(v[pl * 8 + 6], v[pl * 8 + 7]);
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&p0);
-    o.y = *reinterpret_cast<uint32_t*>(&p1);
-    o.z = *reinterpret_cast<uint32_t*>(&p2);
-    o.w = *reinterpret_cast<uint32_t*>(&p3);
-    out[((static_cast<size_t>(n) * out_planes + out_plane_off + pl) * H + y) * W + x] = o;
-  }
+  for (int pl = 0; pl < 2; ++pl)
+    out[((static_cast<size_t>(n) * out_planes + out_plane_off + pl) * H + y) * W + x] = pack8_act16(v + pl * 8, (relu & 2) != 0);
 }
 
 // Streaming variant (the default): one warp owns a 128-pixel-wide, kC1Rows-high strip and walks down its rows.
@@ -69,18 +60,8 @@ __global__ void __launch_bounds__(256) conv3x3_c1_kernel(const T* __restrict__ i
 //    fp32 images still work.
 constexpr int kC1Rows = 16;
 
-__device__ __forceinline__ uint4 c1_pack8(const float* a) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0], a[1]);
-  __nv_bfloat162 p1 = __floats2bfloat162_rn(a[2], a[3]);
-  __nv_bfloat162 p2 = __floats2bfloat162_rn(a[4], a[5]);
-  __nv_bfloat162 p3 = __floats2bfloat162_rn(a[6], a[7]);
-  uint4 q;
-  q.x = *reinterpret_cast<uint32_t*>(&p0);
-  q.y = *reinterpret_cast<uint32_t*>(&p1);
-  q.z = *reinterpret_cast<uint32_t*>(&p2);
-  q.w = *reinterpret_cast<uint32_t*>(&p3);
-  return q;
-}
+// `relu` carries two flags in all stem kernels: bit 0 = ReLU, bit 1 = fp16 output instead of bf16 (abc_conv3x3_stem)
+__device__ __forceinline__ uint4 c1_pack8(const float* a, int flags) { return pack8_act16(a, (flags & 2) != 0); }
 
 // Arithmetic path for one pixel (non-binary inputs); ws = [tap][co] weights followed by bias[co]. Out of line: rare.
 template <typename T>
@@ -101,9 +82,9 @@ __device__ __noinline__ void c1_generic_pixel(const T* __restrict__ im, int y, i
       float a = ws[144 + co];
 #pragma unroll
       for (int k = 0; k < 9; ++k) a = fmaf(t[k], ws[k * 16 + co], a);
-      v[c8] = relu ? fmaxf(a, 0.f) : a;
+      v[c8] = (relu & 1) ? fmaxf(a, 0.f) : a;
     }
-    *(pl ? o1 : o0) = c1_pack8(v);
+    *(pl ? o1 : o0) = c1_pack8(v, relu);
   }
 }
 
@@ -128,9 +109,9 @@ __global__ void __launch_bounds__(256, 4) conv3x3_c1_rows_kernel(const T* __rest
         float a = ws[144 + co];
 #pragma unroll
         for (int k = 0; k < 9; ++k) a = fmaf(((e >> k) & 1) ? 1.f : 0.f, ws[k * 16 + co], a);
-        v[c8] = relu ? fmaxf(a, 0.f) : a;
+        v[c8] = (relu & 1) ? fmaxf(a, 0.f) : a;
       }
-      lut[e][pl] = c1_pack8(v);
+      lut[e][pl] = c1_pack8(v, relu);
     }
   }
   __syncthreads();
@@ -247,22 +228,13 @@ __global__ void __launch_bounds__(256) conv3x3_cn_kernel(const float* __restrict
       v[co] = a;
     }
   }
+  if (relu & 1) {
 #pragma unroll
-  for (int pl = 0; pl < 2; ++pl) {
-    uint4 o;
-    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a = v[pl * 8 + 2 * i], c = v[pl * 8 + 2 * i + 1];
-      if (relu) {
-        a = fmaxf(a, 0.f);
-        c = fmaxf(c, 0.f);
-      }
-      __nv_bfloat162 pk = __floats2bfloat162_rn(a, c);
-      ow[i] = *reinterpret_cast<uint32_t*>(&pk);
-    }
-    out[((static_cast<size_t>(n) * out_planes + out_plane_off + pl) * H + y) * W + x] = o;
+    for (int co = 0; co < 16; ++co) v[co] = fmaxf(v[co], 0.f);
   }
+#pragma unroll
+  for (int pl = 0; pl < 2; ++pl)
+    out[((static_cast<size_t>(n) * out_planes + out_plane_off + pl) * H + y) * W + x] = pack8_act16(v + pl * 8, (relu & 2) != 0);
 }
 
 }  // namespace abc
@@ -326,4 +298,17 @@ extern "C" int abc_conv3x3_c1_raw(const void* img, int img_is_u8, const float* w
   if (img_is_u8)
     return conv3x3_c1_launch<uint8_t>(static_cast<const uint8_t*>(img), w, b, out, N, H, W, out_planes, out_plane_off, stream, 0);
   return conv3x3_c1_launch<float>(static_cast<const float*>(img), w, b, out, N, H, W, out_planes, out_plane_off, stream, 0);
+}
+
+
+extern "C" int abc_conv3x3_stem(const void* img, int img_is_u8, int cin, const float* w, const float* b, void* out, int N, int H, int W,
+                                int out_planes, int out_plane_off, int flags, void* stream) {
+  ABC_REQUIRE(flags >= 0 && flags <= 3, "abc_conv3x3_stem: flags=%d (bit 0 ReLU, bit 1 fp16 output)", flags);
+  if (cin != 1) {
+    ABC_REQUIRE(!img_is_u8, "abc_conv3x3_stem: uint8 images are the 1-channel binarised format");
+    return abc_conv3x3_cn(static_cast<const float*>(img), cin, w, b, out, N, H, W, out_planes, out_plane_off, flags, stream);
+  }
+  if (img_is_u8)
+    return conv3x3_c1_launch<uint8_t>(static_cast<const uint8_t*>(img), w, b, out, N, H, W, out_planes, out_plane_off, stream, flags);
+  return conv3x3_c1_launch<float>(static_cast<const float*>(img), w, b, out, N, H, W, out_planes, out_plane_off, stream, flags);
 }

@@ -62,6 +62,7 @@ struct ConvKParams {
   void* pool_out;
   int pool_planes, pool_plane_off;
   int subpixel;                              // channels per sub-pixel phase (AbcConvDesc.subpixel), 0 = off
+  int fp16;                                  // activations / weights are IEEE fp16 instead of bf16 (AbcConvDesc.act_fp16)
   // fused train-mode BatchNorm statistics (AbcConvDesc.stat_sum / stat_sq): per output channel sum / sum of squares of the
   // bf16-rounded outputs, accumulated per thread over the CTA's whole tile loop, one fp64 atomic per thread at the end
   double* stat_sum;
@@ -87,39 +88,33 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   return r;
 }
 
-__device__ __forceinline__ uint32_t pool_max_bf16x2(uint32_t a) {
+// 2x2 max-pool helpers on packed 16-bit pairs (bf16 or fp16: f16)
+__device__ __forceinline__ uint32_t pool_max_bf16x2(uint32_t a, bool f16) {
   uint32_t b = __shfl_xor_sync(0xffffffffu, a, 1);
-  __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  a = *reinterpret_cast<uint32_t*>(&m);
+  a = max2_act16(a, b, f16);
   b = __shfl_xor_sync(0xffffffffu, a, 8);
-  m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  return *reinterpret_cast<uint32_t*>(&m);
+  return max2_act16(a, b, f16);
 }
 
-__device__ __forceinline__ uint32_t hmax_bf16x2(uint32_t a, uint32_t b) {
-  __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  return *reinterpret_cast<uint32_t*>(&m);
-}
-
-__device__ __forceinline__ uint4 hmax_bf16x8(uint4 a, uint4 b) {
-  return make_uint4(hmax_bf16x2(a.x, b.x), hmax_bf16x2(a.y, b.y), hmax_bf16x2(a.z, b.z), hmax_bf16x2(a.w, b.w));
+__device__ __forceinline__ uint4 hmax_bf16x8(uint4 a, uint4 b, bool f16) {
+  return make_uint4(max2_act16(a.x, b.x, f16), max2_act16(a.y, b.y, f16), max2_act16(a.z, b.z, f16), max2_act16(a.w, b.w, f16));
 }
 
 // max with the horizontally adjacent pixel (lane ^ 1)
-__device__ __forceinline__ uint4 pool_hmax_x(uint4 q) {
+__device__ __forceinline__ uint4 pool_hmax_x(uint4 q, bool f16) {
   uint4 o;
   o.x = __shfl_xor_sync(0xffffffffu, q.x, 1);
   o.y = __shfl_xor_sync(0xffffffffu, q.y, 1);
   o.z = __shfl_xor_sync(0xffffffffu, q.z, 1);
   o.w = __shfl_xor_sync(0xffffffffu, q.w, 1);
-  return hmax_bf16x8(q, o);
+  return hmax_bf16x8(q, o, f16);
 }
 
-__device__ __forceinline__ uint4 pool_max_bf16x8(uint4 q) {
-  q.x = pool_max_bf16x2(q.x);
-  q.y = pool_max_bf16x2(q.y);
-  q.z = pool_max_bf16x2(q.z);
-  q.w = pool_max_bf16x2(q.w);
+__device__ __forceinline__ uint4 pool_max_bf16x8(uint4 q, bool f16) {
+  q.x = pool_max_bf16x2(q.x, f16);
+  q.y = pool_max_bf16x2(q.y, f16);
+  q.z = pool_max_bf16x2(q.z, f16);
+  q.w = pool_max_bf16x2(q.w, f16);
   return q;
 }
 
@@ -297,7 +292,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = SWAP ? umma_idesc_bf16(128, 256, 0, 0) : umma_idesc_bf16(CG2 ? 256 : 128, p.n_tile, 0, 0);
+    const bool f16 = p.fp16 != 0;
+    const uint32_t idesc = SWAP ? umma_idesc_16(128, 256, 0, 0, f16) : umma_idesc_16(CG2 ? 256 : 128, p.n_tile, 0, 0, f16);
     const int b_rows = CG2 ? p.n_tile >> 1 : p.n_tile;          // weight rows held by this CTA
     auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t a_hi_, uint32_t b_lo, uint32_t b_hi_, uint32_t acc_) {
       if (CG2) umma_bf16_lohi_pair(d, a_lo, a_hi_, b_lo, b_hi_, idesc, acc_);
@@ -461,7 +457,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const int m0 = q * 32 + g8 * 8;
     const int fj = m0 / cpj, ch0 = m0 - fj * cpj;
     uint8_t* stage = smem + kHeaderBytes + (warp - 4) * kSwapWarpBytes;
-    __nv_bfloat16* st_w = reinterpret_cast<__nv_bfloat16*>(stage) + lane;                     // + pixel * (kSwapRowBytes / 2)
+    unsigned short* st_w = reinterpret_cast<unsigned short*>(stage) + lane;                 // + pixel * (kSwapRowBytes / 2)
+    const bool f16 = p.fp16 != 0;
     const uint4* st_r = reinterpret_cast<const uint4*>(stage + i8 * kSwapRowBytes + g8 * 16);  // + row * 8 * kSwapRowBytes / 16
     const bool plane_ok = (n0 + ch0) < p.cout;
     const size_t out_plane_px = static_cast<size_t>(p.out_H) * p.out_W;
@@ -497,10 +494,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float t = __uint_as_float(raw[i]) + bias;
-          const __nv_bfloat16 hv = __float2bfloat16_rn(fmaxf(t, t * slope));
+          const unsigned short hv = to_act16(fmaxf(t, t * slope), f16);
           st_w[i * (kSwapRowBytes / 2)] = hv;
-          if (do_stats && ((vmask >> i) & 1u)) {
-            const float r = __bfloat162float(hv);
+          if (do_stats && ((vmask >> i) & 1u)) {              // training (bf16 only, checked on the host)
+            const float r = __uint_as_float(static_cast<uint32_t>(hv) << 16);
             st_s += r;
             st_q = fmaf(r, r, st_q);
           }
@@ -555,6 +552,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
     const int units = (p.mt * p.n_tile) >> 4;
     const int nchunks = (units + 1) >> 1;
     const float slope = p.act == 1 ? 0.f : (p.act == 2 ? 0.01f : 1.f);     // act(v) = max(v, slope * v)
+    const bool f16 = p.fp16 != 0;
     const float4* bias4 = reinterpret_cast<const float4*>(bias_s);
     const size_t out_plane_px = static_cast<size_t>(p.out_H) * p.out_W;
     const int ph = p.H >> 1, pw = p.W >> 1;
@@ -614,7 +612,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
             v[4 * i + 3] = fmaxf(t3, t3 * slope);
           }
           if (p.out_mode == 0) {
-            uint4 q0 = pack8_bf16(v), q1 = pack8_bf16(v + 8);
+            uint4 q0 = pack8_act16(v, f16), q1 = pack8_act16(v + 8, f16);
             if constexpr (STATS) {
               if (valid) {
                 float r[16];
@@ -646,8 +644,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
               bool write;
               if (p.fold == 1) {
                 // lane <-> pixel: xor 1 = x neighbour, xor 8 = y neighbour
-                q0 = pool_max_bf16x8(q0);
-                q1 = pool_max_bf16x8(q1);
+                q0 = pool_max_bf16x8(q0, f16);
+                q1 = pool_max_bf16x8(q1, f16);
                 write = !(c & 1) && !(r & 1);
               } else {
                 // folded rows: the vertical neighbour (j ^ 1) is the other half of this chunk, in the same thread
@@ -656,8 +654,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap, const ConvKParams p)
                   keep1 = q1;
                   continue;
                 }
-                q0 = pool_hmax_x(hmax_bf16x8(q0, keep0));
-                q1 = pool_hmax_x(hmax_bf16x8(q1, keep1));
+                q0 = pool_hmax_x(hmax_bf16x8(q0, keep0, f16), f16);
+                q1 = pool_hmax_x(hmax_bf16x8(q1, keep1, f16), f16);
                 write = !(c & 1);
               }
               if (valid && write) {
@@ -973,6 +971,8 @@ extern "C" int abc_conv_igemm(const AbcConvDesc* d, void* stream_) {
   p.out_sy = d->out_sy; p.out_oy = d->out_oy; p.out_sx = d->out_sx; p.out_ox = d->out_ox;
   p.pool_out = d->pool_out; p.pool_planes = d->pool_planes; p.pool_plane_off = d->pool_plane_off;
   p.subpixel = subpixel;
+  p.fp16 = d->act_fp16 ? 1 : 0;
+  ABC_REQUIRE(!(p.fp16 && (want_pair || d->stat_sum)), "abc_conv_igemm: act_fp16 is an inference mode (no cta_pair, no fused statistics)");
   cudaStream_t st_ = static_cast<cudaStream_t>(stream_);
   // fused BatchNorm statistics (training forward)
   const bool stats = d->stat_sum != nullptr || d->stat_sq != nullptr;

@@ -2,6 +2,7 @@
 // (un)packing, activation derivatives and the counter-based dropout mask of the head BatchNorm (src/unet.py:69).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace abc {
@@ -19,6 +20,43 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   return u;
+}
+
+// fp32 -> one 16-bit activation value in the storage format of the launch: bf16 (default) or IEEE fp16 (AbcConvDesc.act_fp16;
+// saturating, fp16 has no headroom beyond 65504). Returned as raw bits.
+__device__ __forceinline__ unsigned short to_act16(float v, bool fp16) {
+  if (fp16) return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ uint32_t pack2_act16(float a, float b, bool fp16) {
+  return static_cast<uint32_t>(to_act16(a, fp16)) | (static_cast<uint32_t>(to_act16(b, fp16)) << 16);
+}
+__device__ __forceinline__ uint4 pack8_act16(const float* v, bool fp16) {
+  uint4 r;
+  if (fp16) {                                   // one (warp-uniform) branch per vector, two straight-line conversion sequences
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      h[i] = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f), fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
+    r.x = *reinterpret_cast<uint32_t*>(&h[0]); r.y = *reinterpret_cast<uint32_t*>(&h[1]);
+    r.z = *reinterpret_cast<uint32_t*>(&h[2]); r.w = *reinterpret_cast<uint32_t*>(&h[3]);
+  } else {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    r.x = *reinterpret_cast<uint32_t*>(&h[0]); r.y = *reinterpret_cast<uint32_t*>(&h[1]);
+    r.z = *reinterpret_cast<uint32_t*>(&h[2]); r.w = *reinterpret_cast<uint32_t*>(&h[3]);
+  }
+  return r;
+}
+// element-wise max of two packed pairs in that format
+__device__ __forceinline__ uint32_t max2_act16(uint32_t a, uint32_t b, bool fp16) {
+  if (fp16) {
+    __half2 m = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&m);
+  }
+  __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&m);
 }
 
 __device__ __forceinline__ float act_grad(float pre, int act) {

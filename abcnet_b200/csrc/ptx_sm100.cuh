@@ -210,5 +210,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// Same with the 16-bit operand format as a parameter: A / B format fields (bits 7-9, 10-12) 0 = FP16, 1 = BF16; D = FP32.
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int a_mn_major, int b_mn_major, bool fp16) {
+  return umma_idesc_bf16(M, N, a_mn_major, b_mn_major) & ~(fp16 ? ((1u << 7) | (1u << 10)) : 0u);
+}
 
 }  // namespace abc

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -81,7 +82,7 @@ struct Logical {
   float& at(int t, int r, int c) { return w[(static_cast<size_t>(t) * rows + r) * cin + c]; }
 };
 
-static void append_pack(std::vector<uint8_t>& arena, PackedConv& pc, Logical& L, int n_tile) {
+static void append_pack(std::vector<uint8_t>& arena, PackedConv& pc, Logical& L, int n_tile, bool fp16) {
   const int kc = L.cin < 64 ? L.cin : 64;
   const int n_tiles = (L.rows + n_tile - 1) / n_tile;
   pc.n_tile = n_tile;
@@ -91,7 +92,7 @@ static void append_pack(std::vector<uint8_t>& arena, PackedConv& pc, Logical& L,
   pc.w_off = static_cast<int64_t>(arena.size());
   const size_t n_el = static_cast<size_t>(n_tiles) * n_tile * L.cin * L.ntaps;
   arena.resize(arena.size() + n_el * 2);
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(arena.data() + pc.w_off);
+  uint16_t* dst = reinterpret_cast<uint16_t*>(arena.data() + pc.w_off);
   size_t o = 0;
   for (int nt = 0; nt < n_tiles; ++nt)
     for (int c = 0; c < L.cin / kc; ++c)
@@ -100,7 +101,14 @@ static void append_pack(std::vector<uint8_t>& arena, PackedConv& pc, Logical& L,
           for (int r = 0; r < n_tile; ++r)
             for (int e = 0; e < 8; ++e) {
               const int row = nt * n_tile + r;
-              dst[o++] = __float2bfloat16_rn(row < L.rows ? L.at(t, row, c * kc + p * 8 + e) : 0.f);
+              const float v = row < L.rows ? L.at(t, row, c * kc + p * 8 + e) : 0.f;
+              if (fp16) {
+                const __half hv = __float2half_rn(v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v));
+                memcpy(&dst[o++], &hv, 2);
+              } else {
+                const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+                memcpy(&dst[o++], &bv, 2);
+              }
             }
   while (arena.size() % 256) arena.push_back(0);
   pc.b_off = static_cast<int64_t>(arena.size());
@@ -151,7 +159,7 @@ static bool folded_conv(const Tensors& T, const std::string& conv, const std::st
 
 // 3x3 conv [cout][cin][3][3] (folded) -> packed, with the row-folding / operand-swap layout the layer uses
 static void pack3x3(std::vector<uint8_t>& arena, PackedConv& pc, const std::vector<float>& w, const std::vector<float>& b, int cout, int cin,
-                    bool plain_output) {
+                    bool plain_output, bool fp16) {
   const int js = swap_fold_for(cin, cout, plain_output);
   const int J = js ? js : row_fold_for(cin, cout);
   pc.cout = cout;
@@ -171,7 +179,7 @@ static void pack3x3(std::vector<uint8_t>& arena, PackedConv& pc, const std::vect
       for (int co = 0; co < cout; ++co)
         for (int ci = 0; ci < cin; ++ci) L.at(t, co, ci) = W(co, ci, t / 3 - 1, t % 3 - 1);
     }
-    append_pack(arena, pc, L, default_n_tile(cin, cout));
+    append_pack(arena, pc, L, default_n_tile(cin, cout), fp16);
     return;
   }
   // Toeplitz expansion along y (AbcConvDesc.row_fold / swap_mn): folded taps t' = 3 r + c, r in [0, J + 2)
@@ -195,7 +203,7 @@ static void pack3x3(std::vector<uint8_t>& arena, PackedConv& pc, const std::vect
       }
   for (int j = 0; j < J; ++j)
     for (int co = 0; co < cout; ++co) L.bias[js ? j * cout + co : ((co / 16) * J + j) * 16 + (co % 16)] = b[co];
-  append_pack(arena, pc, L, J * cout);
+  append_pack(arena, pc, L, J * cout, fp16);
   pc.ntaps = 9;                                  // descriptor ntaps (the kernel derives the folded count)
 }
 
@@ -268,6 +276,7 @@ extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* t
   }
   auto* h = new UNetHandle();
   h->cfg = *cfg;
+  const bool fp16 = cfg->act_fp16 != 0;
   std::vector<uint8_t> arena;
   arena.reserve(64 << 20);
   std::vector<float> w, b;
@@ -291,7 +300,7 @@ extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* t
         memcpy(arena.data() + h->stem_b_off, b.data(), 64);
         continue;
       }
-      pack3x3(arena, h->convs[name], w, b, cout, cin, !is_pooled(name));
+      pack3x3(arena, h->convs[name], w, b, cout, cin, !is_pooled(name), fp16);
     }
   }
   // ---- up-sampling convolutions: the four sub-pixel phases as blocks of the N axis (AbcConvDesc.subpixel)
@@ -345,7 +354,7 @@ extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* t
     }
     pc.cout = 4 * cout;
     pc.subpixel = cout;
-    append_pack(arena, pc, L, cout % 64 == 0 ? 256 : 128);
+    append_pack(arena, pc, L, cout % 64 == 0 ? 256 : 128, fp16);
   }
   // ---- heads: the conv1 of all heads as one N = 128 * n_heads GEMM; conv2 per head
   {
@@ -371,7 +380,7 @@ extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* t
       pc.tap_dx[t] = t % 3 - 1;
     }
     pc.cout = 128 * nh;
-    append_pack(arena, pc, L, 256);
+    append_pack(arena, pc, L, 256, fp16);
     for (int i = 0; i < nh; ++i) {
       const int hc = cfg->heads[i];
       const std::string om = "out_modules." + std::to_string(i);
@@ -386,7 +395,7 @@ extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* t
       L2.bias.assign(b2, b2 + hc);
       PackedConv& p2 = h->convs["heads." + std::to_string(i) + ".conv2"];
       p2.cout = hc;
-      append_pack(arena, p2, L2, head_conv2_n_tile(hc));
+      append_pack(arena, p2, L2, head_conv2_n_tile(hc), fp16);
     }
   }
   if (static_cast<int64_t>(arena.size()) > wpack_bytes) {
@@ -453,6 +462,7 @@ extern "C" int abc_unet_forward_infer(AbcUNet* net, const void* img, int img_is_
     d.out_H = hh * d.out_sy; d.out_W = ww * d.out_sx;
     d.pool_out = pool; d.pool_planes = pool_planes;
     d.row_fold = pc.fold; d.subpixel = pc.subpixel;
+    d.act_fp16 = cfg.act_fp16 ? 1 : 0;
     d.swap_mn = (!pc.subpixel && pc.n_tile == 128 && (pc.fold == 1 || pc.fold_swap) && dst != nullptr && pool == nullptr) ? 1 : 0;
     return abc_conv_igemm(&d, stream);
   };
@@ -463,9 +473,7 @@ extern "C" int abc_unet_forward_infer(AbcUNet* net, const void* img, int img_is_
 
   const float* sw = reinterpret_cast<const float*>(h->arena + h->stem_w_off);
   const float* sb = reinterpret_cast<const float*>(h->arena + h->stem_b_off);
-  if (cfg.in_channels != 1) RUN(abc_conv3x3_cn(static_cast<const float*>(img), cfg.in_channels, sw, sb, a, N, H, W, 2, 0, 1, stream));
-  else if (img_is_u8) RUN(abc_conv3x3_c1_u8(static_cast<const uint8_t*>(img), sw, sb, a, N, H, W, 2, 0, stream));
-  else RUN(abc_conv3x3_c1(static_cast<const float*>(img), sw, sb, a, N, H, W, 2, 0, stream));
+  RUN(abc_conv3x3_stem(img, img_is_u8 ? 1 : 0, cfg.in_channels, sw, sb, a, N, H, W, 2, 0, 1 | (cfg.act_fp16 ? 2 : 0), stream));
   RUN(conv("inc1.3", a, 2, H, W, b, 2, 0, 1, nullptr, 0));
   RUN(conv("inc2.0", b, 2, H, W, a, 2, 0, 1, nullptr, 0));
   RUN(conv("inc2.3", a, 2, H, W, nullptr, 0, 0, 1, p1, 2));                       // x1 is never used as a skip
@@ -510,6 +518,7 @@ extern "C" int abc_unet_forward_infer(AbcUNet* net, const void* img, int img_is_
     d.out = out_ptrs[i]; d.out_planes = d.out_mode == 2 ? (pc.cout + 7) / 8 : 0; d.out_plane_off = 0;
     d.out_H = H / 4; d.out_W = W / 4; d.out_sy = d.out_sx = 1;
     d.row_fold = 1;
+    d.act_fp16 = cfg.act_fp16 ? 1 : 0;
     RUN(abc_conv_igemm(&d, stream));
   }
 #undef RUN

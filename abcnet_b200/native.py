@@ -20,12 +20,15 @@ from .unet import HeadMaps
 class NativeUNet:
     """net = NativeUNet(state_dict, in_channels=1, heads=[1, 14, 3, 2, 1, 360, 60, 60]); outs = net(x)  # x: CUDA [B,C,H,W]"""
 
-    def __init__(self, state_dict, in_channels=1, heads=(1, 14, 3, 2, 1, 360, 60, 60), crop_first=True, device=None):
+    def __init__(self, state_dict, in_channels=1, heads=(1, 14, 3, 2, 1, 360, 60, 60), crop_first=True, device=None, act_dtype="bf16"):
         _lib.require_device()
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.heads = list(heads)
         cfg = self.cfg = AbcUNetConfig()
+        if act_dtype not in ("bf16", "fp16"):
+            raise ValueError("act_dtype must be 'bf16' or 'fp16'")
         cfg.in_channels, cfg.n_heads, cfg.crop_first = int(in_channels), len(self.heads), int(bool(crop_first))
+        cfg.act_fp16 = int(act_dtype == "fp16")
         for i, h in enumerate(self.heads):
             cfg.heads[i] = int(h)
         n = lib.abc_unet_wpack_bytes(C.byref(cfg))

@@ -49,8 +49,9 @@ class SparseHeadsPipeline:
         self.peak_pix = torch.zeros((batch, 2, peak_cap), dtype=torch.int32, device=dev)
         self.peak_cnt = torch.zeros((batch, 2), dtype=torch.int32, device=dev)
         rows = self.P // 8
-        self.patches = torch.zeros((1, 144, rows, 8, 8), dtype=torch.bfloat16, device=dev)      # unused slots stay finite
-        self.hid_c = torch.zeros((1, 128, rows, 8, 8), dtype=torch.bfloat16, device=dev)
+        adt = model._act_torch_dtype                                                              # 16-bit storage format of the model
+        self.patches = torch.zeros((1, 144, rows, 8, 8), dtype=adt, device=dev)                  # unused slots stay finite
+        self.hid_c = torch.zeros((1, 128, rows, 8, 8), dtype=adt, device=dev)
         self.logits_c = {k: torch.zeros((1, (V2_HEADS[k] + 7) // 8, rows, 8, 8), dtype=torch.float32, device=dev) for k in _CLASS_HEADS}
         self._bufs = {}
         self._centre_pack = None
@@ -75,10 +76,11 @@ class SparseHeadsPipeline:
         if self._centre_pack is None or self._centre_key != m._pack_gen:
             wt, bias, _ = m._heads_w1                                    # [9, 1024, 128] BN-folded conv1 of all heads
             sel = torch.cat([torch.arange(0, 128), torch.arange(512, 640)]).to(wt.device)       # heads 0 and 4
-            self._centre_pack = _Packed(wt[:, sel].contiguous(), bias[sel].contiguous(), [(dy, dx) for (dy, dx, _, _) in _TAPS3], 256, 256)
+            self._centre_pack = _Packed(wt[:, sel].contiguous(), bias[sel].contiguous(), [(dy, dx) for (dy, dx, _, _) in _TAPS3], 256, 256,
+                                        dtype=m._act_torch_dtype)
             self._centre_key = m._pack_gen
         # dense centre heads
-        hid2 = self._buf("hid2", (B, 32, H4, W4, 8), torch.bfloat16)
+        hid2 = self._buf("hid2", (B, 32, H4, W4, 8), m._act_torch_dtype)
         m._conv(self._centre_pack, k2, 0, hid2, act=2, stream=st)
         za = self._buf("za", (B, 1, H4, W4), torch.float32)
         zb = self._buf("zb", (B, 1, H4, W4), torch.float32)
@@ -160,3 +162,4 @@ class _PackView:
         self.cin = pk.cin * len(pk.taps)
         self.taps = [(0, 0)]
         self.fold, self.pair = 1, False
+        self.fp16 = getattr(pk, "fp16", False)

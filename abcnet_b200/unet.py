@@ -169,7 +169,7 @@ def fold_rows(w_taps, bias, taps, J):
 class _Packed:
     """Device-resident, kernel-ready form of one convolution: packed bf16 weights + fp32 bias + tap list."""
 
-    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1, pair=None, fold_swap=False, kc=None):
+    def __init__(self, w_taps, bias, taps, n_tile, cout, fold=1, pair=None, fold_swap=False, kc=None, dtype=torch.bfloat16):
         # w_taps: fp32 [ntaps, cout, cin] (already BN-folded); taps: list of (dy, dx)
         # pair: CTA-pair mode (AbcConvDesc.cta_pair); None = decide from the layer size (weights too large to stay resident)
         # fold_swap: row folding in the row order of the operand-swap kernel (the launch must then use swap_mn)
@@ -192,7 +192,8 @@ class _Packed:
             w = pair_pack(w_taps, n_tiles, n_tile)
         else:
             w = w_taps.view(ntaps, n_tiles, n_tile, cin // kc, kc // 8, 8).permute(1, 3, 0, 4, 2, 5)
-        self.w = w.contiguous().to(torch.bfloat16)
+        self.fp16 = dtype == torch.float16            # AbcConvDesc.act_fp16: weights AND activations of the launch are fp16
+        self.w = (w.contiguous().clamp(-65504.0, 65504.0) if self.fp16 else w.contiguous()).to(dtype)
         assert self.w.numel() * 2 == lib.abc_conv_wpack_bytes(cin, co, ntaps, n_tile)
         self.bias = bias.contiguous().float()
         self.taps, self.n_tile, self.cout, self.cin = taps, n_tile, cout, cin
@@ -253,8 +254,15 @@ class _LaunchTimer:
 
 
 class UNet(nn.Module):
-    def __init__(self, in_channels, heads=[1, 21, 5, 1, 4, 2], crop_first=True):
+    def __init__(self, in_channels, heads=[1, 21, 5, 1, 4, 2], crop_first=True, act_dtype="bf16"):
+        """``act_dtype``: storage format of the eval-mode activations and packed weights. "bf16" (default; the format north_star
+        names and the only one the training pass uses) or "fp16": IEEE half, 8 x smaller rounding error per stored value at the
+        same tensor-core rate -- the decision-stable inference mode (fewer threshold / NMS / omega ties flip against the fp32
+        reference); values saturate at +-65504."""
         super().__init__()
+        if act_dtype not in ("bf16", "fp16"):
+            raise ValueError("act_dtype must be 'bf16' or 'fp16'")
+        self.act_dtype = act_dtype
         # in_channels = 1: the binarised drawings of the reference's datasets (utils.py:80-81), table-driven stem kernel;
         # 2..8 real-valued channels (unet.py:127 self-checks in_channels=3): general fp32 stem kernel (abc_conv3x3_cn)
         if not (1 <= int(in_channels) <= 8):
@@ -315,10 +323,15 @@ class UNet(nn.Module):
         seq = holder.double_conv
         return [(seq[0], seq[1]), (seq[3], seq[4])]
 
+    @property
+    def _act_torch_dtype(self):
+        return torch.float16 if self.act_dtype == "fp16" else torch.bfloat16
+
     @torch.no_grad()
     def prepare(self):
         """Fold BatchNorm (running statistics) and pack every convolution for the kernels. Called lazily by forward."""
         dev = self.s.device
+        adt = self._act_torch_dtype
         if dev.type != "cuda":
             raise RuntimeError("abcnet_b200.UNet runs on a CUDA (sm_100) device only; call .cuda() first -- there is no CPU path")
         P = {}
@@ -331,7 +344,7 @@ class UNet(nn.Module):
             wt = torch.stack([w[:, :, ky, kx] for (_, _, ky, kx) in _TAPS3])
             js = swap_fold_for(cin, cout, name not in pooled)
             P[name] = _Packed(wt, b, [(dy, dx) for (dy, dx, _, _) in _TAPS3], _default_n_tile(cin, cout), cout,
-                              fold=js or row_fold_for(cin, cout), fold_swap=bool(js))
+                              fold=js or row_fold_for(cin, cout), fold_swap=bool(js), dtype=adt)
 
         # first conv (1 -> 16): direct kernel, fp32 folded weights [16][9]
         c0, b0 = self.inc1.double_conv[0], self.inc1.double_conv[1]
@@ -358,7 +371,7 @@ class UNet(nn.Module):
                     xs = self._phase_taps(px)
                     taps = [(dy, dx) for (ky, dy) in ys for (kx, dx) in xs]
                     wt = torch.stack([w[:, :, ky, kx].t() for (ky, dy) in ys for (kx, dx) in xs])
-                    P[f"{name}.up.{py}{px}"] = _Packed(wt.contiguous(), b, taps, _default_n_tile(cin, cout), cout)
+                    P[f"{name}.up.{py}{px}"] = _Packed(wt.contiguous(), b, taps, _default_n_tile(cin, cout), cout, dtype=adt)
         # heads: the eight conv1 share their input -> one GEMM with N = 128 * len(heads); conv2 is a per-head 1x1
         ws, bs = [], []
         for om in self.out_modules:
@@ -368,7 +381,7 @@ class UNet(nn.Module):
         w = torch.cat(ws, 0)
         wt = torch.stack([w[:, :, ky, kx] for (_, _, ky, kx) in _TAPS3])
         nt = int(os.environ.get("ABCNET_NTILE_HEADS", "256"))       # N = 256 tiles: measured 1.4x faster than N = 128
-        P["heads.conv1"] = _Packed(wt, torch.cat(bs), [(dy, dx) for (dy, dx, _, _) in _TAPS3], nt, w.shape[0])
+        P["heads.conv1"] = _Packed(wt, torch.cat(bs), [(dy, dx) for (dy, dx, _, _) in _TAPS3], nt, w.shape[0], dtype=adt)
         P["heads.conv1.plain"] = P["heads.conv1"] if not P["heads.conv1"].pair else None   # abc_heads_fused reads the unpaired pack
         self._heads_w1 = (wt, torch.cat(bs), w.shape[0])
         self._packed_heads_ntile = nt
@@ -379,8 +392,8 @@ class UNet(nn.Module):
             # small heads run at 6.5 - 6.7 TB/s, 60 channels at 5.4; for 360 channels two tiles of 192 (4.63 TB/s) beat three of
             # 128 (4.36) and two of 256 (3.9): fewer re-reads of the hidden tile at the same padding.
             n_tile = 16 if h <= 16 else (64 if h <= 64 else (128 if h <= 128 else (192 if (h + 191) // 192 * 192 <= (h + 127) // 128 * 128 else 128)))
-            P[f"heads.{i}.conv2"] = _Packed(w2.unsqueeze(0).contiguous(), om.conv2.bias.detach().float(), [(0, 0)], n_tile, h)
-        P["heads.fused"] = self._pack_fused_heads(dev)
+            P[f"heads.{i}.conv2"] = _Packed(w2.unsqueeze(0).contiguous(), om.conv2.bias.detach().float(), [(0, 0)], n_tile, h, dtype=adt)
+        P["heads.fused"] = self._pack_fused_heads(dev) if self.act_dtype == "bf16" else None      # abc_heads_fused is a bf16 kernel
         self._packed = P
         self._packed_key = self._param_key()
         self._pack_gen += 1                  # consumers that derive their own packs (SparseHeadsPipeline) key on this
@@ -430,7 +443,7 @@ class UNet(nn.Module):
                 for (ky, dy) in self._phase_taps(py):
                     for (kx, dx) in self._phase_taps(px):
                         wt[offs.index((dy, dx)), ph * cout:(ph + 1) * cout] = w[:, :, ky, kx].t()
-        pk = _Packed(wt, b.repeat(4), offs, 256 if cout % 64 == 0 else 128, 4 * cout, pair=False)
+        pk = _Packed(wt, b.repeat(4), offs, 256 if cout % 64 == 0 else 128, 4 * cout, pair=False, dtype=self._act_torch_dtype)
         pk.subpixel = cout
         return pk
 
@@ -443,8 +456,9 @@ class UNet(nn.Module):
     # ------------------------------------------------------------------ launch helpers
     def _buf(self, key, shape):
         t = self._bufs.get(key)
-        if t is None or tuple(t.shape) != tuple(shape) or t.device != self.s.device:
-            t = torch.empty(shape, dtype=torch.bfloat16, device=self.s.device)
+        dt = self._act_torch_dtype
+        if t is None or tuple(t.shape) != tuple(shape) or t.device != self.s.device or t.dtype != dt:
+            t = torch.empty(shape, dtype=dt, device=self.s.device)
             self._bufs[key] = t
         return t
 
@@ -461,6 +475,7 @@ class UNet(nn.Module):
             d.tap_dy[i], d.tap_dx[i] = dy, dx
         d.row_fold, d.cta_pair = pk.fold, int(pk.pair)
         d.k_chunk = getattr(pk, "kc", 0) if getattr(pk, "kc", 0) != min(pk.cin, 64) else 0
+        d.act_fp16 = int(getattr(pk, "fp16", False))
         d.subpixel = getattr(pk, "subpixel", 0)
         d.swap_mn = int(use_swap(pk, out_mode, dst, pool)) if not d.subpixel else 0
         d.act, d.out_mode = act, out_mode
@@ -517,17 +532,12 @@ class UNet(nn.Module):
             self.prepare()
         P = self._packed
         # fp32 {0,1} images as the reference's DataLoader delivers them, or the same bits as uint8 / bool
-        if self.n_channels != 1:
-            x = x.contiguous().float()
+        u8 = self.n_channels == 1 and x.dtype in (torch.uint8, torch.bool)
+        x = x.contiguous().view(torch.uint8) if u8 else x.contiguous().float()
+        stem_flags = 1 | (2 if self.act_dtype == "fp16" else 0)           # ReLU | fp16 output
 
-            def first(xp, wp, bp, op, B_, H_, W_, planes, off, st_):
-                return lib.abc_conv3x3_cn(xp, self.n_channels, wp, bp, op, B_, H_, W_, planes, off, 1, st_)
-        elif x.dtype in (torch.uint8, torch.bool):
-            x = x.contiguous().view(torch.uint8)
-            first = lib.abc_conv3x3_c1_u8
-        else:
-            x = x.contiguous().float()
-            first = lib.abc_conv3x3_c1
+        def first(xp, wp, bp, op, B_, H_, W_, planes, off, st_):
+            return lib.abc_conv3x3_stem(xp, int(u8), self.n_channels, wp, bp, op, B_, H_, W_, planes, off, stem_flags, st_)
         B, _, H, W = x.shape
         st = _lib.current_stream_ptr()
 
@@ -539,7 +549,7 @@ class UNet(nn.Module):
         b = self._buf("b", (B, 2, H, W, 8))
         w0, b0 = P["inc1.0"]
         with self._timed("inc1.0"):
-            check(first(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), a.data_ptr(), B, H, W, 2, 0, st), "abc_conv3x3_c1")
+            check(first(x.data_ptr(), w0.data_ptr(), b0.data_ptr(), a.data_ptr(), B, H, W, 2, 0, st), "abc_conv3x3_stem")
         cv("inc1.3", a, 0, b)
         cv("inc2.0", b, 0, a)
         p1 = self._buf("p1", (B, 2, H // 2, W // 2, 8))
@@ -630,12 +640,12 @@ class UNet(nn.Module):
             fused = fpack is not None and os.environ.get("ABCNET_FUSED_HEADS", "0") == "1"
         if fused:
             if fpack is None:
-                raise ValueError("this head list does not fit abc_heads_fused (see include/abcnet_b200.h); use fused=False")
+                raise ValueError("abc_heads_fused is not available for this head list / act_dtype (see include/abcnet_b200.h); use fused=False")
             w2pack, bias2 = fpack
             pk1 = self._packed["heads.conv1.plain"]
             if pk1 is None:
                 wt1, b1, c1 = self._heads_w1
-                pk1 = self._packed["heads.conv1.plain"] = _Packed(wt1, b1, [(dy, dx) for (dy, dx, _, _) in _TAPS3], 256, c1, pair=False)
+                pk1 = self._packed["heads.conv1.plain"] = _Packed(wt1, b1, [(dy, dx) for (dy, dx, _, _) in _TAPS3], 256, c1, pair=False)      # bf16 only
             d = AbcHeadsFusedDesc()
             d.in_, d.N, d.H, d.W, d.in_planes, d.in_plane_off = k2.data_ptr(), B, H4, W4, k2.shape[1], 0
             d.w1pack, d.bias1, d.n_heads = pk1.w.data_ptr(), pk1.bias.data_ptr(), len(self.heads)

@@ -58,6 +58,10 @@ ABC_API int abc_conv3x3_c1(const float* img, const float* w, const float* b, voi
  * 4x fewer bytes over PCIe and HBM. */
 ABC_API int abc_conv3x3_c1_u8(const uint8_t* img, const float* w, const float* b, void* out, int N, int H, int W,
                               int out_planes, int out_plane_off, void* stream);
+/* The stem with every option: img fp32 [N][cin][H][W] (img_is_u8 = 0) or uint8 {0,1} [N][1][H][W] (img_is_u8 = 1, cin = 1);
+ * flags bit 0: ReLU (eval) / raw conv + bias (train), bit 1: fp16 output instead of bf16 (AbcConvDesc.act_fp16). */
+ABC_API int abc_conv3x3_stem(const void* img, int img_is_u8, int cin, const float* w, const float* b, void* out, int N, int H, int W,
+                             int out_planes, int out_plane_off, int flags, void* stream);
 /* General stem for in_channels = cin in 1..8 real-valued fp32 channels (src/unet.py:77,83 with in_channels != 1; the reference's
  * self-check builds UNet(in_channels=3), unet.py:127): img fp32 NCHW [N][cin][H][W], w fp32 [16][cin][9], b fp32 [16];
  * relu = 1: (BatchNorm-folded) conv + ReLU for eval, relu = 0: raw conv + bias for the training pass. Output as above. */
@@ -153,6 +157,12 @@ typedef struct AbcConvDesc {
    * so deepens both shared-memory rings: for the 64-channel layers at 128 x 128, which are bound by pipeline depth rather than
    * by the tensor pipe or HBM (profiles/r01_down2_3_swapfold_v33.summary.txt). The K order of the accumulation changes with it. */
   int k_chunk;
+  /* Optional IEEE fp16 activations and weights (0 = bf16, the default and the only training format): input, packed weights and
+   * P8 outputs of this launch are fp16 (same 16-bit P8 layout, same tcgen05 rate; fp32 accumulation and fp32 logits as before).
+   * fp16 carries 11 significand bits against bf16's 8, so the rounding error of every stored activation is 8 x smaller -- the
+   * "decision-stable" inference mode (UNet(..., act_dtype="fp16")): fewer threshold / NMS / omega ties flip against the fp32
+   * reference. Outputs saturate at +-65504. Inference only (no fused statistics, no cta_pair). */
+  int act_fp16;
 } AbcConvDesc;
 
 ABC_API int abc_conv_igemm(const AbcConvDesc* desc, void* stream);
@@ -435,6 +445,7 @@ typedef struct AbcUNetConfig {
   int n_heads;         /* 1..16 */
   int heads[16];       /* output channels per head (v2: 1, 14, 3, 2, 1, 360, 60, 60) */
   int crop_first;      /* 1: torch >= 1.13 semantics of unet.py:54-55 (drop the FIRST row / column of the up-sampled map) */
+  int act_fp16;        /* 0: bf16 activations / weights (default); 1: IEEE fp16 (AbcConvDesc.act_fp16) */
 } AbcUNetConfig;
 typedef struct AbcNamedTensor {
   const char* name;

@@ -181,6 +181,12 @@ def test_trained_network_end_to_end_identity():
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False       # fp32 hybrid heads below: true fp32
     dec = abcnet_b200.PeakDecoder(CHUNK, atom_cap=2048, bond_cap=8192)
     pipe = abcnet_b200.SparseHeadsPipeline(model, CHUNK, peak_cap=256, bond_cap=8192)
+    # the same trained weights in the decision-stable inference mode (fp16 activations / weights: 8 x smaller rounding error)
+    model16 = abcnet_b200.UNet(1, HEADS, act_dtype="fp16").cuda().eval()
+    model16.load_state_dict(model.state_dict())
+    dec16 = abcnet_b200.PeakDecoder(CHUNK, atom_cap=2048, bond_cap=8192)
+    f16 = dict(identical_record_images=0, identical_molblock_images=0, identical_topology_images=0, differing_decisions=0,
+               logit_max_abs_err=[0.0] * 8)
     report = dict(images=N_IMG, train_steps=STEPS, loss_curve=curve, differences=[], identical_record_images=0,
                   identical_molblock_images=0, identical_graph_images=0, identical_topology_images=0, molecules_compared=0, labelled_atoms=0, found_atoms=0,
                   ref_atom_peaks=0, ref_bond_records=0, images_with_differences=[], graph_changes=[])
@@ -220,6 +226,10 @@ def test_trained_network_end_to_end_identity():
             budget[k]["trunk"] = max(budget[k]["trunk"], float(np.abs(h - ref[k]).max()))
             budget[k]["heads"] = max(budget[k]["heads"], float(np.abs(ours[k] - h).max()))
             budget[k]["total"] = max(budget[k]["total"], float(np.abs(ours[k] - ref[k]).max()))
+        recs16 = dec16(model16.infer(xs, layout="p8f"), thr=THR)
+        ours16 = [o.float().cpu().numpy() for o in model16(xs)]
+        for i in range(8):
+            f16["logit_max_abs_err"][i] = max(f16["logit_max_abs_err"][i], float(np.abs(ours16[i] - ref[i]).max()))
         for jj in range(n):
             j = c0 + jj
             R = [r[jj] for r in ref]
@@ -249,6 +259,25 @@ def test_trained_network_end_to_end_identity():
             report["identical_topology_images"] += int(t_r == t_o)
             assert mol_o == blocks[jj], f"image {j}: native assembler text != reference assembly of the same records"
             report["molecules_compared"] += int(mol_r is not None)
+            # fp16 mode on the same image: records / MOL text / topology against the same reference
+            a16, b16, n16 = recs16[jj]
+            ga16 = np.stack([a16["x"], a16["y"], a16["type"], a16["charge"], a16["hs"]], -1).astype(np.int32).reshape(-1, 5)
+            gb16 = np.stack([b16["x"], b16["y"], b16["omega"], b16["type"]], -1).astype(np.int32).reshape(-1, 4)
+            same16 = np.array_equal(ga16, ra) and np.array_equal(gb16, rb)
+            f16["identical_record_images"] += int(same16)
+            L16 = abcnet_b200.records_to_lists(a16, b16, n16)
+            f16["identical_molblock_images"] += int((assemble_ref.records_to_molblock(L16) if L16 is not None else None) == mol_r)
+            f16["identical_topology_images"] += int((assemble_ref.molecule_graph(L16, with_positions=False) if L16 is not None else None) ==
+                                                    (assemble_ref.molecule_graph(L_ref, with_positions=False) if L_ref is not None else None))
+            if not same16:
+                O16 = [o[jj] for o in ours16]
+                oa16, (ob16, _) = decode_ref.decode_records(O16, THR, "nms")
+                assert np.array_equal(ga16, oa16) and np.array_equal(gb16, ob16), f"image {j}: fp16 mode: CUDA decode != oracle decode on the same logits"
+                d16 = _explain(j, R, O16, ra, rb, oa16, ob16)
+                f16["differing_decisions"] += len(d16)
+                for item in d16:
+                    if not (item["flips"] and all(f["margin"] <= f["local_err"] for f in item["flips"])):
+                        unexplained.append(dict(item, mode="fp16"))
             same_rec = np.array_equal(ga, ra) and np.array_equal(gb, rb)
             report["identical_record_images"] += int(same_rec)
             report["identical_molblock_images"] += int(mol_r == mol_o)
@@ -274,7 +303,7 @@ def test_trained_network_end_to_end_identity():
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
     rel = np.sqrt(num / np.maximum(den, 1e-30))
     report.update(logit_max_abs_err=err.tolist(), logit_scale=scale.tolist(), logit_rel_l2=rel.tolist(),
-                  error_budget_max_abs={str(k): v for k, v in budget.items()})
+                  error_budget_max_abs={str(k): v for k, v in budget.items()}, fp16_mode=f16)
     margins = [f["margin"] for it in report["differences"] for f in it["flips"]]
     report["flip_margin_max"] = max(margins) if margins else 0.0
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -288,6 +317,10 @@ def test_trained_network_end_to_end_identity():
           f"{report['identical_topology_images']}); molecules {report['molecules_compared']}; reference atom peaks "
           f"{report['ref_atom_peaks']} (labelled {report['labelled_atoms']}, found {report['found_atoms']}), bond records "
           f"{report['ref_bond_records']}; listed boundary cases: {len(report['differences'])}, largest flipped margin {report['flip_margin_max']:.4f}")
+    print(f"fp16 activation mode on the same weights: identical records {f16['identical_record_images']}, identical MOL text "
+          f"{f16['identical_molblock_images']}, identical topology {f16['identical_topology_images']}, differing decisions "
+          f"{f16['differing_decisions']} (bf16: {len(report['differences'])}); logit max-abs error "
+          f"{[round(e, 4) for e in f16['logit_max_abs_err']]}")
     for item in report["differences"][:40]:
         print("  boundary case:", item)
     for i in range(8):
@@ -297,6 +330,10 @@ def test_trained_network_end_to_end_identity():
     assert report["ref_atom_peaks"] >= 4 * N_IMG and report["found_atoms"] >= 0.7 * report["labelled_atoms"], "degenerate network"
     assert report["identical_record_images"] >= (2 * N_IMG) // 3
     assert report["identical_graph_images"] >= (9 * N_IMG) // 10
+    # the decision-stable mode must be at least as close to the reference as bf16, in logits and in decisions
+    assert all(a <= b + 1e-6 for a, b in zip(f16["logit_max_abs_err"], err.tolist())), (f16["logit_max_abs_err"], err.tolist())
+    assert f16["identical_record_images"] >= report["identical_record_images"]
+    assert f16["differing_decisions"] <= len(report["differences"])
 
 
 def test_eval_cache_follows_graph_training():

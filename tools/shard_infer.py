@@ -107,6 +107,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=0, help="train on pseudo-molecules first (rank 0) and broadcast the weights")
     ap.add_argument("--dump-subset", type=int, default=0, help="write weights + MOL blocks of the first M images to gpurun_out/")
     ap.add_argument("--weights", default="", help="load this state_dict (.pt) instead of training / random init")
+    ap.add_argument("--act-dtype", default="bf16", choices=["bf16", "fp16"], help="UNet(act_dtype=...): storage format of the eval activations")
     ap.add_argument("--ref-check", action="store_true",
                     help="second pass: compare every image with the fp32 torch / cuDNN forward (TF32 off) of the same weights at record level")
     args = ap.parse_args()
@@ -120,7 +121,7 @@ def main():
     B = args.batch
     total = args.images // (B * world) * (B * world)   # whole batches per rank: the batch ranges (hence the digest) do not depend on N
     heads = list(synthdata.V2_HEADS)
-    model = abcnet_b200.UNet(1, heads).to(dev)
+    model = abcnet_b200.UNet(1, heads, act_dtype=args.act_dtype).to(dev)
     trained = args.train_steps > 0 or bool(args.weights)
     if trained:
         from synthdata import molecules
@@ -243,7 +244,7 @@ def main():
             h.update(f"{a}:{d};".encode())
         print(json.dumps({"tool": "shard_infer", "images": total, "n_gpus": world, "batch": B, "sparse_heads": bool(args.sparse),
                           "seconds": dt, "images_per_s": total / dt, "molecules": int(sum(n for _, n in parts)),
-                          "batches": len(allb), "digest": h.hexdigest(), "weights": "trained on pseudo-molecules" if trained else "random init, calibrated",
+                          "batches": len(allb), "digest": h.hexdigest(), "weights": "trained on pseudo-molecules" if trained else "random init, calibrated", "act_dtype": args.act_dtype,
                           "subset_dumped": int(args.dump_subset), "ref_check_fp32_torch": ref,
                           "what": "forward + decode + native MOL-block assembly per image, sharded by contiguous image ranges, "
                                   "no data-path collective; digest over all MOL-block texts in global image order"}))
