@@ -35,9 +35,10 @@ __device__ __forceinline__ uint4 pack8_act16(const float* v, bool fp16) {
   uint4 r;
   if (fp16) {                                   // one (warp-uniform) branch per vector, two straight-line conversion sequences
     __half2 h[4];
+    const __half2 hi = __floats2half2_rn(65504.f, 65504.f), lo = __floats2half2_rn(-65504.f, -65504.f);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      h[i] = __floats2half2_rn(fminf(fmaxf(v[2 * i], -65504.f), 65504.f), fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f));
+    for (int i = 0; i < 4; ++i)                 // saturate on the packed pair: +-inf -> +-65504 (two instructions per pair)
+      h[i] = __hmax2(__hmin2(__floats2half2_rn(v[2 * i], v[2 * i + 1]), hi), lo);
     r.x = *reinterpret_cast<uint32_t*>(&h[0]); r.y = *reinterpret_cast<uint32_t*>(&h[1]);
     r.z = *reinterpret_cast<uint32_t*>(&h[2]); r.w = *reinterpret_cast<uint32_t*>(&h[3]);
   } else {
