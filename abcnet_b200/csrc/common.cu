@@ -42,6 +42,19 @@ int device_check() {
   return ABC_OK;
 }
 
+void* tensor_map_encode_fn() {
+  static void* const fn = [] {                       // C++11 magic static: initialised exactly once, thread-safe
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      return ptr;
+    cudaGetLastError();
+    return static_cast<void*>(nullptr);
+  }();
+  return fn;
+}
+
 int sm_count() {
   const int dev = current_device();
   if (dev < 0) return 0;

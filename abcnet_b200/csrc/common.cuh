@@ -15,6 +15,7 @@ extern std::atomic<int64_t> g_launches;
 int device_check();   // ABC_OK or ABC_ERR_NO_DEVICE (message set); the positive answer is cached per device
 int sm_count();
 int current_device();  // cudaGetDevice, -1 on failure
+void* tensor_map_encode_fn();   // cuTensorMapEncodeTiled through the runtime's driver entry point (resolved once, thread-safe); nullptr if unavailable
 
 constexpr int kMaxDevices = 64;
 

@@ -421,21 +421,7 @@ typedef CUresult (*HfEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static HfEncodeTiledFn hf_encode_fn() {
-  static HfEncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<HfEncodeTiledFn>(ptr);
-    else
-      cudaGetLastError();
-  }
-  return fn;
-}
+static HfEncodeTiledFn hf_encode_fn() { return reinterpret_cast<HfEncodeTiledFn>(tensor_map_encode_fn()); }
 
 }  // namespace abc
 

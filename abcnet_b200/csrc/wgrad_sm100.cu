@@ -186,21 +186,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant_
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn2 wg_encode_fn() {
-  static EncodeTiledFn2 fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn2>(ptr);
-    else
-      cudaGetLastError();
-  }
-  return fn;
-}
+static EncodeTiledFn2 wg_encode_fn() { return reinterpret_cast<EncodeTiledFn2>(tensor_map_encode_fn()); }
 
 static int make_map(CUtensorMap* m, const void* base, int W, int H, int planes, int N, int box_cols, int box_rows, int box_planes) {
   EncodeTiledFn2 enc = wg_encode_fn();
