@@ -181,7 +181,8 @@ def conv(pk, src, in_plane_off, dst, out_plane_off=0, act=0, out_mode=0, out_sca
         for i, (t0, nt) in enumerate(pk.segments):
             d.seg_tap0[i], d.seg_ntaps[i] = t0, nt
     d.row_fold, d.cta_pair = pk.fold, int(pk.pair)
-    d.swap_mn = int(use_swap(pk, out_mode, dst, pool))
+    d.subpixel = getattr(pk, "subpixel", 0)
+    d.swap_mn = int(use_swap(pk, out_mode, dst, pool)) if not d.subpixel else 0
     d.act, d.out_mode = act, out_mode
     d.out_sy, d.out_oy, d.out_sx, d.out_ox = out_scale
     if dst is not None:
@@ -450,16 +451,24 @@ class TrainEngine:
             if "up" in u:                                            # up-sampling conv: 4 sub-pixel phases, bias, no BN
                 src = self._tensor(u["src"], B, H, W, (B, u["cin"] // 8, h, w, 8))
                 cat = self._tensor(u["dst"], B, H, W)
-                for py in (0, 1):
-                    for px in (0, 1):
-                        ys, xs = phase_taps(py, m.crop_first), phase_taps(px, m.crop_first)
-                        taps = [(dy, dx) for (ky, dy) in ys for (kx, dx) in xs]
 
-                        def make(up=u["up"], ys=ys, xs=xs, taps=taps):
-                            wt = self._w(up.weight)
-                            mats = torch.stack([wt[:, :, ky, kx].t() for (ky, dy) in ys for (kx, dx) in xs]).contiguous()
-                            return Packed(mats, self._w(up.bias), taps)
-                        conv(self._pk(f"{u['name']}.{py}{px}", make), src, 0, cat, out_plane_off=u["dst_off"], out_scale=(2, py, 2, px))
+                def make(up=u["up"], cout=u["cout"]):
+                    # the four sub-pixel phases as blocks of the GEMM N axis (AbcConvDesc.subpixel): one launch, zero blocks where
+                    # a phase does not use an input offset (same layout as UNet._pack_subpixel)
+                    wt = self._w(up.weight)
+                    offs = sorted({(dy, dx) for py in (0, 1) for px in (0, 1) for (_, dy) in phase_taps(py, m.crop_first)
+                                   for (_, dx) in phase_taps(px, m.crop_first)})
+                    mats = wt.new_zeros(len(offs), 4 * cout, wt.shape[0])
+                    for py in (0, 1):
+                        for px in (0, 1):
+                            ph = 2 * py + px
+                            for (ky, dy) in phase_taps(py, m.crop_first):
+                                for (kx, dx) in phase_taps(px, m.crop_first):
+                                    mats[offs.index((dy, dx)), ph * cout:(ph + 1) * cout] = wt[:, :, ky, kx].t()
+                    pk = Packed(mats, self._w(up.bias).repeat(4), offs, n_tile=256 if cout % 64 == 0 else 128)
+                    pk.subpixel = cout
+                    return pk
+                conv(self._pk(u["name"] + ".sub", make), src, 0, cat, out_plane_off=u["dst_off"], out_scale=(2, 0, 2, 0))
                 continue
             cout = u["cout"]
             z = self.buf("z:" + u["name"], (B, cout // 8, h, w, 8))
