@@ -1,6 +1,10 @@
 #!/usr/bin/env python
 """Stand-alone timing of single conv_igemm launches (CUDA events, device-resident synthetic data).
-Usage: python tools/layer_bench.py  -> prints one line per (layer, variant): ms, TFLOP/s, GB/s (algorithmic bytes)."""
+Usage: python tools/layer_bench.py  -> prints one line per (layer, variant): ms, TFLOP/s, GB/s (algorithmic bytes).
+
+Note (round 2): the library reads its experiment knobs (ABCNET_MT, ABCNET_NACC, ABCNET_MT256, ABCNET_PAIR_DBG) ONCE per process --
+the launch path no longer calls getenv. The mt / nacc / MT256 sweeps below therefore need one process per setting: run e.g.
+`ABCNET_MT=1 python tools/layer_bench.py shallow`; values set through os.environ after the first launch are ignored."""
 import ctypes as C
 import os
 import sys
