@@ -233,19 +233,34 @@ static int check_cfg(const AbcUNetConfig* c) {
   return ABC_OK;
 }
 
-// bytes of caller-owned DEVICE memory for the packed weights (an upper bound that abc_unet_create fills from the start)
+// bytes of caller-owned DEVICE memory for the packed weights: the exact size abc_unet_create fills (same layer rules)
+static int64_t pack_bytes(int rows, int cin, int ntaps, int n_tile) {
+  const int64_t n_tiles = (rows + n_tile - 1) / n_tile;
+  return align256(n_tiles * n_tile * cin * ntaps * 2) + align256(n_tiles * n_tile * 4);
+}
+
 extern "C" int64_t abc_unet_wpack_bytes(const AbcUNetConfig* cfg) {
   if (check_cfg(cfg)) return -1;
-  int64_t el = 0;
+  int64_t b = 0;
   for (int i = 0; i < 13; ++i) {
-    const int cin = kDcIn[i] ? kDcIn[i] : 16, cout = kDcOut[i];
-    el += 2ll * 6 * 3 * 512 * 64;          // generous per-DoubleConv slack for the folded (Toeplitz) layouts of the small layers
-    el += 9ll * cout * (cin + cout) * 2;
+    const int cin0 = kDcIn[i] ? kDcIn[i] : cfg->in_channels, cout = kDcOut[i];
+    for (int half = 0; half < 2; ++half) {
+      const int cin = half ? cout : cin0;
+      if (i == 0 && half == 0) {                                   // stem: fp32 [16][cin * 9] + bias
+        b += align256(static_cast<int64_t>(16) * cin * 9 * 4) + align256(64);
+        continue;
+      }
+      const std::string name = std::string(kShort[i]) + (half ? ".3" : ".0");
+      const int js = swap_fold_for(cin, cout, !is_pooled(name));
+      const int J = js ? js : row_fold_for(cin, cout);
+      b += J == 1 ? pack_bytes(cout, cin, 9, default_n_tile(cin, cout)) : pack_bytes(J * cout, cin, 3 * (J + 2), J * cout);
+    }
   }
-  el += 4ll * 4 * (512 * 256 + 256 * 128 + 128 * 64);                 // sub-pixel packs of the three up-sampling convolutions
-  el += 9ll * 128 * 128 * cfg->n_heads;
-  for (int i = 0; i < cfg->n_heads; ++i) el += 128ll * ((cfg->heads[i] + 255) / 16 * 16 + 256);
-  return el * 2 + (1 << 20);
+  const int up_cin[] = {512, 256, 128};
+  for (int u = 0; u < 3; ++u) b += pack_bytes(4 * (up_cin[u] / 2), up_cin[u], 4, (up_cin[u] / 2) % 64 == 0 ? 256 : 128);
+  b += pack_bytes(128 * cfg->n_heads, 128, 9, 256);
+  for (int i = 0; i < cfg->n_heads; ++i) b += pack_bytes(cfg->heads[i], 128, 1, head_conv2_n_tile(cfg->heads[i]));
+  return b + 256;
 }
 
 extern "C" int64_t abc_unet_workspace_bytes(const AbcUNetConfig* cfg, int N, int H, int W) {

@@ -55,7 +55,10 @@ class NativeUNet:
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
-            lib.abc_unet_destroy(h)
+            try:
+                lib.abc_unet_destroy(h)
+            except Exception:                                # interpreter shutdown: the library may already be gone
+                pass
             self._h = None
 
     @torch.no_grad()
