@@ -277,11 +277,9 @@ extern "C" int64_t abc_unet_workspace_bytes(const AbcUNetConfig* cfg, int N, int
   return b + 4096;
 }
 
-extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* tensors, int n_tensors, void* wpack_dev, int64_t wpack_bytes,
-                               void* stream, AbcUNet** out) {
-  if (int rc = check_cfg(cfg)) return rc;
-  if (int rc = device_check()) return rc;
-  ABC_REQUIRE(tensors && n_tensors > 0 && wpack_dev && out, "abc_unet_create: null argument");
+// Host-only part of abc_unet_create: fold + pack every convolution of the network into `arena` (the bytes that are uploaded) and
+// record the per-layer offsets in `h`. No CUDA call.
+static int pack_all(const AbcUNetConfig* cfg, const AbcNamedTensor* tensors, int n_tensors, UNetHandle* h, std::vector<uint8_t>& arena) {
   Tensors T;
   for (int i = 0; i < n_tensors; ++i) {
     ABC_REQUIRE(tensors[i].name != nullptr, "abc_unet_create: tensor %d has no name", i);
@@ -289,13 +287,11 @@ extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* t
     if (nm.rfind("module.", 0) == 0) nm = nm.substr(7);          // DataParallel / DDP checkpoints (train.py:435)
     T.by_name[nm] = &tensors[i];
   }
-  auto* h = new UNetHandle();
   h->cfg = *cfg;
   const bool fp16 = cfg->act_fp16 != 0;
-  std::vector<uint8_t> arena;
   arena.reserve(64 << 20);
   std::vector<float> w, b;
-  auto fail = [&]() { delete h; return ABC_ERR_INVALID; };
+  auto fail = [&]() { return ABC_ERR_INVALID; };
   // ---- DoubleConvs
   for (int i = 0; i < 13; ++i) {
     const int cin0 = kDcIn[i] ? kDcIn[i] : cfg->in_channels, cout = kDcOut[i];
@@ -413,6 +409,20 @@ extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* t
       append_pack(arena, p2, L2, head_conv2_n_tile(hc), fp16);
     }
   }
+  return ABC_OK;
+}
+
+extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* tensors, int n_tensors, void* wpack_dev, int64_t wpack_bytes,
+                               void* stream, AbcUNet** out) {
+  if (int rc = check_cfg(cfg)) return rc;
+  if (int rc = device_check()) return rc;
+  ABC_REQUIRE(tensors && n_tensors > 0 && wpack_dev && out, "abc_unet_create: null argument");
+  auto* h = new UNetHandle();
+  std::vector<uint8_t> arena;
+  if (int rc = pack_all(cfg, tensors, n_tensors, h, arena)) {
+    delete h;
+    return rc;
+  }
   if (static_cast<int64_t>(arena.size()) > wpack_bytes) {
     set_error("abc_unet_create: packed weights need %lld bytes, wpack_bytes = %lld", static_cast<long long>(arena.size()),
               static_cast<long long>(wpack_bytes));
@@ -430,6 +440,22 @@ extern "C" int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* t
   h->arena = static_cast<const uint8_t*>(wpack_dev);
   h->arena_bytes = static_cast<int64_t>(arena.size());
   *out = reinterpret_cast<AbcUNet*>(h);
+  return ABC_OK;
+}
+
+// The packed weight arena in HOST memory (what abc_unet_create uploads): lets a host inspect / cache the pack, and lets the CPU
+// test suite compare the C++ packing with the Python packing byte for byte. No CUDA call; `used` receives the byte count.
+extern "C" int abc_unet_pack_host(const AbcUNetConfig* cfg, const AbcNamedTensor* tensors, int n_tensors, void* out, int64_t out_bytes,
+                                  int64_t* used) {
+  if (int rc = check_cfg(cfg)) return rc;
+  ABC_REQUIRE(tensors && n_tensors > 0 && out && used, "abc_unet_pack_host: null argument");
+  UNetHandle h;
+  std::vector<uint8_t> arena;
+  if (int rc = pack_all(cfg, tensors, n_tensors, &h, arena)) return rc;
+  *used = static_cast<int64_t>(arena.size());
+  ABC_REQUIRE(*used <= out_bytes, "abc_unet_pack_host: %lld bytes needed, %lld given", static_cast<long long>(*used),
+              static_cast<long long>(out_bytes));
+  memcpy(out, arena.data(), arena.size());
   return ABC_OK;
 }
 

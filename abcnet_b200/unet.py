@@ -201,7 +201,9 @@ class _Packed:
 
 def _fold(conv_w, conv_b, bn):
     """Inference BatchNorm fold: W' = W * g / sqrt(var + eps), b' = (b - mean) * g / sqrt(var + eps) + beta."""
-    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    # sqrt through fp64 and back = the correctly rounded fp32 sqrt on every backend (CUDA's sqrtf already is; torch's vectorised CPU
+    # sqrt is not always), so the packs are the same bytes wherever they are built -- and the same as csrc/unet_plan.cu's sqrtf
+    scale = bn.weight.detach().float() / torch.sqrt((bn.running_var.detach().float() + bn.eps).double()).float()
     w = conv_w.detach().float() * scale.view(-1, 1, 1, 1)
     b = (conv_b.detach().float() - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
     return w, b
@@ -328,11 +330,13 @@ class UNet(nn.Module):
         return torch.float16 if self.act_dtype == "fp16" else torch.bfloat16
 
     @torch.no_grad()
-    def prepare(self):
-        """Fold BatchNorm (running statistics) and pack every convolution for the kernels. Called lazily by forward."""
+    def prepare(self, _inspect_on_cpu=False):
+        """Fold BatchNorm (running statistics) and pack every convolution for the kernels. Called lazily by forward.
+        ``_inspect_on_cpu``: build the packs from CPU parameters (pure data movement, no kernel) so that tests can compare them
+        with the C++ packing of ``abc_unet_pack_host``; the forward pass itself still refuses to run without a CUDA device."""
         dev = self.s.device
         adt = self._act_torch_dtype
-        if dev.type != "cuda":
+        if dev.type != "cuda" and not _inspect_on_cpu:
             raise RuntimeError("abcnet_b200.UNet runs on a CUDA (sm_100) device only; call .cuda() first -- there is no CPU path")
         P = {}
 

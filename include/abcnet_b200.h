@@ -460,6 +460,10 @@ ABC_API int abc_unet_create(const AbcUNetConfig* cfg, const AbcNamedTensor* tens
 ABC_API int abc_unet_forward_infer(AbcUNet* net, const void* img, int img_is_u8, int N, int H, int W, void* workspace,
                                    int64_t workspace_bytes, void* const* out_ptrs, int logits_layout, void* stream);
 ABC_API int abc_unet_destroy(AbcUNet* net);
+/* The packed weight arena in HOST memory -- exactly the bytes abc_unet_create uploads (out_bytes >= abc_unet_wpack_bytes); no
+ * CUDA call, usable without a GPU (offline packing, caching, and the CPU test that compares it with the Python packing). */
+ABC_API int abc_unet_pack_host(const AbcUNetConfig* cfg, const AbcNamedTensor* tensors, int n_tensors, void* out, int64_t out_bytes,
+                               int64_t* used);
 
 #ifdef __cplusplus
 }
