@@ -58,6 +58,13 @@ print(f"total device time {tot / 1e3:.2f} ms over {sum(v[0] for v in rows.values
 for name, (n, us) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{us / 1e3:9.3f} ms  {n:5d}x  {name[:110]}")
 
+# the BatchNorm / activation passes in launch order (forward: layer order, backward: reversed), one duration per launch
+seq = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "bn_" in e.name and "finalize" not in e.name),
+             key=lambda e: e.time_range.start)
+print("BatchNorm passes in launch order (us):")
+for kind in ("bn_act_kernel", "bn_stats_kernel", "bn_act_bwd_reduce_kernel", "bn_act_bwd_apply_kernel"):
+    print(f"  {kind}: " + " ".join(f"{e.device_time:.0f}{'p' if '<true>' in e.name or '<(bool)1>' in e.name else ''}" for e in seq if kind in e.name))
+
 # per-launch CUDA-event timing of the tensor-core kernels (conv fprop / dgrad, wgrad), grouped by shape
 from abcnet_b200 import train as _tr  # noqa: E402
 _tr.timing = []
