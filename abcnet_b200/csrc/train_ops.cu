@@ -250,8 +250,8 @@ __device__ __forceinline__ void bwd_block4(const BnActBwdParams& p, const float 
 }
 
 // reduce: s1 = sum g, s2 = sum g * xhat (xhat = (z - mean) * invstd, accumulated as sum g*z and combined per block)
-template <bool POOL>
-__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwdParams p) {
+template <bool POOL, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) bn_act_bwd_reduce_kernel(const BnActBwdParams p) {
   const int plane = blockIdx.y, n = blockIdx.z;
   const int HW = p.H * p.W;
   float sc[8], sh[8];
@@ -334,8 +334,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const BnActBwdPa
 }
 
 // apply: dz = scale * (g - s1/M - xhat * s2/M) = scale * g + cb * z + ca  with per-channel constants ca, cb
-template <bool POOL>
-__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const BnActBwdParams p) {
+template <bool POOL, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) bn_act_bwd_apply_kernel(const BnActBwdParams p) {
   const int plane = blockIdx.y, n = blockIdx.z;
   const int HW = p.H * p.W;
   __shared__ float cst[2][8];
@@ -613,7 +613,8 @@ static int p8_check(const void* ptr, int planes, int plane_off, int cplanes, con
 // thread streams several vectors and the per-block atomics stay negligible
 static int plane_grid_x(long long items, int planes, int N, int per_thread = 1) {
   long long need = (items + 256ll * per_thread - 1) / (256ll * per_thread);
-  long long cap = (148ll * 16 + static_cast<long long>(planes) * N - 1) / (static_cast<long long>(planes) * N);
+  static const long long per_sm = [] { const char* e = getenv("ABCNET_BN_BLOCKS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 16; }();
+  long long cap = (148ll * per_sm + static_cast<long long>(planes) * N - 1) / (static_cast<long long>(planes) * N);
   if (cap < 1) cap = 1;
   if (need > cap) need = cap;
   return need < 1 ? 1 : static_cast<int>(need);
@@ -712,9 +713,14 @@ extern "C" int abc_bn_act_backward(const AbcBnActBwdDesc* d, void* stream) {
   } else {
     const long long items = static_cast<long long>(d->H) * d->W;
     const dim3 grid(plane_grid_x(items, cp, d->N, 2), cp, d->N);
-    bn_act_bwd_reduce_kernel<false><<<grid, 256, 0, st>>>(p);
+    // resident blocks per SM (register cap) of the two passes: ABCNET_BN_MINB = <reduce digit><apply digit>, read once
+    static const int minb = [] { const char* e = getenv("ABCNET_BN_MINB"); return e ? atoi(e) : 44; }();
+    if (minb / 10 == 4) bn_act_bwd_reduce_kernel<false, 4><<<grid, 256, 0, st>>>(p);
+    else bn_act_bwd_reduce_kernel<false, 3><<<grid, 256, 0, st>>>(p);
     if (int rc = launch_check("bn_act_bwd_reduce_kernel")) return rc;
-    bn_act_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(p);
+    if (minb % 10 == 4) bn_act_bwd_apply_kernel<false, 4><<<grid, 256, 0, st>>>(p);
+    else if (minb % 10 == 3) bn_act_bwd_apply_kernel<false, 3><<<grid, 256, 0, st>>>(p);
+    else bn_act_bwd_apply_kernel<false, 2><<<grid, 256, 0, st>>>(p);
   }
   return launch_check("bn_act_bwd_apply_kernel");
 }
