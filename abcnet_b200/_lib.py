@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libabcnet_b200.so")
 EXPORTS = (
     "abc_last_error", "abc_version", "abc_device_ok", "abc_sm_count", "abc_launch_count",
     "abc_conv3x3_c1", "abc_conv3x3_c1_u8", "abc_conv3x3_cn", "abc_conv3x3_cn_wgrad", "abc_conv3x3_stem", "abc_conv_igemm", "abc_conv_wpack_bytes", "abc_decode_peaks",
-    "abc_loss_partials", "abc_loss_backward",
+    "abc_loss_partials", "abc_loss_backward", "abc_loss_partials_p8",
     "abc_bn_stats", "abc_bn_finalize", "abc_bn_act", "abc_bn_act_backward", "abc_nchw_to_p8", "abc_channel_sum",
     "abc_nchw_to_p8_ex", "abc_deinterleave2", "abc_conv_wgrad", "abc_conv3x3_c1_wgrad", "abc_conv3x3_c1_raw",
     "abc_heads_fused", "abc_heads_fused_pack_sizes", "abc_gather_pack", "abc_adam_step", "abc_adam_chunk_elems", "abc_assemble_molblocks", "abc_gather_patches", "abc_rasterise_targets",
@@ -111,7 +111,7 @@ class AbcBnActBwdDesc(C.Structure):
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
         ("act", C.c_int), ("drop_p", C.c_float), ("seed", C.c_uint64),
-        ("s1", C.c_void_p), ("s2", C.c_void_p), ("seed_dev", C.c_void_p),
+        ("s1", C.c_void_p), ("s2", C.c_void_p), ("seed_dev", C.c_void_p), ("gscale", C.c_void_p),
     ]
 
 
@@ -133,6 +133,10 @@ class AbcLossDesc(C.Structure):
         ("type_weights", C.c_void_p), ("sums", C.c_void_p), ("scale", C.c_void_p),
         ("dlogits", C.c_void_p * 8),
     ]
+
+
+class AbcLossP8Out(C.Structure):
+    _fields_ = [("dz", C.c_void_p * 8), ("planes", C.c_int * 8), ("dbias", C.c_void_p * 8)]
 
 
 assert C.sizeof(AbcAtomRec) == 8 and C.sizeof(AbcBondRec) == 12
@@ -161,6 +165,7 @@ def _load():
     lib.abc_decode_peaks.argtypes = [C.POINTER(AbcDecodeDesc), C.c_void_p]
     lib.abc_loss_partials.argtypes = [C.POINTER(AbcLossDesc), C.c_void_p]
     lib.abc_loss_backward.argtypes = [C.POINTER(AbcLossDesc), C.c_void_p]
+    lib.abc_loss_partials_p8.argtypes = [C.POINTER(AbcLossDesc), C.POINTER(AbcLossP8Out), C.c_void_p]
     vp, ci = C.c_void_p, C.c_int
     lib.abc_bn_stats.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp, vp]
     lib.abc_channel_sum.argtypes = lib.abc_bn_stats.argtypes

@@ -210,6 +210,7 @@ struct BnActBwdParams {
   uint4* dz;                // apply: output
   int dz_planes, dz_plane_off;
   double count;
+  const float* gscale;      // [C] or null: per-channel factor on dA / dP (everything downstream is linear in g)
 };
 
 // Gradient g wrt the BatchNorm output for one pixel (8 channels): g = dA * act'(pre) * dropout scale.
@@ -327,6 +328,15 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_reduce_kernel(const BnAc
   float mean[8], istd[8], s2[8];
   load8f(p.mean + plane * 8, mean);
   load8f(p.invstd + plane * 8, istd);
+  if (p.gscale != nullptr) {                // g is linear in dA: the per-channel factor is applied to the sums
+    float gs[8];
+    load8f(p.gscale + plane * 8, gs);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s1[i] *= gs[i];
+      t2[i] *= gs[i];
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) s2[i] = istd[i] * (t2[i] - mean[i] * s1[i]);
   __shared__ double red[16][8];
@@ -347,13 +357,20 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_apply_kernel(const BnAct
     cst[1][threadIdx.x] = -sc * m2 * is;
   }
   __syncthreads();
-  float sc[8], sh[8], ca[8], cb[8];
+  float sc[8], sh[8], ca[8], cb[8], sg[8];
   load8f(p.scale + plane * 8, sc);
   load8f(p.shift + plane * 8, sh);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     ca[i] = cst[0][i];
     cb[i] = cst[1][i];
+    sg[i] = sc[i];
+  }
+  if (p.gscale != nullptr) {                // coefficient of g: BatchNorm scale x the per-channel factor on dA (s1, s2 already hold it)
+    float gs[8];
+    load8f(p.gscale + plane * 8, gs);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sg[i] *= gs[i];
   }
   const uint4* __restrict__ zb = p.z.ptr + (static_cast<size_t>(n) * p.z.planes + p.z.plane_off + plane) * HW;
   const uint4* __restrict__ db = p.dA.ptr ? p.dA.ptr + (static_cast<size_t>(n) * p.dA.planes + p.dA.plane_off + plane) * HW : nullptr;
@@ -374,8 +391,8 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_apply_kernel(const BnAct
       bwd_pixel(p, w, f, sc, sh, seed, vbase, e + stride, h);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        g[i] = fmaf(g[i], sc[i], fmaf(v[i], cb[i], ca[i]));
-        h[i] = fmaf(h[i], sc[i], fmaf(w[i], cb[i], ca[i]));
+        g[i] = fmaf(g[i], sg[i], fmaf(v[i], cb[i], ca[i]));
+        h[i] = fmaf(h[i], sg[i], fmaf(w[i], cb[i], ca[i]));
       }
       ob[e] = pack8(g);
       ob[e + stride] = pack8(h);
@@ -387,7 +404,7 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_apply_kernel(const BnAct
       unpack8u(du, d);
       bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], sc[i], fmaf(v[i], cb[i], ca[i]));
+      for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], sg[i], fmaf(v[i], cb[i], ca[i]));
       ob[e] = pack8(g);
     }
   } else {
@@ -413,7 +430,7 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_apply_kernel(const BnAct
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[k][i] = fmaf(g[k][i], sc[i], fmaf(v[k][i], cb[i], ca[i]));
+        for (int i = 0; i < 8; ++i) g[k][i] = fmaf(g[k][i], sg[i], fmaf(v[k][i], cb[i], ca[i]));
         ob[i00 + (k >> 1) * p.W + (k & 1)] = pack8(g[k]);
       }
     }
@@ -702,6 +719,8 @@ extern "C" int abc_bn_act_backward(const AbcBnActBwdDesc* d, void* stream) {
   p.s1 = d->s1; p.s2 = d->s2;
   p.dz = static_cast<uint4*>(d->dz); p.dz_planes = d->dz_planes; p.dz_plane_off = d->dz_plane_off;
   p.count = static_cast<double>(d->N) * d->H * d->W;
+  p.gscale = d->gscale;
+  ABC_REQUIRE((reinterpret_cast<uintptr_t>(d->gscale) & 15) == 0, "abc_bn_act_backward: gscale must be 16-byte aligned");
   ABC_CUDA(cudaMemsetAsync(d->s1, 0, d->C * sizeof(double), st));
   ABC_CUDA(cudaMemsetAsync(d->s2, 0, d->C * sizeof(double), st));
   if (d->dP) {

@@ -13,7 +13,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AbcLossDesc, check, lib
+from ._lib import AbcLossDesc, AbcLossP8Out, check, lib
 
 ATOM_TYPE_WEIGHTS = [1, 0.1, 0.1, 0.1, 1, 1, 1, 1, 1, 10, 10, 10, 10, 10]          # train.py:16
 # kernel order: atom, bond, type, charge, btype, rho, omega, hs  ->  index into model.s (train.py:127-135)
@@ -81,6 +81,18 @@ def loss_forward_backward(s, type_w, targets, logits, scaled=True):
     dlogits = [torch.empty_like(z) for z in logits]
     check(lib.abc_loss_partials(C.byref(_desc(logits, targets, type_w, sums, None, None if scaled else dlogits)), st),
           "abc_loss_partials")
+    total, parts, ds, scale, h2l = _weighting(sums, s, dev)
+    head_scale = None
+    if scaled:
+        check(lib.abc_loss_backward(C.byref(_desc(logits, targets, type_w, None, scale, dlogits)), st), "abc_loss_backward")
+    else:
+        head_scale = scale[h2l]
+    return total, parts, ds, dlogits, head_scale
+
+
+def _weighting(sums, s, dev):
+    """Uncertainty weighting of train.py:127-137 from the 8 numerators / 8 denominators: (total, weighted parts, dL/ds [10],
+    per-loss gradient factor u_k / denom_k in kernel order, head -> loss index)."""
     num, den = sums[:8], sums[8:].clone()
     den[7] = den[7] + 0.1                                                  # train.py:114
     raw = num / den
@@ -89,14 +101,54 @@ def loss_forward_backward(s, type_w, targets, logits, scaled=True):
     u = half * torch.exp(-sk) + sk
     total = (raw * u).sum()
     scale = (u / den).float().contiguous()
-    head_scale = None
-    if scaled:
-        check(lib.abc_loss_backward(C.byref(_desc(logits, targets, type_w, None, scale, dlogits)), st), "abc_loss_backward")
-    else:
-        head_scale = scale[h2l]
     ds = torch.zeros(10, dtype=torch.float64, device=dev)
     ds[idx] = raw * (1.0 - half * torch.exp(-sk))
-    return total, (raw * u).detach(), ds, dlogits, head_scale
+    return total, (raw * u).detach(), ds, scale, h2l
+
+
+def head_grad_planes(h):
+    """P8 planes of the gradient operand of a head with h logit channels (K of its data-gradient GEMM, zero padded)."""
+    c = (h + 15) // 16 * 16 if h <= 64 else (h + 63) // 64 * 64
+    return c // 8
+
+
+def p8_loss_supported(logits):
+    """abc_loss_partials_p8 covers the v2 head list (src/train.py:47): 14 / 3 / 2 classes, 6 bond types, n_omega % 4 == 0."""
+    n_omega = logits[7].shape[1]
+    return ([z.shape[1] for z in logits[:5]] == [1, 14, 3, 2, 1] and n_omega % 4 == 0 and n_omega >= 4
+            and logits[5].shape[1] == 6 * n_omega and logits[6].shape[1] == n_omega)
+
+
+def loss_forward_p8(s, type_w, targets, logits, dz_p8, dbias):
+    """One pass over logits + targets (abc_loss_partials_p8): the losses and the UNSCALED gradient written directly as the bf16 P8
+    operand of the head weight- / data-gradient GEMMs (``dz_p8[i]``: [B, head_grad_planes(h_i), H, W, 8] bf16) plus its per-channel
+    sums (``dbias[i]``: fp64 [h_i]). Returns (total fp64 scalar, 8 weighted parts, dL/ds [10] fp64, head_scale fp32 [8]) with
+    dL/dlogits[i] = head_scale[i] * dz_p8[i]. No fp32 gradient maps, no conversion pass, no host synchronisation."""
+    _lib.require_device()
+    logits = [z.contiguous() for z in logits]
+    if targets[6].dtype != targets[7].dtype:
+        raise ValueError("rho / omega targets must share a dtype (fp32 or fp64, utils.py:91-92)")
+    for i, t in enumerate(targets):
+        want = (torch.float32, torch.float64) if i >= 6 else (torch.float32,)
+        if not (t.is_cuda and t.is_contiguous() and t.dtype in want):
+            raise ValueError(f"target {i}: contiguous CUDA tensor of dtype {want} required")
+    dev = logits[0].device
+    B, _, H, W = logits[0].shape
+    out = AbcLossP8Out()
+    for i, z in enumerate(logits):
+        if not (z.is_cuda and z.dtype == torch.float32):
+            raise ValueError("loss inputs must be fp32 CUDA tensors (no CPU fallback)")
+        g, b = dz_p8[i], dbias[i]
+        if not (g.dtype == torch.bfloat16 and g.is_contiguous() and tuple(g.shape) == (B, g.shape[1], H, W, 8) and g.shape[1] * 8 >= z.shape[1]):
+            raise ValueError(f"dz_p8[{i}]: contiguous bf16 [B, planes, H, W, 8] with planes * 8 >= {z.shape[1]} required")
+        if not (b.dtype == torch.float64 and b.numel() >= z.shape[1]):
+            raise ValueError(f"dbias[{i}]: fp64 [{z.shape[1]}] required")
+        out.dz[i], out.planes[i], out.dbias[i] = g.data_ptr(), g.shape[1], b.data_ptr()
+    sums = torch.empty(16, dtype=torch.float64, device=dev)
+    check(lib.abc_loss_partials_p8(C.byref(_desc(logits, targets, type_w, sums, None, None)), C.byref(out), _lib.current_stream_ptr()),
+          "abc_loss_partials_p8")
+    total, parts, ds, scale, h2l = _weighting(sums, s, dev)
+    return total, parts, ds, scale[h2l]
 
 
 class _HeatmapLossFn(torch.autograd.Function):

@@ -351,7 +351,7 @@ class TrainEngine:
     def _bwd_sum_bufs(self, key, Cc):
         return self.buf(key + ".s1", (Cc,), torch.float64), self.buf(key + ".s2", (Cc,), torch.float64)
 
-    def _bn_backward(self, key, z, Cc, st, act, dA, dA_off, dP, dz, drop_p, seed):
+    def _bn_backward(self, key, z, Cc, st, act, dA, dA_off, dP, dz, drop_p, seed, gscale=None):
         N, _, H, W, _ = z.shape
         s1, s2 = self._bwd_sum_bufs(key, Cc)
         d = AbcBnActBwdDesc()
@@ -366,6 +366,7 @@ class TrainEngine:
         d.act, d.drop_p, d.seed = act, drop_p, 0
         d.seed_dev = seed.data_ptr() if (seed is not None and drop_p > 0) else None
         d.s1, d.s2 = s1.data_ptr(), s2.data_ptr()
+        d.gscale = gscale.data_ptr() if gscale is not None else None
         check(lib.abc_bn_act_backward(C.byref(d), _st()), "abc_bn_act_backward")
         return s1, s2
 
@@ -541,8 +542,21 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ backward
     @torch.no_grad()
-    def backward(self, dlogits, sink, head_scale=None):
+    def head_grad_buffers(self):
+        """The bf16 P8 gradient operands and fp64 bias-gradient vectors of the eight heads (the buffers ``backward`` itself uses): a
+        loss that writes them directly (loss.loss_forward_p8) passes them back as ``backward(None, sink, head_scale, p8=...)``."""
+        from .loss import head_grad_planes
+        sv = self.saved
+        B, H4, W4 = sv["B"], sv["H"] // 4, sv["W"] // 4
+        dl = [self.buf(f"g:logit{i}", (B, head_grad_planes(h_), H4, W4, 8)) for i, h_ in enumerate(self.m.heads)]
+        db = [self.buf(f"g:bias{i}", (h_,), torch.float64) for i, h_ in enumerate(self.m.heads)]
+        return dl, db
+
+    @torch.no_grad()
+    def backward(self, dlogits, sink, head_scale=None, p8=None):
         """dlogits: 8 fp32 NCHW gradients (times ``head_scale[i]``, an fp32 device tensor [8], when given).
+        ``p8 = head_grad_buffers()`` already filled with the UNSCALED gradient (dlogits is ignored; head_scale required): the
+        factor is applied to the head weight / bias gradients and, per channel, inside the BatchNorm backward of the heads.
         ``sink(param, grad_tensor)`` receives every parameter gradient as soon as it is complete (reverse layer order)
         -- e.g. GradBuckets-aware accumulation."""
         m, sv = self.m, self.saved
@@ -552,29 +566,40 @@ class TrainEngine:
         hd = sv["heads"]
         nh = len(m.heads)
         dhid = self.buf("g:hid", (B, 16 * nh, H4, W4, 8))
+        if p8 is not None and head_scale is None:
+            raise ValueError("backward(p8=...): the unscaled P8 gradient needs head_scale")
         for i, (h_, om) in enumerate(zip(m.heads, m.out_modules)):
-            g = dlogits[i]
-            if g is None:
-                g = torch.zeros((B, h_, H4, W4), dtype=torch.float32, device=dev)
-            g = g.contiguous().float()
             c16 = (h_ + 15) // 16 * 16 if h_ <= 64 else (h_ + 63) // 64 * 64     # K of the data-gradient GEMM
             dl = self.buf(f"g:logit{i}", (B, c16 // 8, H4, W4, 8))
             db = self.buf(f"g:bias{i}", (h_,), torch.float64)
-            # one pass: (optional per-head loss scale) * dlogits -> bf16 P8 with zero K padding, + conv2 bias gradient
-            check(lib.abc_nchw_to_p8_ex(g.data_ptr(), dl.data_ptr(), B, h_, H4, W4, c16 // 8,
-                                        head_scale[i:i + 1].data_ptr() if head_scale is not None else None, db.data_ptr(), _st()),
-                  "abc_nchw_to_p8_ex")
+            if p8 is not None:
+                if p8[0][i].data_ptr() != dl.data_ptr() or p8[1][i].data_ptr() != db.data_ptr():
+                    raise ValueError("backward(p8=...): pass the buffers of head_grad_buffers()")
+            else:
+                g = dlogits[i]
+                if g is None:
+                    g = torch.zeros((B, h_, H4, W4), dtype=torch.float32, device=dev)
+                g = g.contiguous().float()
+                # one pass: (optional per-head loss scale) * dlogits -> bf16 P8 with zero K padding, + conv2 bias gradient
+                check(lib.abc_nchw_to_p8_ex(g.data_ptr(), dl.data_ptr(), B, h_, H4, W4, c16 // 8,
+                                            head_scale[i:i + 1].data_ptr() if head_scale is not None else None, db.data_ptr(), _st()),
+                      "abc_nchw_to_p8_ex")
             c8 = (h_ + 7) // 8 * 8
             dw2 = wgrad(dl, 0, c8, hd["hid"], 16 * i, 128, [(0, 0)])[0][:h_]
+            dbf = db.float()
+            if p8 is not None:                                    # the factor the loss kernel left out (linear in the gradient)
+                dw2 = dw2 * head_scale[i]
+                dbf = dbf * head_scale[i]
             sink(om.conv2.weight, dw2.reshape(h_, 128, 1, 1))
-            sink(om.conv2.bias, db.float())
+            sink(om.conv2.bias, dbf)
             def make_d2(om=om, h_=h_, c16=c16):
                 w2 = self._w(om.conv2.weight).reshape(h_, 128)
                 w2p = torch.cat([w2, w2.new_zeros(c16 - h_, 128)], 0)        # K = padded logits channels
                 return Packed(w2p.t().contiguous().unsqueeze(0), self._zeros(128), [(0, 0)], n_tile=128)
             conv(self._pk(f"heads.{i}.conv2.dgrad", make_d2), dl, 0, dhid, out_plane_off=16 * i)
         dzh = self.buf("g:zheads", (B, 16 * nh, H4, W4, 8))
-        s1, s2 = self._bn_backward("bn:heads", hd["z"], 128 * nh, hd["st"], 2, dhid, 0, None, dzh, hd["p_drop"], sv["seed"])
+        gscale = head_scale.float().view(-1, 1).expand(-1, 128).reshape(-1).contiguous() if p8 is not None else None    # per hidden channel
+        s1, s2 = self._bn_backward("bn:heads", hd["z"], 128 * nh, hd["st"], 2, dhid, 0, None, dzh, hd["p_drop"], sv["seed"], gscale=gscale)
         dw1 = wgrad(dzh, 0, 128 * nh, hd["trunk"], 0, 128, TAPS3)            # [9][128*nh][128]
         for i, om in enumerate(m.out_modules):
             sl = slice(128 * i, 128 * (i + 1))

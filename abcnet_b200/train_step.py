@@ -12,12 +12,13 @@ The step is enqueued without any host synchronisation and -- by default -- captu
 """
 from __future__ import annotations
 
+import os
 from typing import Sequence
 
 import torch
 
 from . import _lib
-from .loss import ATOM_TYPE_WEIGHTS, loss_forward_backward
+from .loss import ATOM_TYPE_WEIGHTS, loss_forward_backward, loss_forward_p8, p8_loss_supported
 
 
 class TrainStep:
@@ -63,11 +64,18 @@ class TrainStep:
         if self.buckets is not None:
             self.buckets.zero()
         outs = eng.forward(x)
-        total, parts, ds, dlogits, head_scale = loss_forward_backward(m.s, self.type_w, list(targets), outs, scaled=False)
+        if p8_loss_supported(outs) and not os.environ.get("ABCNET_LOSS_FP32"):
+            # the loss writes the (unscaled) gradient straight into the bf16 P8 operands of the head gradient GEMMs
+            p8 = eng.head_grad_buffers()
+            total, parts, ds, head_scale = loss_forward_p8(m.s, self.type_w, list(targets), outs, *p8)
+            dlogits = None
+        else:                                              # other head lists: fp32 gradient maps + one conversion pass per head
+            p8 = None
+            total, parts, ds, dlogits, head_scale = loss_forward_backward(m.s, self.type_w, list(targets), outs, scaled=False)
         self.loss.copy_(total)
         self.parts.copy_(parts)
         self._sink(m.s, ds.to(m.s.dtype))
-        eng.backward(dlogits, self._sink, head_scale=head_scale)
+        eng.backward(dlogits, self._sink, head_scale=head_scale, p8=p8)
         if self.buckets is not None:
             self.buckets.finish()
         if with_opt and self.opt is not None:

@@ -315,6 +315,19 @@ typedef struct AbcLossDesc {
 enum AbcLossIndex { ABC_L_ATOM = 0, ABC_L_BOND, ABC_L_TYPE, ABC_L_CHARGE, ABC_L_BTYPE, ABC_L_RHO, ABC_L_OMEGA, ABC_L_HS };
 ABC_API int abc_loss_partials(const AbcLossDesc* desc, void* stream);
 ABC_API int abc_loss_backward(const AbcLossDesc* desc, void* stream);
+/* abc_loss_partials in fused mode with the UNSCALED gradient written directly as the tensor-core operand of the head
+ * weight- / data-gradient GEMMs: bf16 P8 [N][planes[k]][H][W][8] for head k (order of `logits`; planes[k] * 8 >= channels of the
+ * head; channel padding and padding planes are written as zeros = the K padding of the GEMM), and dbias[k][c] = sum over
+ * (n, y, x) of the unscaled fp32 gradient (fp64, zeroed by this call) = the bias gradient of the 1x1 head convolutions
+ * (src/unet.py:70) up to the per-loss factor. `dlogits` / `scale` of the descriptor are ignored. Saves the fp32 round trip
+ * of the 501-channel gradient and the abc_nchw_to_p8_ex pass. v2 head list only (14 / 3 / 2 / 6 classes, n_omega % 4 == 0);
+ * any other head list returns ABC_ERR_INVALID and the caller uses abc_loss_partials + abc_nchw_to_p8_ex. */
+typedef struct AbcLossP8Out {
+  void* dz[8];
+  int planes[8];
+  double* dbias[8];
+} AbcLossP8Out;
+ABC_API int abc_loss_partials_p8(const AbcLossDesc* desc, const AbcLossP8Out* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Training-mode building blocks (autograd of src/unet.py as used by src/train.py:94,139-140).
@@ -352,6 +365,8 @@ typedef struct AbcBnActBwdDesc {
   int act; float drop_p; uint64_t seed;
   double* s1; double* s2;                          /* [C] each */
   const uint64_t* seed_dev;                        /* as in AbcBnActDesc */
+  const float* gscale;                             /* [C] device or NULL: dA is multiplied by gscale[c] first (a per-channel
+                                                      factor the producer of dA left out, e.g. the per-loss scale of the heads) */
 } AbcBnActBwdDesc;
 ABC_API int abc_bn_act_backward(const AbcBnActBwdDesc* desc, void* stream);
 /* fp32 NCHW -> bf16 P8 with zero-padded channels (dlogits -> tensor-core operand). */

@@ -203,6 +203,78 @@ def test_fused_loss_mode_and_scaled_p8_conversion():
         assert_close(db.cpu().float(), ref.double().sum((0, 2, 3)).float(), 1e-5, 1e-9, f"dbias {i}")
 
 
+def test_loss_writes_p8_gradient_operands_directly():
+    """abc_loss_partials_p8: the same losses as abc_loss_partials and the unscaled gradient written directly as bf16 P8 operands
+    (zero channel padding and zero padding planes over NaN-filled buffers), bit-identical to rounding the fp32 gradient of the
+    fused fp32 pass, plus the per-channel sums (conv2 bias gradient / per-loss factor). train.py:95-137."""
+    from abcnet_b200.loss import ATOM_TYPE_WEIGHTS, head_grad_planes, loss_forward_backward, loss_forward_p8, p8_loss_supported
+    from oracle import synth
+    dev = "cuda"
+    for seed, B, H, W in ((7, 2, 32, 32), (8, 3, 16, 24)):
+        tg = [torch.from_numpy(t).to(dev).contiguous() for t in synth.dense_targets(seed, B, H, W)]
+        logits = [torch.from_numpy(o).to(dev) for o in synth.random_logits(seed, B, H, W)]
+        assert p8_loss_supported(logits)
+        s = rnd(9, (10,), -0.3, 0.3).to(dev)
+        tw = torch.tensor(ATOM_TYPE_WEIGHTS, device=dev)
+        t2, p2, ds2, d2, hs2 = loss_forward_backward(s, tw, tg, logits, scaled=False)
+        dz = [torch.full((B, head_grad_planes(z.shape[1]), H, W, 8), float("nan"), dtype=torch.bfloat16, device=dev) for z in logits]
+        db = [torch.full((z.shape[1],), float("nan"), dtype=torch.float64, device=dev) for z in logits]
+        t3, p3, ds3, hs3 = loss_forward_p8(s, tw, tg, logits, dz, db)
+        torch.cuda.synchronize()
+        assert abs(t3.item() - t2.item()) <= 1e-6 * abs(t2.item())          # fp32 per-thread partial sums in a different order
+        assert_close(p3.cpu(), p2.cpu(), 1e-6, 1e-12, "parts")
+        assert_close(ds3.cpu(), ds2.cpu(), 1e-6, 1e-12, "ds")
+        assert_close(hs3.cpu(), hs2.cpu(), 1e-6, 1e-12, "head_scale")
+        nonzero = 0
+        for i, g in enumerate(d2):
+            Cc = g.shape[1]
+            got = from_p8(dz[i]).cpu()
+            assert not torch.isnan(got).any(), i
+            assert torch.equal(got[:, :Cc], bf16_round(g.cpu())), i
+            assert (got[:, Cc:] == 0).all(), i
+            ref = g.double().sum((0, 2, 3)).cpu()
+            assert_close(db[i].cpu(), ref, 1e-6, 1e-9 * max(1.0, ref.abs().max().item()), f"dbias {i}")
+            nonzero += int((g != 0).sum())
+        assert nonzero > 1000
+
+
+def test_bn_backward_channel_factor():
+    """AbcBnActBwdDesc.gscale: dz, dbeta, dgamma equal those of the same call on gscale[c] * dA (everything is linear in dA), with the
+    factor applied in fp32 inside the kernel instead of being rounded into the bf16 gradient."""
+    L = _lib()
+    dev = "cuda"
+    N, Cc, H, W = 2, 32, 12, 20
+    z = bf16_round(rnd(1, (N, Cc, H, W)) * 2 + rnd(2, (1, Cc, 1, 1)))
+    gamma, beta = rnd(3, (Cc,), 0.5, 1.5), rnd(4, (Cc,), -0.3, 0.3)
+    zp, bufs, out, _ = bn_forward(z, gamma, beta, 2, False)
+    dA = bf16_round(rnd(5, (N, Cc, H, W)))
+    gs = torch.tensor([2.0 ** (i % 5 - 6) for i in range(Cc)])           # powers of two: gs * dA is exact in bf16
+    res = []
+    for mode in ("factor", "prescaled"):
+        dAp = to_p8(dA if mode == "factor" else dA * gs.view(1, -1, 1, 1)).to(dev)
+        dz = torch.empty_like(zp)
+        s1 = torch.zeros(Cc, dtype=torch.float64, device=dev)
+        s2 = torch.zeros_like(s1)
+        gsd = gs.to(dev)
+        d = L.AbcBnActBwdDesc()
+        d.z, d.z_planes, d.z_plane_off = zp.data_ptr(), Cc // 8, 0
+        d.dA, d.dA_planes, d.dA_plane_off = dAp.data_ptr(), Cc // 8, 0
+        d.dz, d.dz_planes, d.dz_plane_off = dz.data_ptr(), Cc // 8, 0
+        d.N, d.H, d.W, d.C = N, H, W, Cc
+        d.scale, d.shift, d.mean, d.invstd = [t.data_ptr() for t in bufs]
+        d.act, d.drop_p, d.seed = 2, 0.2, 1234
+        d.s1, d.s2 = s1.data_ptr(), s2.data_ptr()
+        d.gscale = gsd.data_ptr() if mode == "factor" else None
+        L.check(L.lib.abc_bn_act_backward(C.byref(d), _st()))
+        torch.cuda.synchronize()
+        res.append((from_p8(dz).cpu(), s1.cpu(), s2.cpu()))
+    (dz_a, s1_a, s2_a), (dz_b, s1_b, s2_b) = res
+    assert_close(s1_a, s1_b, 1e-5, 1e-9, "dbeta")
+    assert_close(s2_a, s2_b, 1e-5, 1e-9, "dgamma")
+    assert_close(dz_a, dz_b, 2 ** -7, 1e-6 * dz_b.abs().max().item(), "dz")
+    assert dz_b.abs().max().item() > 0
+
+
 def test_gather_pack_kernel():
     """abc_gather_pack: out[i] = params[code >> 22][code & 0x3FFFFF] (bf16 or fp32), 0xFFFFFFFF -> 0."""
     import ctypes as C
