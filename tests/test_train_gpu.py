@@ -172,15 +172,20 @@ def _targets(seed, B, h, w):
     return [torch.from_numpy(t).cuda().contiguous() for t in synth.dense_targets(seed, B, h, w)]
 
 
-def test_train_step_matches_autograd_path_and_graph_replays():
+def test_train_step_matches_autograd_path_and_graph_replays(monkeypatch):
     """abcnet_b200.TrainStep (no autograd; eager and CUDA-graph replay) against model(x) + HeatmapLoss + loss.backward():
-    same loss, same gradients (fp32 atomics in the wgrad kernels -> 1e-4 relative), and after two optimiser steps the
-    same parameters. Dropout off so that the three runs see the same function."""
+    same loss, same gradients, and after two optimiser steps the same loss / running statistics. With the fp32 head-gradient maps
+    (ABCNET_LOSS_FP32=1) both paths round the same values, so only the fp32 atomics of the wgrad kernels differ (1e-3); the
+    default TrainStep path (the loss writes bf16 P8 operands itself) is held to the bf16-storage bound. Dropout off so that all
+    runs see the same function."""
     import abcnet_b200
     B, H, W, seed = 2, 64, 64, 11
     tg = None
     results = {}
-    for mode in ("autograd", "eager", "graph"):
+    for mode in ("autograd", "eager", "graph", "eager-fp32-grad"):
+        monkeypatch.delenv("ABCNET_LOSS_FP32", raising=False)
+        if mode == "eager-fp32-grad":                      # fp32 gradient maps + conversion pass: the roundings of the autograd path
+            monkeypatch.setenv("ABCNET_LOSS_FP32", "1")
         m, sd, x = _setup(seed, B, H, W)
         xg = x.cuda()
         tg = tg or _targets(seed, B, H // 4, W // 4)
@@ -209,14 +214,25 @@ def test_train_step_matches_autograd_path_and_graph_replays():
         results[mode] = (losses, g0, {n: p.detach().clone() for n, p in m.named_parameters()},
                          {n: b.detach().clone() for n, b in m.named_buffers()})
     la, ga, pa, ba = results["autograd"]
+    l, g, p, b = results["eager-fp32-grad"]                # same storage roundings as autograd: fp32 atomics are the only difference
+    assert abs(l[0] - la[0]) <= 1e-6 * abs(la[0]) and abs(l[1] - la[1]) <= 2e-3 * abs(la[1]), (l, la)
+    for n in ga:
+        assert _rel(g[n], ga[n]) <= 1e-3 or ga[n].abs().max().item() == 0.0, (n, _rel(g[n], ga[n]))
     for mode in ("eager", "graph"):
         l, g, p, b = results[mode]
         assert abs(l[0] - la[0]) <= 1e-6 * abs(la[0]), (mode, l, la)
-        worst = max(((_rel(g[n], ga[n]), n) for n in ga if ga[n].abs().max().item() != 0.0))
-        assert worst[0] <= 1e-3, (mode, worst)
+        # TrainStep rounds the UNSCALED head gradient to bf16 and applies the per-loss factor afterwards (abc_loss_partials_p8), the
+        # autograd path rounds the scaled one: from the heads down, every bf16 storage point of the backward pass rounds slightly
+        # different fp32 values in the two runs. Per parameter the bound is therefore the one of the in-situ test against fp64
+        # (3e-2; the worst cases are cancellation-dominated sums such as the bias of an up-convolution that feeds a BatchNorm,
+        # 2.1e-2 measured), and all gradients taken together must agree to 1e-2 in the L2 sense.
+        names = [n for n in ga if ga[n].abs().max().item() != 0.0]
+        worst = max((_rel(g[n], ga[n]), n) for n in names)
+        assert worst[0] <= 3e-2, (mode, worst)
+        flat, flat_a = torch.cat([g[n].flatten().double() for n in names]), torch.cat([ga[n].flatten().double() for n in names])
+        assert _rel(flat, flat_a) <= 1e-2, (mode, _rel(flat, flat_a))
         # after one Adam step: the first update is sign-like (lr * g / |g|), so parameters whose gradient is ~0 move by +-lr on
-        # rounding noise. TrainStep rounds the UNSCALED head gradient to bf16 and applies the per-loss factor afterwards, the
-        # autograd path rounds the scaled one: same gradients to 1e-3 (above), step-2 loss to 5e-3 (2.5e-3 measured)
+        # that rounding noise: step-2 loss to 5e-3 (2.5e-3 measured)
         assert abs(l[1] - la[1]) <= 5e-3 * abs(la[1]), (mode, l, la)
         for n in ba:                                                               # running statistics: exactly two updates
             assert _rel(b[n].float(), ba[n].float()) <= 1e-2, (mode, n)      # 2nd update sees a (noise-amplified) step-2 forward
