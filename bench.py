@@ -262,7 +262,7 @@ def run_reference(args, rank, world):
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{steps} x {n} images, oracle port of src/unet.py + img2smiles.py:62-193"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    _emit(out)
 
 
 # ----------------------------------------------------------------------------------------- GPU arm: training step
@@ -808,7 +808,27 @@ def run_ours(args, rank, world, local_rank):
            "graph_replay": None if graph_ms is None else {"ms_per_step": graph_ms, "value": world * B / (graph_ms * 1e-3), "unit": UNIT,
                                                            "what": "the device-resident step (`value` = eager launches) as one CUDA-graph replay"},
            "gpu_launches": int(launches), "clocks": clocks, "train": train}
-    print(json.dumps(out))
+    _emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def _emit(obj):
+    """The ONE JSON line, on the process's original stdout."""
+    f = _REAL_STDOUT or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
+def _reserve_stdout():
+    """Keep a private handle on the original stdout and point file descriptor 1 at stderr: libraries that write to stdout from C
+    (NCCL prints 'NCCL version ...' there at NCCL_DEBUG=VERSION / WARN) can then not put a second line next to the JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def main():
@@ -833,6 +853,8 @@ def main():
     if os.environ.get("ABCNET_BENCH_WATCHDOG"):          # debugging aid: dump every thread's stack and exit if the run takes too long
         import faulthandler
         faulthandler.dump_traceback_later(float(os.environ["ABCNET_BENCH_WATCHDOG"]), exit=True)
+    if world > 1 or args.gpus == 1:
+        _reserve_stdout()                                # (not in the convenience re-launch below: the children inherit fd 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -852,7 +874,7 @@ def main():
             out = run_train(args, rank, world, torch.device("cuda", local_rank))
             if rank == 0:
                 out.update(n_gpus=world, steps=args.steps, higher_is_better=True)
-                print(json.dumps(out))
+                _emit(out)
         else:
             run_ours(args, rank, world, local_rank)
     finally:
