@@ -121,7 +121,7 @@ class AbcWgradDesc(C.Structure):
         ("in_", C.c_void_p), ("in_planes", C.c_int), ("in_plane_off", C.c_int), ("cin", C.c_int),
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
         ("ntaps", C.c_int), ("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9),
-        ("dw", C.c_void_p),
+        ("dw", C.c_void_p), ("row_boxes", C.c_int),
     ]
 
 

@@ -35,8 +35,12 @@ struct WgradParams {
   // tap-folded mode (cin <= 32): every tap's shifted 16 x 8 box of the input is loaded as its own smem block, so that the
   // taps line up on the GEMM N axis (N = taps * cin) and ONE MMA per K step replaces `ntaps` N = cin MMAs whose cost is
   // bounded below by the A-operand read, not by N.
+  // row-box mode (fold == 2; the plain 3x3 tap set, cin <= 32): only the THREE row-shifted 16 x 10 boxes are loaded (the dy taps on
+  // the GEMM N axis, N = 3 * cin) and the dx taps are 16-byte start-address shifts inside them: three MMAs per K step, but
+  // 19 KB instead of 40 KB of L2 -> shared-memory traffic per 128 pixels, which is what bounded the 9-box variant.
   int fold, fold_groups, fold_tap0[2], fold_ntaps[2];
   int tap_dy[9], tap_dx[9];
+  int tap_col[9];          // row-box mode: accumulator column block of tap t = (dx + 1) * 3 + (dy + 1)
   float* dw;               // [ntaps][cout][cin] fp32, accumulated with atomicAdd
 };
 
@@ -90,7 +94,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant_
         const uint32_t dst = stage0 + stage * p.a_stage_bytes;
         mbar_arrive_expect_tx(bar_full + 8 * stage, p.dz_tile_bytes + p.in_tile_bytes);
         tma_load_4d(dst, &tmap_dz, bar_full + 8 * stage, tx * 64, ty * 16, p.dz_plane_off + co_t * 16, n);
-        if (p.fold) {
+        if (p.fold == 2) {
+          const uint32_t blk = static_cast<uint32_t>(p.n_tile >> 3) * 2560u;      // one dy box: planes x 16 rows x 10 pixels x 16 B
+          for (int j = 0; j < 3; ++j)
+            tma_load_4d(dst + 32768 + j * blk, &tmap_in, bar_full + 8 * stage, (tx * 8 - 1) * 8, ty * 16 + j - 1,
+                        p.a_plane_off + ci_t * (p.n_tile >> 3), n);
+        } else if (p.fold) {
           const uint32_t blk = static_cast<uint32_t>(p.n_tile >> 3) * 2048u;
           for (int t = 0; t < ntap; ++t)
             tma_load_4d(dst + 32768 + t * blk, &tmap_in, bar_full + 8 * stage, (tx * 8 + p.tap_dx[tap0 + t]) * 8,
@@ -110,15 +119,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant_
     // A = dz^T (M = co): MN-major, LBO = next 8 pixels = next tile row (128 B), SBO = next 8 channels = plane pitch (2048 B)
     // B = a     (N = ci): MN-major, LBO = halo row pitch, SBO = halo plane pitch
     const uint32_t idesc = umma_idesc_bf16(128, p.n_tile, 1, 1);
-    const uint32_t idesc_f0 = umma_idesc_bf16(128, p.fold ? p.fold_ntaps[0] * p.n_tile : 16, 1, 1);
+    const uint32_t idesc_f0 = umma_idesc_bf16(128, p.fold == 2 ? 3 * p.n_tile : (p.fold ? p.fold_ntaps[0] * p.n_tile : 16), 1, 1);
     const uint32_t idesc_f1 = umma_idesc_bf16(128, (p.fold && p.fold_groups > 1) ? p.fold_ntaps[1] * p.n_tile : 16, 1, 1);
     const uint64_t a_hi64 = umma_desc_hi(128, 2048);
-    const uint64_t b_hi64 = p.fold ? umma_desc_hi(128, 2048) : umma_desc_hi(p.in_row_bytes, p.in_plane_bytes);
+    const uint64_t b_hi64 = p.fold == 2 ? umma_desc_hi(160, 2560) : (p.fold ? umma_desc_hi(128, 2048) : umma_desc_hi(p.in_row_bytes, p.in_plane_bytes));
     const uint32_t a_hi = static_cast<uint32_t>(a_hi64 >> 32), b_hi = static_cast<uint32_t>(b_hi64 >> 32);
     const uint32_t a_lo0 = static_cast<uint32_t>(a_hi64) | (stage0 >> 4);
     const uint32_t b_lo0 = static_cast<uint32_t>(b_hi64) | ((stage0 + 32768) >> 4);
     const uint32_t stage16 = p.a_stage_bytes >> 4;
-    const uint32_t a_kstep = (2 * 128) >> 4, b_kstep = p.fold ? a_kstep : (2 * p.in_row_bytes) >> 4;
+    const uint32_t a_kstep = (2 * 128) >> 4, b_kstep = p.fold == 2 ? (2 * 160) >> 4 : (p.fold ? a_kstep : (2 * p.in_row_bytes) >> 4);
     const uint32_t fold_blk16 = (static_cast<uint32_t>(p.n_tile >> 3) * 2048u) >> 4;
     int stage = 0;
     uint32_t phase = 0, first = 0;
@@ -127,7 +136,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant_
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_base = a_lo0 + stage * stage16, b_base = b_lo0 + stage * stage16;
-        if (p.fold) {
+        if (p.fold == 2) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)          // dx = j - 1: one pixel = 16 bytes further into the 10-pixel rows
+              umma_bf16_lohi(tmem_base + j * 3 * p.n_tile, a_base + s * a_kstep, a_hi, b_base + j + s * b_kstep, b_hi, idesc_f0,
+                             s != 0 ? 1u : first);
+        } else if (p.fold) {
 #pragma unroll
           for (int s = 0; s < 8; ++s) {
             umma_bf16_lohi(tmem_base, a_base + s * a_kstep, a_hi, b_base + s * b_kstep, b_hi, idesc_f0, s != 0 ? 1u : first);
@@ -162,7 +178,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant_
     tc_fence_after();
     for (int t = 0; t < ntap; ++t) {
       float* dst = p.dw + (static_cast<size_t>(tap0 + t) * p.cout + co) * p.cin + ci_t * p.n_tile;
-      const uint32_t taddr = tmem_base + t * p.n_tile + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (p.fold == 2 ? p.tap_col[tap0 + t] : t) * p.n_tile + (static_cast<uint32_t>(q * 32) << 16);
       for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
         uint32_t raw[16];
         tmem_ld16(taddr + c0, raw);
@@ -264,6 +280,23 @@ extern "C" int abc_conv_wgrad(const AbcWgradDesc* d, void* stream) {
       p.fold_tap0[1] = p.fold_ntaps[0]; p.fold_ntaps[1] = d->ntaps - p.fold_ntaps[0];
     }
   }
+  // Opt-in (AbcWgradDesc.row_boxes): measured equal to the 9-box variant on the whole training step (1744 vs 1745 img/s,
+  // profiles/r02_train_ab_wgrad_rowbox.txt) -- the halved L2 fill is paid back by three A-operand reads per K step -- so the
+  // default stays the 9-box variant; both are covered by tests/test_train_ops_gpu.py::test_wgrad_conv3x3.
+  if (p.fold && d->ntaps == 9 && d->row_boxes) {
+    bool seen[9] = {false, false, false, false, false, false, false, false, false};
+    bool plain = true;
+    for (int t = 0; t < 9; ++t) {
+      const int cb = (d->tap_dx[t] + 1) * 3 + (d->tap_dy[t] + 1);
+      plain = plain && !seen[cb];
+      seen[cb] = true;
+      p.tap_col[t] = cb;
+    }
+    if (plain) {                       // the 9 distinct taps of a 3x3 kernel, in any order
+      p.fold = 2;
+      p.in_tile_bytes = 3u * (p.n_tile / 8) * 2560u;
+    }
+  }
   p.a_stage_bytes = 32768 + ((p.in_tile_bytes + 1023u) & ~1023u);
   for (int t = 0; t < d->ntaps; ++t) {
     p.tap_off[t] = static_cast<uint32_t>(((d->tap_dy[t] + halo) * cols + (d->tap_dx[t] + halo)) * 16);
@@ -278,7 +311,8 @@ extern "C" int abc_conv_wgrad(const AbcWgradDesc* d, void* stream) {
 
   CUtensorMap map_dz, map_in;
   if (int rc = make_map(&map_dz, d->dz, d->W, d->H, d->dz_planes, d->N, 8, 16, p.m_planes)) return rc;
-  if (int rc = make_map(&map_in, d->in, d->W, d->H, d->in_planes, d->N, p.fold ? 8 : cols, p.fold ? 16 : rows, p.n_tile / 8)) return rc;
+  if (int rc = make_map(&map_in, d->in, d->W, d->H, d->in_planes, d->N, p.fold == 2 ? 10 : (p.fold ? 8 : cols), p.fold ? 16 : rows, p.n_tile / 8))
+    return rc;
   static PerDeviceOnce attr_once;
   ABC_CUDA(attr_once.run([] { return cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); }));
   const int gy = p.n_co_tiles * p.n_ci_tiles * p.tap_groups;

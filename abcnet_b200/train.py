@@ -211,6 +211,7 @@ def wgrad(dz, dz_off, cout, a, a_off, cin, taps):
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
     d.dw = dw.data_ptr()
+    d.row_boxes = 1 if os.environ.get("ABCNET_WGRAD_ROWBOX") else 0
     with _timed(f"wgrad {cin}->{cout} t{len(taps)} @{H}x{W}"):
         check(lib.abc_conv_wgrad(C.byref(d), _st()), "abc_conv_wgrad")
     return dw

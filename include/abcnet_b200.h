@@ -425,6 +425,9 @@ typedef struct AbcWgradDesc {
   int N, H, W;
   int ntaps; int tap_dy[9]; int tap_dx[9];
   float* dw;
+  int row_boxes;   /* 0 (default) / 1: tap-folded launches (cin <= 32, the plain 3x3 tap set) load three row-shifted 16 x 10 boxes and
+                      take the dx taps as operand start offsets instead of loading nine shifted 16 x 8 boxes: half the L2 ->
+                      shared-memory traffic, three MMAs per K step instead of one; same result, measured equally fast */
 } AbcWgradDesc;
 ABC_API int abc_conv_wgrad(const AbcWgradDesc* desc, void* stream);
 /* First convolution without folded BN / activation (training mode): z = conv(img) + b. */

@@ -91,7 +91,7 @@ def test_bn_train_forward_and_backward(act):
     assert_close(s2.cpu().float(), gg.grad.float(), 1e-3, 1e-3, "dgamma")
 
 
-def run_wgrad(dz, a, taps):
+def run_wgrad(dz, a, taps, row_boxes=0):
     L = _lib()
     dev = "cuda"
     N, cout, H, W = dz.shape
@@ -105,6 +105,7 @@ def run_wgrad(dz, a, taps):
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
     d.dw = dw.data_ptr()
+    d.row_boxes = row_boxes
     L.check(L.lib.abc_conv_wgrad(C.byref(d), _st()), "abc_conv_wgrad")
     torch.cuda.synchronize()
     return dw.cpu()
@@ -112,16 +113,21 @@ def run_wgrad(dz, a, taps):
 
 @pytest.mark.parametrize("cin,cout,N,H,W", [
     (16, 16, 2, 32, 32), (32, 64, 2, 32, 24), (128, 128, 2, 32, 32), (256, 256, 2, 16, 16), (128, 1024, 1, 32, 16),
-    (512, 256, 1, 16, 16), (64, 128, 3, 6, 10),
+    (512, 256, 1, 16, 16), (64, 128, 3, 6, 10), (16, 32, 2, 20, 12), (32, 32, 1, 37, 21),
 ])
 def test_wgrad_conv3x3(cin, cout, N, H, W):
     a = bf16_round(rnd(cin, (N, cin, H, W)))
     dz = bf16_round(rnd(cout + 1, (N, cout, H, W)))
     w = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
     (F.conv2d(a.double(), w, padding=1) * dz.double()).sum().backward()
-    got = run_wgrad(dz, a, TAPS3)                                  # [9][cout][cin]
     ref = torch.stack([w.grad[:, :, dy + 1, dx + 1] for dy, dx in TAPS3]).float()
-    assert_close(got, ref, 1e-3, 1e-3 * ref.abs().max().item(), f"wgrad {cin}->{cout}")
+    for row_boxes in ((0, 1) if cin <= 32 else (0,)):             # the two tap-folded variants (AbcWgradDesc.row_boxes)
+        got = run_wgrad(dz, a, TAPS3, row_boxes)                   # [9][cout][cin]
+        assert_close(got, ref, 1e-3, 1e-3 * ref.abs().max().item(), f"wgrad {cin}->{cout} row_boxes={row_boxes}")
+    if cin <= 32:                                                  # any order of the nine taps
+        perm = [TAPS3[i] for i in (4, 0, 8, 2, 6, 1, 3, 5, 7)]
+        got = run_wgrad(dz, a, perm, 1)
+        assert_close(got, torch.stack([w.grad[:, :, dy + 1, dx + 1] for dy, dx in perm]).float(), 1e-3, 1e-3 * ref.abs().max().item(), "permuted taps")
 
 
 def test_wgrad_1x1_and_padded_cout():
