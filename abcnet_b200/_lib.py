@@ -98,7 +98,7 @@ class AbcBnActDesc(C.Structure):
         ("pool", C.c_void_p), ("pool_planes", C.c_int), ("pool_plane_off", C.c_int),
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
         ("scale", C.c_void_p), ("shift", C.c_void_p),
-        ("act", C.c_int), ("drop_p", C.c_float), ("seed", C.c_uint64), ("seed_dev", C.c_void_p),
+        ("act", C.c_int), ("drop_p", C.c_float), ("seed", C.c_uint64), ("seed_dev", C.c_void_p), ("drop_mask", C.c_void_p),
     ]
 
 
@@ -111,7 +111,7 @@ class AbcBnActBwdDesc(C.Structure):
         ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
         ("act", C.c_int), ("drop_p", C.c_float), ("seed", C.c_uint64),
-        ("s1", C.c_void_p), ("s2", C.c_void_p), ("seed_dev", C.c_void_p), ("gscale", C.c_void_p),
+        ("s1", C.c_void_p), ("s2", C.c_void_p), ("seed_dev", C.c_void_p), ("gscale", C.c_void_p), ("drop_mask", C.c_void_p),
     ]
 
 

@@ -138,6 +138,7 @@ struct BnActParams {
   float drop_p;
   unsigned long long seed;
   const unsigned long long* seed_dev;
+  unsigned char* drop_mask;   // optional [N][planes][HW]: bit i of a byte = channel i of that P8 vector was kept
 };
 
 template <bool POOL>
@@ -156,7 +157,15 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActParams p) {
     for (int e = blockIdx.x * 256 + threadIdx.x; e < HW; e += stride) {
       float v[8], dm[8];
       unpack8u(zb[e], v);
-      if (p.drop_p > 0.f) drop_scale8(seed, vbase + e, p.drop_p, dm);
+      if (p.drop_p > 0.f) {
+        drop_scale8(seed, vbase + e, p.drop_p, dm);
+        if (p.drop_mask != nullptr) {               // the backward passes then read 1 byte instead of hashing again
+          unsigned bits = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bits |= (dm[i] != 0.f ? 1u : 0u) << i;
+          p.drop_mask[vbase + e] = static_cast<unsigned char>(bits);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float a = act_fwd(fmaf(v[i], sc[i], sh[i]), p.act);
@@ -211,13 +220,23 @@ struct BnActBwdParams {
   int dz_planes, dz_plane_off;
   double count;
   const float* gscale;      // [C] or null: per-channel factor on dA / dP (everything downstream is linear in g)
+  const unsigned char* drop_mask;   // the mask bytes bn_act wrote (null: regenerate the mask from the counter-based hash)
 };
 
 // Gradient g wrt the BatchNorm output for one pixel (8 channels): g = dA * act'(pre) * dropout scale.
+// mbits >= 0: the saved keep bits of this vector (AbcBnActDesc.drop_mask); < 0: regenerate them.
 __device__ __forceinline__ void bwd_pixel(const BnActBwdParams& p, const float* v, const float* d, const float* sc, const float* sh,
-                                          unsigned long long seed, unsigned long long vbase, int e, float* g) {
+                                          unsigned long long seed, unsigned long long vbase, int e, float* g, int mbits = -1) {
   float dm[8];
-  if (p.drop_p > 0.f) drop_scale8(seed, vbase + e, p.drop_p, dm);
+  if (p.drop_p > 0.f) {
+    if (mbits >= 0) {
+      const float keep = 1.f / (1.f - p.drop_p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dm[i] = ((mbits >> i) & 1) ? keep : 0.f;
+    } else {
+      drop_scale8(seed, vbase + e, p.drop_p, dm);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float pre = fmaf(v[i], sc[i], sh[i]);
@@ -267,16 +286,18 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_reduce_kernel(const BnAc
   if (!POOL) {
     const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
     const unsigned long long vbase = (static_cast<unsigned long long>(n) * p.planes + plane) * HW;
+    const unsigned char* __restrict__ mk = (p.drop_p > 0.f && p.drop_mask != nullptr) ? p.drop_mask + vbase : nullptr;
     int e = blockIdx.x * 256 + threadIdx.x;
     for (; e + stride < HW; e += 2 * stride) {            // four independent 16-byte loads in flight per thread
       const uint4 zu0 = zb[e], du0 = db[e], zu1 = zb[e + stride], du1 = db[e + stride];
+      const int m0 = mk ? mk[e] : -1, m1 = mk ? mk[e + stride] : -1;
       float v[8], d[8], g[8], w[8], f[8], h[8];
       unpack8u(zu0, v);
       unpack8u(du0, d);
       unpack8u(zu1, w);
       unpack8u(du1, f);
-      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
-      bwd_pixel(p, w, f, sc, sh, seed, vbase, e + stride, h);
+      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g, m0);
+      bwd_pixel(p, w, f, sc, sh, seed, vbase, e + stride, h, m1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s1[i] += g[i] + h[i];
@@ -286,9 +307,10 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_reduce_kernel(const BnAc
     if (e < HW) {
       float v[8], d[8], g[8];
       const uint4 zu = zb[e], du = db[e];
+      const int m0 = mk ? mk[e] : -1;
       unpack8u(zu, v);
       unpack8u(du, d);
-      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
+      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g, m0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s1[i] += g[i];
@@ -379,16 +401,18 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_apply_kernel(const BnAct
   if (!POOL) {
     const unsigned long long seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
     const unsigned long long vbase = (static_cast<unsigned long long>(n) * p.planes + plane) * HW;
+    const unsigned char* __restrict__ mk = (p.drop_p > 0.f && p.drop_mask != nullptr) ? p.drop_mask + vbase : nullptr;
     int e = blockIdx.x * 256 + threadIdx.x;
     for (; e + stride < HW; e += 2 * stride) {            // four independent 16-byte loads in flight per thread
       const uint4 zu0 = zb[e], du0 = db[e], zu1 = zb[e + stride], du1 = db[e + stride];
+      const int m0 = mk ? mk[e] : -1, m1 = mk ? mk[e + stride] : -1;
       float v[8], d[8], g[8], w[8], f[8], h[8];
       unpack8u(zu0, v);
       unpack8u(du0, d);
       unpack8u(zu1, w);
       unpack8u(du1, f);
-      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
-      bwd_pixel(p, w, f, sc, sh, seed, vbase, e + stride, h);
+      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g, m0);
+      bwd_pixel(p, w, f, sc, sh, seed, vbase, e + stride, h, m1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         g[i] = fmaf(g[i], sg[i], fmaf(v[i], cb[i], ca[i]));
@@ -400,9 +424,10 @@ __global__ void __launch_bounds__(256, MINB) bn_act_bwd_apply_kernel(const BnAct
     if (e < HW) {
       float v[8], d[8], g[8];
       const uint4 zu = zb[e], du = db[e];
+      const int m0 = mk ? mk[e] : -1;
       unpack8u(zu, v);
       unpack8u(du, d);
-      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g);
+      bwd_pixel(p, v, d, sc, sh, seed, vbase, e, g, m0);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], sg[i], fmaf(v[i], cb[i], ca[i]));
       ob[e] = pack8(g);
@@ -681,6 +706,7 @@ extern "C" int abc_bn_act(const AbcBnActDesc* d, void* stream) {
   p.N = d->N; p.H = d->H; p.W = d->W; p.planes = d->C / 8;
   p.scale = d->scale; p.shift = d->shift; p.act = d->act; p.drop_p = d->drop_p; p.seed = d->seed;
   p.seed_dev = reinterpret_cast<const unsigned long long*>(d->seed_dev);
+  p.drop_mask = static_cast<unsigned char*>(d->drop_mask);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d->pool) {
     const long long items = static_cast<long long>(d->H / 2) * (d->W / 2);
@@ -720,6 +746,7 @@ extern "C" int abc_bn_act_backward(const AbcBnActBwdDesc* d, void* stream) {
   p.dz = static_cast<uint4*>(d->dz); p.dz_planes = d->dz_planes; p.dz_plane_off = d->dz_plane_off;
   p.count = static_cast<double>(d->N) * d->H * d->W;
   p.gscale = d->gscale;
+  p.drop_mask = static_cast<const unsigned char*>(d->drop_mask);
   ABC_REQUIRE((reinterpret_cast<uintptr_t>(d->gscale) & 15) == 0, "abc_bn_act_backward: gscale must be 16-byte aligned");
   ABC_CUDA(cudaMemsetAsync(d->s1, 0, d->C * sizeof(double), st));
   ABC_CUDA(cudaMemsetAsync(d->s2, 0, d->C * sizeof(double), st));
@@ -733,7 +760,7 @@ extern "C" int abc_bn_act_backward(const AbcBnActBwdDesc* d, void* stream) {
     const long long items = static_cast<long long>(d->H) * d->W;
     const dim3 grid(plane_grid_x(items, cp, d->N, 2), cp, d->N);
     // resident blocks per SM (register cap) of the two passes: ABCNET_BN_MINB = <reduce digit><apply digit>, read once
-    static const int minb = [] { const char* e = getenv("ABCNET_BN_MINB"); return e ? atoi(e) : 44; }();
+    static const int minb = [] { const char* e = getenv("ABCNET_BN_MINB"); return e ? atoi(e) : 34; }();
     if (minb / 10 == 4) bn_act_bwd_reduce_kernel<false, 4><<<grid, 256, 0, st>>>(p);
     else bn_act_bwd_reduce_kernel<false, 3><<<grid, 256, 0, st>>>(p);
     if (int rc = launch_check("bn_act_bwd_reduce_kernel")) return rc;

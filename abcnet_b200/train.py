@@ -271,6 +271,7 @@ class TrainEngine:
     def __init__(self, model):
         self.m = model
         self.bufs = {}
+        self._mask_keys = set()          # BatchNorm keys whose forward pass stored its dropout keep bits (AbcBnActDesc.drop_mask)
         self.saved = {}
         self.arena = None            # PackArena of the current parameter storage (ABCNET_NO_ARENA=1: re-pack with torch ops)
         self._packs = {}
@@ -346,6 +347,12 @@ class TrainEngine:
         d.scale, d.shift = st[0].data_ptr(), st[1].data_ptr()
         d.act, d.drop_p, d.seed = act, drop_p, 0
         d.seed_dev = seed.data_ptr() if (seed is not None and drop_p > 0) else None
+        if drop_p > 0 and pool is None and not os.environ.get("ABCNET_NO_DROP_MASK"):
+            # 1 byte of keep bits per P8 vector (+3 % traffic) saves the backward passes the mask hash they were co-bound by
+            d.drop_mask = self.buf(key + ".mask", (N * (Cc // 8) * H * W,), torch.uint8).data_ptr()
+            self._mask_keys.add(key)
+        else:
+            self._mask_keys.discard(key)
         check(lib.abc_bn_act(C.byref(d), _st()), "abc_bn_act")
         return st
 
@@ -368,6 +375,8 @@ class TrainEngine:
         d.seed_dev = seed.data_ptr() if (seed is not None and drop_p > 0) else None
         d.s1, d.s2 = s1.data_ptr(), s2.data_ptr()
         d.gscale = gscale.data_ptr() if gscale is not None else None
+        if drop_p > 0 and key in self._mask_keys:                      # the keep bits the forward pass of this step stored
+            d.drop_mask = self.bufs[key + ".mask"].data_ptr()
         check(lib.abc_bn_act_backward(C.byref(d), _st()), "abc_bn_act_backward")
         return s1, s2
 

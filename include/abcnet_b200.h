@@ -353,6 +353,9 @@ typedef struct AbcBnActDesc {
   int act;                                         /* 0 none, 1 ReLU, 2 LeakyReLU(0.01) */
   float drop_p; uint64_t seed;                     /* counter-based dropout, p = 0 disables */
   const uint64_t* seed_dev;                        /* optional device word added to seed at run time (CUDA-graph replays) */
+  void* drop_mask;                                 /* optional uint8 [N][C/8][H][W]: with dropout (no pool) the keep bits of each P8
+                                                      vector are also stored (bit i = channel 8 * plane + i kept), so that
+                                                      abc_bn_act_backward reads 1 byte per vector instead of re-hashing */
 } AbcBnActDesc;
 ABC_API int abc_bn_act(const AbcBnActDesc* desc, void* stream);
 typedef struct AbcBnActBwdDesc {
@@ -367,6 +370,7 @@ typedef struct AbcBnActBwdDesc {
   const uint64_t* seed_dev;                        /* as in AbcBnActDesc */
   const float* gscale;                             /* [C] device or NULL: dA is multiplied by gscale[c] first (a per-channel
                                                       factor the producer of dA left out, e.g. the per-loss scale of the heads) */
+  const void* drop_mask;                           /* the bytes abc_bn_act stored (AbcBnActDesc.drop_mask) or NULL = regenerate */
 } AbcBnActBwdDesc;
 ABC_API int abc_bn_act_backward(const AbcBnActBwdDesc* desc, void* stream);
 /* fp32 NCHW -> bf16 P8 with zero-padded channels (dlogits -> tensor-core operand). */
