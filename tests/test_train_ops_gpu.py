@@ -281,6 +281,59 @@ def test_bn_backward_channel_factor():
     assert dz_b.abs().max().item() > 0
 
 
+def test_stored_dropout_mask_equals_regenerated_mask():
+    """AbcBnActDesc.drop_mask: the keep bits abc_bn_act stores (1 byte per P8 vector) are exactly the mask the backward pass would
+    regenerate from the counter-based hash -- dz, dbeta, dgamma identical with and without them -- and they describe the zeros of
+    the forward output (LeakyReLU never yields an exact zero by itself). unet.py:69."""
+    L = _lib()
+    dev = "cuda"
+    N, Cc, H, W = 2, 32, 12, 20
+    z = bf16_round(rnd(1, (N, Cc, H, W)) * 2 + rnd(2, (1, Cc, 1, 1)))
+    gamma, beta = rnd(3, (Cc,), 0.5, 1.5), rnd(4, (Cc,), -0.3, 0.3)
+    zp, bufs, _, _ = bn_forward(z, gamma, beta, 2, False)                # statistics / scale / shift
+    seed_dev = torch.tensor([77], dtype=torch.int64, device=dev)
+    mask = torch.full((N * (Cc // 8) * H * W,), 255, dtype=torch.uint8, device=dev)
+    out = torch.empty_like(zp)
+    f = L.AbcBnActDesc()
+    f.z, f.z_planes, f.z_plane_off = zp.data_ptr(), Cc // 8, 0
+    f.out, f.out_planes, f.out_plane_off = out.data_ptr(), Cc // 8, 0
+    f.N, f.H, f.W, f.C = N, H, W, Cc
+    f.scale, f.shift = bufs[0].data_ptr(), bufs[1].data_ptr()
+    f.act, f.drop_p, f.seed = 2, 0.2, 1234
+    f.seed_dev = seed_dev.data_ptr()
+    f.drop_mask = mask.data_ptr()
+    L.check(L.lib.abc_bn_act(C.byref(f), _st()))
+    torch.cuda.synchronize()
+    a = from_p8(out).cpu()                                                 # [N, C, H, W]
+    bits = mask.view(N, Cc // 8, H, W).cpu()
+    kept = torch.stack([(bits >> i) & 1 for i in range(8)], 2).reshape(N, Cc, H, W).bool()      # channel = plane * 8 + i
+    assert torch.equal(kept, a != 0)
+    assert 0.7 < kept.float().mean().item() < 0.9
+    dA = bf16_round(rnd(5, (N, Cc, H, W)))
+    dAp = to_p8(dA).to(dev)
+    res = []
+    for use_mask in (True, False):
+        dz = torch.empty_like(zp)
+        s1 = torch.zeros(Cc, dtype=torch.float64, device=dev)
+        s2 = torch.zeros_like(s1)
+        d = L.AbcBnActBwdDesc()
+        d.z, d.z_planes, d.z_plane_off = zp.data_ptr(), Cc // 8, 0
+        d.dA, d.dA_planes, d.dA_plane_off = dAp.data_ptr(), Cc // 8, 0
+        d.dz, d.dz_planes, d.dz_plane_off = dz.data_ptr(), Cc // 8, 0
+        d.N, d.H, d.W, d.C = N, H, W, Cc
+        d.scale, d.shift, d.mean, d.invstd = [t.data_ptr() for t in bufs]
+        d.act, d.drop_p, d.seed = 2, 0.2, 1234
+        d.seed_dev = seed_dev.data_ptr()
+        d.s1, d.s2 = s1.data_ptr(), s2.data_ptr()
+        d.drop_mask = mask.data_ptr() if use_mask else None
+        L.check(L.lib.abc_bn_act_backward(C.byref(d), _st()))
+        torch.cuda.synchronize()
+        res.append((dz.clone(), s1.cpu(), s2.cpu()))
+    assert torch.equal(res[0][0].view(torch.int16), res[1][0].view(torch.int16))
+    assert_close(res[0][1], res[1][1], 1e-12, 1e-12, "dbeta")             # fp64 atomics: order only
+    assert_close(res[0][2], res[1][2], 1e-12, 1e-12, "dgamma")
+
+
 def test_gather_pack_kernel():
     """abc_gather_pack: out[i] = params[code >> 22][code & 0x3FFFFF] (bf16 or fp32), 0xFFFFFFFF -> 0."""
     import ctypes as C
