@@ -101,6 +101,30 @@ def golden_unet():
     print("unet goldens written")
 
 
+def golden_unet_rgb():
+    """UNet(in_channels=3) on real-valued input -- the configuration of the reference's own self-check (src/unet.py:122-134),
+    at a size that keeps the fixture small. Eval and train-mode (dropout p = 0) logits."""
+    UNet = import_ref_unet()
+    B, H, W, seed = 1, 96, 64, 9
+    sd = unet_ref.make_state_dict(seed=seed, in_channels=3, variant="W1")
+    m = UNet(in_channels=3, heads=list(unet_ref.V2_HEADS))
+    m.load_state_dict(sd)
+    x = torch.from_numpy(detrand.uniform(77, (B, 3, H, W), 0.0, 1.0).astype(np.float32))       # torch.rand-like
+    out = {}
+    m.eval()
+    with torch.no_grad():
+        for i, y in enumerate(m(x)):
+            out[f"out{i}"] = y.numpy()
+    m.train()
+    for om in m.out_modules:
+        om.drop.p = 0.0
+    with torch.no_grad():
+        for i, y in enumerate(m(x)):
+            out[f"train_out{i}"] = y.numpy()
+    np.savez_compressed(os.path.join(HERE, "unet_rgb.npz"), **out)
+    print("3-channel unet golden written")
+
+
 # ----------------------------------------------------------------------------- decode
 class _FakeChem:
     @staticmethod
@@ -284,10 +308,12 @@ def golden_targets():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["unet", "decode", "loss", "targets"]
+    which = sys.argv[1:] or ["unet", "unet_rgb", "decode", "loss", "targets"]
     torch.set_num_threads(os.cpu_count() or 1)
     if "unet" in which:
         golden_unet()
+    if "unet_rgb" in which:
+        golden_unet_rgb()
     if "decode" in which:
         golden_decode()
     if "loss" in which:

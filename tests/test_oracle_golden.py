@@ -32,6 +32,21 @@ def test_unet_oracle_matches_reference(golden_dir, tag, B, H, W, seed):
         np.testing.assert_allclose(t.numpy(), g[f"{tag}_train_out{i}"], rtol=1e-4, atol=1e-4)
 
 
+def test_unet_oracle_matches_reference_three_channels(golden_dir):
+    """UNet(in_channels=3) on real-valued input (the reference's own self-check configuration, unet.py:122-134): the oracle against
+    logits of the reference module itself (tests/golden/make_golden.py unet_rgb)."""
+    g = np.load(os.path.join(golden_dir, "unet_rgb.npz"))
+    sd = unet_ref.make_state_dict(seed=9, in_channels=3, variant="W1")
+    x = torch.from_numpy(synth.detrand.uniform(77, (1, 3, 96, 64), 0.0, 1.0).astype(np.float32))
+    with torch.no_grad():
+        ys = unet_ref.forward(x, sd)
+        yt = unet_ref.forward(x, sd, training=True)
+    assert [tuple(y.shape) for y in ys] == [(1, h, 24, 16) for h in unet_ref.V2_HEADS]
+    for i, (y, t) in enumerate(zip(ys, yt)):
+        np.testing.assert_allclose(y.numpy(), g[f"out{i}"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(t.numpy(), g[f"train_out{i}"], rtol=1e-4, atol=1e-4)
+
+
 def test_unet_crop_side_is_first_row_col():
     """unet.py:51-55 under torch 2.x drops the FIRST row/column."""
     sd = unet_ref.make_state_dict(seed=4)
