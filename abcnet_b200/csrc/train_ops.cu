@@ -655,7 +655,7 @@ static int p8_check(const void* ptr, int planes, int plane_off, int cplanes, con
 // thread streams several vectors and the per-block atomics stay negligible
 static int plane_grid_x(long long items, int planes, int N, int per_thread = 1) {
   long long need = (items + 256ll * per_thread - 1) / (256ll * per_thread);
-  static const long long per_sm = [] { const char* e = getenv("ABCNET_BN_BLOCKS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 16; }();
+  static const long long per_sm = [] { const char* e = getenv("ABCNET_BN_BLOCKS_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 12; }();
   long long cap = (148ll * per_sm + static_cast<long long>(planes) * N - 1) / (static_cast<long long>(planes) * N);
   if (cap < 1) cap = 1;
   if (need > cap) need = cap;
